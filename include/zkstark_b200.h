@@ -1,0 +1,132 @@
+/*
+ * zkstark_b200.h -- C ABI of libzkstark_b200.so: the B200 (sm_100a) hot path of the STARK-101
+ * FibonacciSq prover in Crocodoctopus/zkstark, as a drop-in for the Rust crate's
+ * field / polynomial / merkle / prover entry points (file:line below are the reference
+ * interfaces each export replaces; INTEGRATION.md shows the Rust `extern "C"` side).
+ *
+ * Conventions
+ *  - field elements cross as canonical u32 residues mod p = 3221225473 (field.rs:41-43), never
+ *    Montgomery form; raw Fiat-Shamir words (alpha/beta) cross un-reduced (channel.rs:28-32)
+ *    and are reduced inside, as F::from(u32) does (field.rs:20-24);
+ *  - digests cross as the 32 raw bytes sha2 emits (merkle.rs:9);
+ *  - the caller owns every buffer; `zk_ctx` owns device memory, tables and one CUDA stream;
+ *  - every call returns 0 on success or a negative zk_status; nothing unwinds across the
+ *    boundary (the reference panics: the Rust shim turns non-zero into panic!);
+ *  - a ctx is not thread-safe: one ctx per (thread, GPU).  Host-buffer calls are synchronous on
+ *    return; `_dev` calls take device pointers, enqueue on the ctx stream and do not synchronize;
+ *  - there is no CPU fallback: without a CUDA device zk_ctx_create fails with ZK_ERR_CUDA.
+ */
+#ifndef ZKSTARK_B200_H
+#define ZKSTARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZK_MODULUS 3221225473u /* main.rs:13 */
+#define ZK_LOG_BLOWUP 3u       /* prover.rs:56-57 (8192 / 1024) */
+#define ZK_MIN_LOG_N 3u
+#define ZK_MAX_LOG_N 27u
+
+typedef struct zk_ctx zk_ctx;
+
+typedef enum zk_status {
+    ZK_OK = 0,
+    ZK_ERR_INVALID = -1, /* bad argument (size not a power of two, log_n out of range, null) */
+    ZK_ERR_CUDA = -2,    /* CUDA runtime error, see zk_last_error */
+    ZK_ERR_NOMEM = -3,   /* device or host allocation failed */
+    ZK_ERR_BUFFER = -4,  /* caller buffer too small */
+    ZK_ERR_ASSERT = -5   /* an inline assert of the reference failed (e.g. prover.rs:42) */
+} zk_status;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int zk_ctx_create(int device, zk_ctx **out);
+/* enqueue on an existing CUDA stream (cudaStream_t) instead of a private one, e.g. torch's */
+int zk_ctx_create_on_stream(int device, void *cuda_stream, zk_ctx **out);
+void zk_ctx_destroy(zk_ctx *ctx);
+const char *zk_last_error(const zk_ctx *ctx);
+const char *zk_version(void);
+int zk_ctx_synchronize(zk_ctx *ctx);
+/* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
+uint64_t zk_ctx_launch_count(const zk_ctx *ctx);
+/* device-side time of the last zk_prove_* call in ms, by stage:
+ * [0] interpolate [1] lde [2] f tree [3] cp+tree [4] fri folds+trees [5] decommit [6] total */
+int zk_ctx_last_stage_ms(zk_ctx *ctx, float out_ms[7]);
+/* enable per-stage CUDA-event timing inside zk_prove_* (off by default: events cost launches) */
+int zk_ctx_set_stage_timing(zk_ctx *ctx, int on);
+
+/* ---- polynomial.rs ---------------------------------------------------------------------- */
+/* lagrange::<F>(&points) for points (g^i, y_i), g = 5^((p-1)/2^log_n)   (polynomial.rs:337,
+ * called at prover.rs:60-61).  n_points is 2^log_n - 1 (the reference: zip truncates to the
+ * 1023 trace values) or 2^log_n.  coeffs_out: 2^log_n ascending coefficients (Polynomial.0). */
+int zk_interpolate_subgroup(zk_ctx *ctx, const uint32_t *y, uint32_t n_points, uint32_t log_n,
+                            uint32_t *coeffs_out);
+/* f_poly.solve(shift * h^i) for i < 2^(log_n+log_blowup), h = 5^((p-1)/N), natural order
+ * (polynomial.rs:49-56 mapped over f_domain, prover.rs:69-70).  log_blowup must be 3. */
+int zk_lde_coset(zk_ctx *ctx, const uint32_t *coeffs, uint32_t log_n, uint32_t log_blowup,
+                 uint32_t shift, uint32_t *evals_out);
+/* fri(poly, beta) followed by evaluation on the squared half domain (polynomial.rs:385-400,
+ * prover.rs:200-211), in evaluation form.  cur: `len` values of layer `layer_k` on the domain
+ * (5 h^i)^(2^layer_k), h of order len << layer_k.  next_out: len/2 values. */
+int zk_fri_fold(zk_ctx *ctx, const uint32_t *cur, uint64_t len, uint32_t layer_k, uint32_t beta_raw,
+                uint32_t *next_out);
+
+/* ---- prover.rs:101-173 ------------------------------------------------------------------ */
+/* The three FibonacciSq constraints combined with alpha0..2, evaluated on the LDE domain.
+ * a_first = a[0], a_last = a[n-2] (the public inputs, prover.rs:33,42). */
+int zk_cp_eval_fibsq(zk_ctx *ctx, const uint32_t *f_eval, uint32_t log_n, uint32_t log_blowup,
+                     const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last, uint32_t *cp_out);
+
+/* ---- merkle.rs -------------------------------------------------------------------------- */
+/* Merkle::new(size, leaves)  (merkle.rs:14-51).  heap_out: 32*(2*size-1) bytes, root first,
+ * children of i at 2i+1 / 2i+2, leaves at [size-1, 2*size-1).  size: power of two, 1..2^30. */
+int zk_merkle_build(zk_ctx *ctx, const uint32_t *leaves, uint64_t size, uint8_t *heap_out);
+/* only the root (merkle[0], prover.rs:82): skips the device->host copy of the heap */
+int zk_merkle_root(zk_ctx *ctx, const uint32_t *leaves, uint64_t size, uint8_t root_out[32]);
+/* Merkle::trace(i) on a heap held by the caller (merkle.rs:54-71); host-side, returns path length */
+int zk_merkle_trace(const uint8_t *heap, uint64_t size, uint64_t index, uint8_t *path_out);
+
+/* ---- prover.rs:9-293 -------------------------------------------------------------------- */
+size_t zk_transcript_len(uint32_t log_n);
+/* generate_proof(Channel::new()) generalised to n = 2^log_n (the reference is log_n = 10,
+ * secret = 3141592).  transcript_out receives Proof.data (channel.rs:8,34-36), state_out
+ * Proof.state.  The trace is generated on the host (prover.rs:32-39 is sequential). */
+int zk_prove_fibsq(zk_ctx *ctx, uint32_t log_n, uint32_t secret, uint8_t *transcript_out, size_t cap,
+                   size_t *len_out, uint8_t state_out[32]);
+/* same, from a caller-provided host trace of 2^log_n - 1 values (H2D copy is part of the call) */
+int zk_prove_fibsq_from_trace(zk_ctx *ctx, uint32_t log_n, const uint32_t *trace, uint8_t *transcript_out,
+                              size_t cap, size_t *len_out, uint8_t state_out[32]);
+/* n_proofs independent proofs of the same size; traces are n_proofs rows of 2^log_n - 1 values,
+ * transcripts_out n_proofs rows of zk_transcript_len(log_n) bytes, states_out rows of 32 bytes.
+ * Internally processed in device-resident sub-batches sized to the ctx memory budget. */
+int zk_prove_fibsq_batch(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t *traces,
+                         uint8_t *transcripts_out, uint8_t *states_out);
+/* prover.rs:32-39: a[0] = 1, a[1] = secret, a[i] = a[i-2]^2 + a[i-1]^2; 2^log_n - 1 values (host) */
+int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t *trace_out);
+/* cap on device bytes a ctx may hold for proving work space (default: 70% of free memory) */
+int zk_ctx_set_memory_budget(zk_ctx *ctx, size_t bytes);
+
+/* ---- device-pointer variants (no host copies, no synchronize; pointers are CUDA device memory,
+ * 16-byte aligned).  Used by bench.py for HBM-resident timing and by multi-GPU drivers. ------ */
+int zk_interpolate_subgroup_dev(zk_ctx *ctx, uint32_t *y_inout_n, uint32_t n_points, uint32_t log_n,
+                                uint32_t *coeffs_out);
+int zk_lde_coset_dev(zk_ctx *ctx, const uint32_t *coeffs, uint32_t log_n, uint32_t log_blowup,
+                     uint32_t shift, uint32_t *evals_out);
+int zk_fri_fold_dev(zk_ctx *ctx, const uint32_t *cur, uint64_t len, uint32_t layer_k, uint32_t beta_raw,
+                    uint32_t *next_out);
+int zk_cp_eval_fibsq_dev(zk_ctx *ctx, const uint32_t *f_eval, uint32_t log_n, uint32_t log_blowup,
+                         const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last, uint32_t *cp_out);
+int zk_merkle_build_dev(zk_ctx *ctx, const uint32_t *leaves, uint64_t size, uint8_t *heap_out);
+/* whole prove() with the traces already resident: traces_dev is n_proofs rows of 2^log_n words
+ * (word n-1 of each row is scratch); transcripts/states are HOST buffers filled after one
+ * synchronize.  This is the region bench.py times for `value`. */
+int zk_prove_fibsq_resident(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t *traces_dev,
+                            uint8_t *transcripts_out, uint8_t *states_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,81 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/zkstark_b200.h
+declares, and its host-only entry points agree with the oracle.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import zkstark_b200 as zk
+
+
+def test_library_built_in_tree():
+    assert os.path.exists(zk.LIB_PATH), "run __graft_entry__.build() first"
+    assert os.path.dirname(zk.LIB_PATH).endswith("zkstark_b200")
+
+
+def test_header_symbols_all_exported():
+    declared = zk.header_symbols()
+    exported = set(zk.exported_symbols())
+    assert len(declared) >= 25
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    L = zk.lib()
+    for s in declared:
+        assert hasattr(L, s)
+
+
+def test_version_string():
+    assert b"sm_100a" in zk.lib().zk_version()
+
+
+def test_transcript_len_matches_oracle(orc):
+    assert zk.transcript_len(10) == 7836  # Proof::size() 7884 - 48 (proof.rs:151-154)
+    for k in range(3, 28):
+        assert zk.transcript_len(k) == orc.lib().orc_transcript_len(k)
+
+
+def test_trace_matches_oracle_and_kat(orc, kats):
+    a = zk.trace_fibsq(10, 3141592)
+    assert int(a[1022]) == kats["prover"]["a_1022"]  # prover.rs:42
+    for k, secret in [(3, 1), (4, 0), (7, 3141592), (12, 0xFFFFFFFF), (14, 3221225473 + 5)]:
+        assert np.array_equal(zk.trace_fibsq(k, secret), orc.trace_fibsq(k, secret))
+
+
+def test_merkle_trace_host_matches_reference_kat(orc, kats):
+    k = kats["merkle_test"]
+    heap = np.array([list(bytes.fromhex(h)) for h in k["heap"]], dtype=np.uint8)
+    for leaf, sibs in k["traces"].items():
+        got = zk.merkle_trace_host(heap, int(leaf))
+        assert [bytes(g).hex() for g in got] == [k["heap"][s] for s in sibs]
+    big = orc.merkle_build(np.arange(64, dtype=np.uint32))
+    for i in (0, 1, 31, 63):
+        assert np.array_equal(zk.merkle_trace_host(big, i), orc.merkle_trace(big, i))
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU, creating a context must fail loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(zk.ZkError):
+        zk.Context(0)
+
+
+def test_invalid_arguments_do_not_crash():
+    L = zk.lib()
+    assert L.zk_trace_fibsq(0, 1, None) < 0
+    assert L.zk_merkle_trace(None, 4, 0, None) < 0
+    assert L.zk_ctx_synchronize(None) < 0
+    assert L.zk_ctx_launch_count(None) == 0
+    L.zk_ctx_destroy(None)
+
+
+def test_product_does_not_import_oracle():
+    """The shipped package must never route through oracle/ (tier rule 3)."""
+    root = os.path.dirname(zk.LIB_PATH)
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "import oracle" not in txt and "liboracle" not in txt and "orc_" not in txt, f

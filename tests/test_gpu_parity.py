@@ -1,0 +1,240 @@
+"""GPU parity tests (-m gpu): every C-ABI entry point against the oracle on the same inputs,
+bit-exact, plus the reference's known-answer values through the CUDA path."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import zkstark_b200 as zk
+
+pytestmark = pytest.mark.gpu
+P = 3221225473
+
+
+def rnd(n, seed):
+    return np.random.default_rng(seed).integers(0, P, size=n, dtype=np.uint64).astype(np.uint32)
+
+
+def edge_values(n, seed):
+    v = rnd(n, seed)
+    edges = [0, 1, 2, P - 1, P - 2, 1 << 31, (1 << 31) - 1, (1 << 31) + 1, P // 2, 5]
+    v[: min(n, len(edges))] = edges[: min(n, len(edges))]
+    return v
+
+
+# ---------------------------------------------------------------- K5 Merkle
+def test_merkle_reference_kat(ctx, kats):  # merkle.rs:112-182 through the CUDA kernels
+    k = kats["merkle_test"]
+    m = zk.Merkle.new(4, np.array(k["leaves"], dtype=np.uint32), ctx=ctx)
+    assert [m[i].hex() for i in range(7)] == k["heap"]
+    for leaf, sibs in k["traces"].items():
+        assert [t.hex() for t in m.trace(int(leaf))] == [k["heap"][s] for s in sibs]
+
+
+@pytest.mark.parametrize("log_size", [0, 1, 2, 3, 5, 9, 10, 11, 12, 13, 14, 16, 19])
+def test_merkle_random_vs_oracle(ctx, orc, log_size):
+    leaves = edge_values(1 << log_size, 100 + log_size)
+    got = ctx.merkle_build(leaves)
+    want = orc.merkle_build(leaves, threads=orc.default_threads())
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert ctx.merkle_root(leaves) == want[0].tobytes()
+
+
+def test_merkle_rejects_bad_size(ctx):
+    with pytest.raises(zk.ZkError):
+        ctx.merkle_build(np.zeros(3, dtype=np.uint32))  # merkle.rs:17-21 assert
+    with pytest.raises(zk.ZkError):
+        zk.Merkle.new(8, np.zeros(4, dtype=np.uint32), ctx=ctx)
+
+
+def test_merkle_full_size_properties(ctx, orc):
+    """2^23 leaves (the 2^20-trace LDE): root equals the oracle's; every auth path of a few leaves
+    recomputes to the root (merkle.rs:82-110)."""
+    n = 1 << 23
+    leaves = rnd(n, 7)
+    heap = ctx.merkle_build(leaves)
+    want_root = orc.merkle_build(leaves, threads=orc.default_threads())[0].tobytes()
+    assert heap[0].tobytes() == want_root
+    for i in (0, 1, n // 3, n - 1):
+        path = zk.merkle_trace_host(heap, i)
+        assert len(path) == 23
+        assert orc.root_from_path(int(leaves[i]), i, path).tobytes() == want_root
+
+
+# ---------------------------------------------------------------- K2 interpolation + LDE
+@pytest.mark.parametrize("log_n", [3, 4, 5, 8, 10, 11, 12, 13, 16, 20])
+def test_interpolate_phantom_vs_oracle(ctx, orc, log_n):
+    y = edge_values((1 << log_n) - 1, 200 + log_n)
+    got = ctx.interpolate_subgroup(y, log_n)
+    want = orc.interpolate_subgroup(y, log_n, threads=orc.default_threads())
+    assert np.array_equal(got, want)
+    assert got[-1] == 0  # degree <= n-2 (prover.rs:154 implies it)
+
+
+@pytest.mark.parametrize("log_n", [3, 6, 10, 11, 15])
+def test_interpolate_full_vs_oracle(ctx, orc, log_n):
+    y = edge_values(1 << log_n, 300 + log_n)
+    assert np.array_equal(ctx.interpolate_subgroup(y, log_n), orc.interpolate_subgroup(y, log_n))
+
+
+@pytest.mark.parametrize("log_n", [3, 4, 7, 10, 11, 12, 13, 16, 20])
+def test_lde_vs_oracle(ctx, orc, log_n):
+    c = edge_values(1 << log_n, 400 + log_n)
+    got = ctx.lde_coset(c, log_n)
+    want = orc.lde_coset(c, log_n, threads=orc.default_threads())
+    assert np.array_equal(got, want)
+
+
+def test_lde_other_shift(ctx, orc):
+    c = rnd(1 << 9, 11)
+    assert np.array_equal(ctx.lde_coset(c, 9, shift=7), orc.lde_coset(c, 9, shift=7))
+    assert np.array_equal(ctx.lde_coset(c, 9, shift=1), orc.lde_coset(c, 9, shift=1))
+
+
+def test_lde_reference_kat(ctx, kats):  # prover.rs:42,73-78 through the CUDA kernels
+    k = kats["prover"]
+    a = zk.trace_fibsq(10, k["secret"])
+    f = ctx.lde_coset(ctx.interpolate_subgroup(a, 10), 10)
+    for idx, v in k["f_eval"].items():
+        assert int(f[int(idx)]) == v
+
+
+def test_lde_linearity_full_size(ctx):
+    """size-independent property at 2^20: LDE(a + b) = LDE(a) + LDE(b) mod p."""
+    n = 1 << 20
+    a, b = rnd(n, 1), rnd(n, 2)
+    s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+    la, lb, ls = ctx.lde_coset(a, 20), ctx.lde_coset(b, 20), ctx.lde_coset(s, 20)
+    assert np.array_equal(((la.astype(np.uint64) + lb) % P).astype(np.uint32), ls)
+
+
+def test_interpolate_then_lde_hits_trace(ctx):
+    """f(g^i) = a[i] (prover.rs:64-66): LDE with shift 1 passes through the subgroup at stride 8."""
+    log_n = 12
+    a = zk.trace_fibsq(log_n, 99)
+    c = ctx.interpolate_subgroup(a, log_n)
+    ev = ctx.lde_coset(c, log_n, shift=1)
+    assert np.array_equal(ev[::8][:-1], a)
+
+
+# ---------------------------------------------------------------- K3 composition polynomial
+@pytest.mark.parametrize("log_n", [3, 4, 8, 10, 13, 16])
+def test_cp_vs_oracle(ctx, orc, log_n):
+    f = edge_values(8 << log_n, 500 + log_n)
+    alpha = [361545003, 3235878091, 0xFFFFFFFF]  # raw challenges >= p occur
+    got = ctx.cp_eval_fibsq(f, log_n, alpha, 1, 2338775057)
+    want = orc.cp_eval_fibsq(f, log_n, alpha, 1, 2338775057, threads=orc.default_threads())
+    assert np.array_equal(got, want)
+
+
+def test_cp_reference_values(ctx, transcripts):  # derived goldens for the canonical run
+    g = transcripts["10"]
+    a = zk.trace_fibsq(10, 3141592)
+    f = ctx.lde_coset(ctx.interpolate_subgroup(a, 10), 10)
+    cp = ctx.cp_eval_fibsq(f, 10, g["alpha_raw"], 1, int(a[1022]))
+    for idx, v in g["cp_eval"].items():
+        assert int(cp[int(idx)]) == v
+
+
+# ---------------------------------------------------------------- K4 FRI fold
+@pytest.mark.parametrize("log_len,layer_k", [(1, 0), (2, 3), (3, 9), (4, 0), (10, 2), (13, 0), (13, 7), (20, 1)])
+def test_fold_vs_oracle(ctx, orc, log_len, layer_k):
+    cur = edge_values(1 << log_len, 600 + log_len)
+    for beta in (3, 4195595581):
+        got = ctx.fri_fold(cur, layer_k, beta)
+        want = orc.fri_fold(cur, layer_k, beta, threads=orc.default_threads())
+        assert np.array_equal(got, want)
+
+
+def test_fold_is_coefficient_fold(ctx, orc):
+    """fri_test's identity (polynomial.rs:419-425) on arrays: fold of evaluations ==
+    evaluations of fri(poly, beta) on the squared half domain."""
+    log_n, beta = 7, 123456789
+    c = rnd(1 << log_n, 5)
+    ev = ctx.lde_coset(c, log_n)
+    c2 = np.zeros(len(c) // 2, dtype=np.uint32)
+    orc.lib().orc_fri_coeff(c.ctypes.data, len(c), beta, c2.ctypes.data, P)
+    folded = ctx.fri_fold(ev, 0, beta)
+    # evaluations of c2 (degree < n/2) on {(5 h^i)^2}: an LDE of c2 with shift 25 over the order-N/2 group
+    want = orc.lde_coset(np.concatenate([c2]), log_n - 1, shift=25)
+    assert np.array_equal(folded, want)
+
+
+# ---------------------------------------------------------------- prove(): bit-exact transcripts
+@pytest.mark.parametrize("log_n", [4, 5, 6, 8, 10, 12, 16])
+def test_prove_matches_goldens(ctx, transcripts, log_n):
+    g = transcripts[str(log_n)]
+    tr, st = ctx.prove_fibsq(log_n, 3141592)
+    assert len(tr) == g["len"]
+    assert tr[:32].hex() == g["f_root"]
+    assert tr[44:76].hex() == g["cp_root"]
+    assert hashlib.sha256(tr).hexdigest() == g["sha256"]
+    assert st.hex() == g["state"]
+
+
+@pytest.mark.parametrize("log_n,secret", [(3, 3141592), (7, 1), (9, 0), (11, 42), (13, 3221225473 + 7), (14, 2), (18, 3141592)])
+def test_prove_vs_oracle(ctx, orc, log_n, secret):
+    tr, st = ctx.prove_fibsq(log_n, secret)
+    otr, ost, info = orc.prove_fibsq(log_n, secret)
+    assert tr == otr and st == ost
+    assert orc.verify_fibsq(log_n, info.a_last, tr, True, st) == 0
+
+
+def test_generate_proof_mirror(ctx, transcripts):
+    proof = zk.generate_proof(zk.Channel.new(), ctx=ctx)  # the reference's only config
+    assert proof.size() == 7884  # proof.rs:151-154
+    assert proof.state.hex() == transcripts["10"]["state"]
+    ch = zk.Channel.new()
+    ch.state = b"\x01" * 32
+    with pytest.raises(zk.ZkError):
+        zk.generate_proof(ch, ctx=ctx)
+
+
+def test_prove_full_size(ctx, orc):
+    """BASELINE config 3 (2^20 trace): bit-exact with the oracle, and accepted by the restated verifier."""
+    tr, st = ctx.prove_fibsq(20, 3141592)
+    otr, ost, info = orc.prove_fibsq(20, 3141592)
+    assert hashlib.sha256(tr).hexdigest() == hashlib.sha256(otr).hexdigest()
+    assert st == ost
+    assert orc.verify_fibsq(20, info.a_last, tr, True, st) == 0
+
+
+def test_prove_batch(ctx, orc):
+    """BASELINE config 4 in miniature: independent proofs, secret_j = 3141592 + j."""
+    log_n, nb = 10, 5
+    traces = np.stack([zk.trace_fibsq(log_n, 3141592 + j) for j in range(nb)])
+    trs, sts = ctx.prove_fibsq_batch(log_n, traces)
+    for j in range(nb):
+        otr, ost, _ = orc.prove_fibsq(log_n, 3141592 + j)
+        assert trs[j].tobytes() == otr and sts[j].tobytes() == ost
+
+
+def test_prove_batch_sub_batching(ctx, orc):
+    log_n, nb = 8, 7
+    ctx.set_memory_budget(3 * 1672 * (1 << log_n) + 4096)  # forces sub-batches of <= 3 proofs
+    try:
+        traces = np.stack([zk.trace_fibsq(log_n, 10 + j) for j in range(nb)])
+        trs, sts = ctx.prove_fibsq_batch(log_n, traces)
+    finally:
+        ctx.set_memory_budget(0)
+    for j in range(nb):
+        otr, ost, _ = orc.prove_fibsq(log_n, 10 + j)
+        assert trs[j].tobytes() == otr and sts[j].tobytes() == ost
+
+
+def test_prove_rejects_bad_args(ctx):
+    with pytest.raises(zk.ZkError):
+        ctx.prove_fibsq(2)
+    with pytest.raises(zk.ZkError):
+        ctx.prove_fibsq(28)
+    with pytest.raises(zk.ZkError):
+        ctx.lde_coset(np.zeros(16, dtype=np.uint32), 4, log_blowup=2)
+    with pytest.raises(zk.ZkError):
+        ctx.fri_fold(np.zeros(12, dtype=np.uint32), 0, 1)
+
+
+def test_launch_counter_counts_own_kernels(ctx):
+    before = ctx.launch_count()
+    ctx.prove_fibsq(8)
+    assert ctx.launch_count() - before >= 12

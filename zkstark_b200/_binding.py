@@ -1,0 +1,264 @@
+"""ctypes binding of include/zkstark_b200.h (the C ABI the Rust shim binds)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libzkstark_b200.so")
+HEADER = os.path.join(_ROOT, "include", "zkstark_b200.h")
+
+ZK_OK = 0
+
+
+class ZkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"zkstark_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build_library(force=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> zkstark_b200/libzkstark_b200.so"""
+    csrc = os.path.join(_PKG, "csrc")
+    args = ["make", "-C", csrc, "-j4"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly when it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ZkError(-2, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA extension is the only implementation)")
+    L = C.CDLL(LIB_PATH)
+    u32, u64, i32, vp, sz = C.c_uint32, C.c_uint64, C.c_int, C.c_void_p, C.c_size_t
+    sig = {
+        "zk_ctx_create": ([i32, C.POINTER(vp)], i32),
+        "zk_ctx_create_on_stream": ([i32, vp, C.POINTER(vp)], i32),
+        "zk_ctx_destroy": ([vp], None),
+        "zk_last_error": ([vp], C.c_char_p),
+        "zk_version": ([], C.c_char_p),
+        "zk_ctx_synchronize": ([vp], i32),
+        "zk_ctx_launch_count": ([vp], u64),
+        "zk_ctx_last_stage_ms": ([vp, vp], i32),
+        "zk_ctx_set_stage_timing": ([vp, i32], i32),
+        "zk_ctx_set_memory_budget": ([vp, sz], i32),
+        "zk_interpolate_subgroup": ([vp, vp, u32, u32, vp], i32),
+        "zk_lde_coset": ([vp, vp, u32, u32, u32, vp], i32),
+        "zk_fri_fold": ([vp, vp, u64, u32, u32, vp], i32),
+        "zk_cp_eval_fibsq": ([vp, vp, u32, u32, vp, u32, u32, vp], i32),
+        "zk_merkle_build": ([vp, vp, u64, vp], i32),
+        "zk_merkle_root": ([vp, vp, u64, vp], i32),
+        "zk_merkle_trace": ([vp, u64, u64, vp], i32),
+        "zk_transcript_len": ([u32], sz),
+        "zk_prove_fibsq": ([vp, u32, u32, vp, sz, C.POINTER(sz), vp], i32),
+        "zk_prove_fibsq_from_trace": ([vp, u32, vp, vp, sz, C.POINTER(sz), vp], i32),
+        "zk_prove_fibsq_batch": ([vp, u32, u32, vp, vp, vp], i32),
+        "zk_trace_fibsq": ([u32, u32, vp], i32),
+        "zk_interpolate_subgroup_dev": ([vp, vp, u32, u32, vp], i32),
+        "zk_lde_coset_dev": ([vp, vp, u32, u32, u32, vp], i32),
+        "zk_fri_fold_dev": ([vp, vp, u64, u32, u32, vp], i32),
+        "zk_cp_eval_fibsq_dev": ([vp, vp, u32, u32, vp, u32, u32, vp], i32),
+        "zk_merkle_build_dev": ([vp, vp, u64, vp], i32),
+        "zk_prove_fibsq_resident": ([vp, u32, u32, vp, vp, vp], i32),
+    }
+    for name, (argt, rest) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argt
+        fn.restype = rest
+    _lib = L
+    return L
+
+
+def header_symbols():
+    """Every function include/zkstark_b200.h declares."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(zk_[a-z0-9_]+)\s*\(", txt)))
+
+
+def exported_symbols():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH], text=True)
+    return sorted(l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("zk_"))
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def transcript_len(log_n):
+    return lib().zk_transcript_len(log_n)
+
+
+def trace_fibsq(log_n, secret=3141592):
+    """prover.rs:32-39 (host, sequential)."""
+    out = np.empty((1 << log_n) - 1, dtype=np.uint32)
+    rc = lib().zk_trace_fibsq(log_n, secret, _p(out))
+    if rc:
+        raise ZkError(rc, "zk_trace_fibsq")
+    return out
+
+
+def merkle_trace_host(heap, index):
+    """merkle.rs:54-71 on a host heap array of shape (2*size-1, 32)."""
+    heap = np.ascontiguousarray(heap, dtype=np.uint8)
+    size = (heap.shape[0] + 1) // 2
+    out = np.empty((64, 32), dtype=np.uint8)
+    n = lib().zk_merkle_trace(_p(heap), size, index, _p(out))
+    if n < 0:
+        raise ZkError(n, "zk_merkle_trace")
+    return out[:n].copy()
+
+
+class Context:
+    """zk_ctx: one per (thread, GPU).  `stream` is a raw cudaStream_t (e.g. torch's current stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        L = lib()
+        rc = (L.zk_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(self._h)) if stream
+              else L.zk_ctx_create(device, C.byref(self._h)))
+        if rc != ZK_OK:
+            self._h = C.c_void_p()
+            raise ZkError(rc, "zk_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().zk_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != ZK_OK:
+            raise ZkError(rc, lib().zk_last_error(self._h).decode())
+
+    # ---- host-buffer entry points
+    def interpolate_subgroup(self, y, log_n):
+        y = _u32(y)
+        out = np.empty(1 << log_n, dtype=np.uint32)
+        self._ck(lib().zk_interpolate_subgroup(self._h, _p(y), len(y), log_n, _p(out)))
+        return out
+
+    def lde_coset(self, coeffs, log_n, log_blowup=3, shift=5):
+        coeffs = _u32(coeffs)
+        assert len(coeffs) == 1 << log_n
+        out = np.empty(1 << (log_n + log_blowup), dtype=np.uint32)
+        self._ck(lib().zk_lde_coset(self._h, _p(coeffs), log_n, log_blowup, shift, _p(out)))
+        return out
+
+    def fri_fold(self, cur, layer_k, beta_raw):
+        cur = _u32(cur)
+        out = np.empty(len(cur) // 2, dtype=np.uint32)
+        self._ck(lib().zk_fri_fold(self._h, _p(cur), len(cur), layer_k, beta_raw, _p(out)))
+        return out
+
+    def cp_eval_fibsq(self, f_eval, log_n, alpha_raw, a_first, a_last, log_blowup=3):
+        f_eval = _u32(f_eval)
+        al = _u32(alpha_raw)
+        out = np.empty_like(f_eval)
+        self._ck(lib().zk_cp_eval_fibsq(self._h, _p(f_eval), log_n, log_blowup, _p(al), a_first, a_last, _p(out)))
+        return out
+
+    def merkle_build(self, leaves):
+        leaves = _u32(leaves)
+        heap = np.empty((2 * len(leaves) - 1, 32), dtype=np.uint8)
+        self._ck(lib().zk_merkle_build(self._h, _p(leaves), len(leaves), _p(heap)))
+        return heap
+
+    def merkle_root(self, leaves):
+        leaves = _u32(leaves)
+        root = np.empty(32, dtype=np.uint8)
+        self._ck(lib().zk_merkle_root(self._h, _p(leaves), len(leaves), _p(root)))
+        return root.tobytes()
+
+    def prove_fibsq(self, log_n, secret=3141592):
+        cap = transcript_len(log_n)
+        tr = np.empty(cap, dtype=np.uint8)
+        st = np.empty(32, dtype=np.uint8)
+        n = C.c_size_t(0)
+        self._ck(lib().zk_prove_fibsq(self._h, log_n, secret, _p(tr), cap, C.byref(n), _p(st)))
+        return tr[: n.value].tobytes(), st.tobytes()
+
+    def prove_fibsq_from_trace(self, log_n, trace):
+        trace = _u32(trace)
+        assert len(trace) == (1 << log_n) - 1
+        cap = transcript_len(log_n)
+        tr = np.empty(cap, dtype=np.uint8)
+        st = np.empty(32, dtype=np.uint8)
+        n = C.c_size_t(0)
+        self._ck(lib().zk_prove_fibsq_from_trace(self._h, log_n, _p(trace), _p(tr), cap, C.byref(n), _p(st)))
+        return tr[: n.value].tobytes(), st.tobytes()
+
+    def prove_fibsq_batch(self, log_n, traces):
+        traces = _u32(traces)
+        assert traces.ndim == 2 and traces.shape[1] == (1 << log_n) - 1
+        nb = traces.shape[0]
+        tl = transcript_len(log_n)
+        tr = np.empty((nb, tl), dtype=np.uint8)
+        st = np.empty((nb, 32), dtype=np.uint8)
+        self._ck(lib().zk_prove_fibsq_batch(self._h, log_n, nb, _p(traces), _p(tr), _p(st)))
+        return tr, st
+
+    # ---- raw-pointer entry points (device memory owned by the caller, e.g. torch tensors)
+    def prove_fibsq_batch_ptr(self, log_n, n_proofs, traces_host_ptr, transcripts_ptr, states_ptr):
+        self._ck(lib().zk_prove_fibsq_batch(self._h, log_n, n_proofs, C.c_void_p(traces_host_ptr),
+                                            C.c_void_p(transcripts_ptr), C.c_void_p(states_ptr)))
+
+    def prove_fibsq_resident_ptr(self, log_n, n_proofs, traces_dev_ptr, transcripts_ptr, states_ptr):
+        self._ck(lib().zk_prove_fibsq_resident(self._h, log_n, n_proofs, C.c_void_p(traces_dev_ptr),
+                                               C.c_void_p(transcripts_ptr), C.c_void_p(states_ptr)))
+
+    def interpolate_subgroup_dev(self, y_ptr, n_points, log_n, coeffs_ptr):
+        self._ck(lib().zk_interpolate_subgroup_dev(self._h, C.c_void_p(y_ptr), n_points, log_n, C.c_void_p(coeffs_ptr)))
+
+    def lde_coset_dev(self, coeffs_ptr, log_n, evals_ptr, log_blowup=3, shift=5):
+        self._ck(lib().zk_lde_coset_dev(self._h, C.c_void_p(coeffs_ptr), log_n, log_blowup, shift, C.c_void_p(evals_ptr)))
+
+    def fri_fold_dev(self, cur_ptr, length, layer_k, beta_raw, next_ptr):
+        self._ck(lib().zk_fri_fold_dev(self._h, C.c_void_p(cur_ptr), length, layer_k, beta_raw, C.c_void_p(next_ptr)))
+
+    def cp_eval_fibsq_dev(self, f_ptr, log_n, alpha_raw, a_first, a_last, cp_ptr, log_blowup=3):
+        al = _u32(alpha_raw)
+        self._ck(lib().zk_cp_eval_fibsq_dev(self._h, C.c_void_p(f_ptr), log_n, log_blowup, _p(al), a_first, a_last,
+                                            C.c_void_p(cp_ptr)))
+
+    def merkle_build_dev(self, leaves_ptr, size, heap_ptr):
+        self._ck(lib().zk_merkle_build_dev(self._h, C.c_void_p(leaves_ptr), size, C.c_void_p(heap_ptr)))
+
+    def synchronize(self):
+        self._ck(lib().zk_ctx_synchronize(self._h))
+
+    def launch_count(self):
+        return lib().zk_ctx_launch_count(self._h)
+
+    def set_stage_timing(self, on=True):
+        self._ck(lib().zk_ctx_set_stage_timing(self._h, int(on)))
+
+    def last_stage_ms(self):
+        arr = (C.c_float * 7)()
+        self._ck(lib().zk_ctx_last_stage_ms(self._h, arr))
+        names = ["interpolate", "lde", "f_tree", "cp_tree", "fri", "decommit", "total"]
+        return dict(zip(names, [float(x) for x in arr]))
+
+    def set_memory_budget(self, nbytes):
+        self._ck(lib().zk_ctx_set_memory_budget(self._h, nbytes))

@@ -1,0 +1,758 @@
+// C ABI (include/zkstark_b200.h): context, constant tables, work space, the device-resident
+// prove() pipeline (prover.rs:9-293) and the per-function entry points.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zkstark_b200.h"
+#include "common.cuh"
+#include "sha256.cuh"
+
+namespace zk {
+cudaError_t launch_interpolate(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow,
+                               PowTab wpow, uint32_t log_n, bool phantom, uint32_t* y, uint64_t y_stride,
+                               uint32_t* coeffs, uint64_t coeffs_stride, uint32_t batch, int* n_launches);
+cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
+                       uint32_t log_n, const uint32_t* coeffs, uint64_t coeffs_stride, uint32_t* work,
+                       uint64_t work_stride, uint32_t* evals, uint64_t evals_stride, uint32_t batch,
+                       int* n_launches);
+}  // namespace zk
+
+using namespace zk;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct PowTabOwned {
+    uint32_t* lo = nullptr;
+    uint32_t* hi = nullptr;
+    PowTab tab{};
+};
+
+struct SizeTables {
+    PowTabOwned h;  // powers of h = 5^((p-1)/N)
+    PowTabOwned w;  // powers of 5
+};
+
+}  // namespace
+
+struct zk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+    uint32_t* tw_fwd = nullptr;
+    uint32_t* tw_inv = nullptr;
+    std::map<uint32_t, SizeTables> tabs;  // by log_N
+    DevBuf s0, s1, s2;                    // scratch for the host-buffer stage calls
+    // prove work space
+    uint32_t w_log_n = 0, w_batch = 0;
+    DevBuf traces, coeffs, work, f_eval, layers, f_heap, layer_heaps, states, transcripts;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    size_t mem_budget = 0;
+    bool stage_timing = false;
+    float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int fail(zk_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+int fail_cuda(zk_ctx* c, cudaError_t e, const char* what)
+{
+    cudaGetLastError();
+    return fail(c, e == cudaErrorMemoryAllocation ? ZK_ERR_NOMEM : ZK_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);   \
+    } while (0)
+
+cudaError_t build_powtab(PowTabOwned& t, uint32_t base, uint32_t log_E /* exponents < 2^log_E */, uint32_t log_N_tag)
+{
+    uint32_t lo_bits = (log_E + 1) / 2, hi_bits = log_E - lo_bits;
+    std::vector<uint32_t> lo((size_t)1 << lo_bits), hi((size_t)1 << hi_bits);
+    uint32_t c = 1;
+    for (size_t i = 0; i < lo.size(); i++) { lo[i] = h_to_mont(c); c = h_mul(c, base); }
+    uint32_t step = c;  // base^(2^lo_bits)
+    c = 1;
+    for (size_t i = 0; i < hi.size(); i++) { hi[i] = h_to_mont(c); c = h_mul(c, step); }
+    cudaError_t e;
+    if ((e = cudaMalloc(&t.lo, lo.size() * 4)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t.hi, hi.size() * 4)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    t.tab.lo = t.lo;
+    t.tab.hi = t.hi;
+    t.tab.lo_bits = lo_bits;
+    t.tab.log_N = log_N_tag;
+    return cudaSuccess;
+}
+void free_powtab(PowTabOwned& t)
+{
+    if (t.lo) cudaFree(t.lo);
+    if (t.hi) cudaFree(t.hi);
+    t = PowTabOwned{};
+}
+
+int get_tables(zk_ctx* ctx, uint32_t log_N, SizeTables** out)
+{
+    auto it = ctx->tabs.find(log_N);
+    if (it == ctx->tabs.end()) {
+        SizeTables st;
+        CK(build_powtab(st.h, h_root(log_N), log_N, log_N));
+        CK(build_powtab(st.w, GEN, log_N, log_N));
+        it = ctx->tabs.emplace(log_N, st).first;
+    }
+    *out = &it->second;
+    return ZK_OK;
+}
+
+int init_tw(zk_ctx* ctx)
+{
+    // radix tables: for R = 2^m (m = 1..10) the R/2 powers of w_R at offset 2^(m-1)-1
+    std::vector<uint32_t> f(1023), inv(1023);
+    for (uint32_t m = 1; m <= 10; m++) {
+        uint32_t w = h_root(m), wi = h_inv(w), c = 1, ci = 1;
+        size_t off = ((size_t)1 << (m - 1)) - 1;
+        for (uint32_t j = 0; j < (1u << (m - 1)); j++) {
+            f[off + j] = h_to_mont(c);
+            inv[off + j] = h_to_mont(ci);
+            c = h_mul(c, w);
+            ci = h_mul(ci, wi);
+        }
+    }
+    CK(cudaMalloc(&ctx->tw_fwd, 1023 * 4));
+    CK(cudaMalloc(&ctx->tw_inv, 1023 * 4));
+    CK(cudaMemcpy(ctx->tw_fwd, f.data(), 1023 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->tw_inv, inv.data(), 1023 * 4, cudaMemcpyHostToDevice));
+    return ZK_OK;
+}
+
+bool is_pow2(uint64_t v) { return v && !(v & (v - 1)); }
+uint32_t ilog2(uint64_t v)
+{
+    uint32_t l = 0;
+    while (((uint64_t)1 << (l + 1)) <= v) l++;
+    return l;
+}
+
+FoldArgs make_fold_args(uint32_t layer_k)
+{
+    FoldArgs f{};
+    f.layer_k = layer_k;
+    f.winv2k_m = h_to_mont(h_inv(h_pow(GEN, (uint64_t)1 << layer_k)));
+    f.inv2_m = h_to_mont(h_inv(2));
+    return f;
+}
+
+CpArgs make_cp_args(uint32_t log_n)
+{
+    CpArgs c{};
+    const uint32_t log_N = log_n + LOG_BLOWUP;
+    const uint64_t n = (uint64_t)1 << log_n;
+    const uint32_t g = h_root(log_n), h = h_root(log_N);
+    c.log_n = log_n;
+    c.g1 = h_pow(g, n - 1);
+    c.g2 = h_pow(g, n - 2);
+    c.g3 = h_pow(g, n - 3);
+    const uint32_t wn = h_pow(GEN, n), hn = h_pow(h, n);
+    uint32_t xn = wn;
+    for (int i = 0; i < 8; i++) {
+        c.zinv_m[i] = h_to_mont(h_inv((uint32_t)(((uint64_t)xn + P - 1) % P)));
+        xn = h_mul(xn, hn);
+    }
+    return c;
+}
+
+struct StageTimer {
+    zk_ctx* ctx;
+    int idx = 0;
+    explicit StageTimer(zk_ctx* c) : ctx(c) {}
+    void mark()
+    {
+        if (ctx->stage_timing && idx < 8) cudaEventRecord(ctx->ev[idx], ctx->stream);
+        idx++;
+    }
+};
+
+size_t per_proof_bytes(uint32_t log_n)
+{
+    const size_t n = (size_t)1 << log_n, N = n << LOG_BLOWUP;
+    return 4 * (2 * n + 4 * N) + 64 * N + 128 * N + sizeof(ProofState) + ((transcript_len(log_n) + 63) & ~(size_t)63);
+}
+
+int ensure_workspace(zk_ctx* ctx, uint32_t log_n, uint32_t batch)
+{
+    const size_t n = (size_t)1 << log_n, N = n << LOG_BLOWUP;
+    const size_t trs = (transcript_len(log_n) + 63) & ~(size_t)63;
+    CK(ctx->traces.ensure(4 * n * batch));
+    CK(ctx->coeffs.ensure(4 * n * batch));
+    CK(ctx->work.ensure(4 * N * batch));
+    CK(ctx->f_eval.ensure(4 * N * batch));
+    CK(ctx->layers.ensure(4 * 2 * N * batch));
+    CK(ctx->f_heap.ensure(64 * N * batch));
+    CK(ctx->layer_heaps.ensure(128 * N * batch));
+    CK(ctx->states.ensure(sizeof(ProofState) * (size_t)batch));
+    CK(ctx->transcripts.ensure(trs * batch));
+    size_t pin = (trs + sizeof(ProofState)) * batch;
+    if (pin > ctx->pinned_bytes) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        CK(cudaMallocHost(&ctx->pinned, pin));
+        ctx->pinned_bytes = pin;
+    }
+    ctx->w_log_n = log_n;
+    ctx->w_batch = batch;
+    return ZK_OK;
+}
+
+// channel.rs:19-26 over the decommitment records (prover.rs:274-288), on the host.
+void finish_channel_host(uint32_t log_n, const ProofState& ps, const uint8_t* tr, uint8_t state_out[32])
+{
+    const uint32_t L = log_n, log_N = log_n + LOG_BLOWUP;
+    uint8_t buf[32 + 24 + 64 * 32];
+    for (int i = 0; i < 8; i++) {
+        uint32_t w = ps.chan_at_query[i];
+        buf[4 * i] = (uint8_t)(w >> 24); buf[4 * i + 1] = (uint8_t)(w >> 16);
+        buf[4 * i + 2] = (uint8_t)(w >> 8); buf[4 * i + 3] = (uint8_t)w;
+    }
+    size_t off = tr_off_decommit(L);
+    for (uint32_t r = 0; r < 4 + L; r++) {
+        size_t len = r < 4 ? 12 + 32 * (size_t)log_N : 24 + 64 * (size_t)(log_N - (r - 4));
+        memcpy(buf + 32, tr + off, len);
+        sha::host_sha256(buf, 32 + len, buf);
+        off += len;
+    }
+    memcpy(state_out, buf, 32);
+}
+
+// One device-resident sub-batch: traces already in ctx->traces (rows of n words).
+int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcripts_out, uint8_t* states_out)
+{
+    const uint32_t log_N = log_n + LOG_BLOWUP, L = log_n;
+    const size_t n = (size_t)1 << log_n, N = n << LOG_BLOWUP;
+    const size_t trs = (transcript_len(log_n) + 63) & ~(size_t)63, trl = transcript_len(log_n);
+    SizeTables* T;
+    int rc = get_tables(ctx, log_N, &T);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    int nl = 0;
+    StageTimer tm(ctx);
+    uint32_t* traces = (uint32_t*)ctx->traces.p;
+    uint32_t* coeffs = (uint32_t*)ctx->coeffs.p;
+    uint32_t* f_eval = (uint32_t*)ctx->f_eval.p;
+    uint32_t* layers = (uint32_t*)ctx->layers.p;
+    ProofState* states = (ProofState*)ctx->states.p;
+    uint8_t* trd = (uint8_t*)ctx->transcripts.p;
+
+    tm.mark();
+    CK(launch_state_init(s, states, traces, n, log_n, nb));
+    nl++;
+    // Part 1 (prover.rs:60-85)
+    CK(launch_interpolate(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, true, traces, n, coeffs, n, nb, &nl));
+    tm.mark();
+    CK(launch_lde(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, coeffs, n, (uint32_t*)ctx->work.p, N,
+                  f_eval, N, nb, &nl));
+    tm.mark();
+    TreeArgs a{};
+    a.state = states;
+    a.transcript = trd;
+    a.transcript_stride = trs;
+    a.n_layers = L;
+    a.pow = T->h.tab;
+    a.vals = f_eval;
+    a.vals_stride = N;
+    a.heap = (uint8_t*)ctx->f_heap.p;
+    a.heap_stride = 64 * N;
+    a.log_size = log_N;
+    a.post = POST_F;
+    CK(launch_merkle_tree(s, SRC_VALUES, a, nb, &nl));
+    tm.mark();
+    // Part 2 (prover.rs:101-180)
+    a.vals = layers;
+    a.vals_stride = 2 * N;
+    a.heap = (uint8_t*)ctx->layer_heaps.p;
+    a.heap_stride = 128 * N;
+    a.post = POST_CP;
+    a.cp = make_cp_args(log_n);
+    a.cp.f = f_eval;
+    a.cp.f_stride = N;
+    a.cp.alpha_from_state = 1;
+    CK(launch_merkle_tree(s, SRC_CP, a, nb, &nl));
+    tm.mark();
+    // Part 3 (prover.rs:192-254)
+    for (uint32_t i = 1; i <= L; i++) {
+        a.fold = make_fold_args(i - 1);
+        a.fold.cur = layers + layer_vals_off(log_N, i - 1);
+        a.fold.cur_stride = 2 * N;
+        a.fold.log_half = log_N - i;
+        a.fold.beta_from_state = 1;
+        a.vals = layers + layer_vals_off(log_N, i);
+        a.heap = (uint8_t*)ctx->layer_heaps.p + layer_heap_off(log_N, i);
+        a.log_size = log_N - i;
+        a.post = POST_FRI;
+        a.fri_layer = i;
+        CK(launch_merkle_tree(s, SRC_FOLD, a, nb, &nl));
+    }
+    tm.mark();
+    // Part 4 (prover.rs:263-289)
+    CK(launch_decommit(s, log_n, f_eval, N, (const uint8_t*)ctx->f_heap.p, 64 * N, layers, 2 * N,
+                       (const uint8_t*)ctx->layer_heaps.p, 128 * N, states, trd, trs, nb));
+    nl++;
+    tm.mark();
+    uint8_t* pin_tr = (uint8_t*)ctx->pinned;
+    ProofState* pin_st = (ProofState*)(pin_tr + trs * nb);
+    CK(cudaMemcpyAsync(pin_tr, trd, trs * nb, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(pin_st, states, sizeof(ProofState) * (size_t)nb, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->launches += nl;
+    if (ctx->stage_timing) {
+        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+        cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[0], ctx->ev[6]);
+    }
+    for (uint32_t b = 0; b < nb; b++) {
+        if (pin_st[b].pad[0] != 0)
+            return fail(ctx, ZK_ERR_ASSERT, "last FRI layer is not constant (prover.rs:238)");
+        memcpy(transcripts_out + trl * b, pin_tr + trs * b, trl);
+        finish_channel_host(log_n, pin_st[b], pin_tr + trs * b, states_out + 32 * (size_t)b);
+    }
+    return ZK_OK;
+}
+
+uint32_t pick_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs)
+{
+    size_t budget = ctx->mem_budget;
+    if (!budget) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        size_t held = ctx->traces.bytes + ctx->coeffs.bytes + ctx->work.bytes + ctx->f_eval.bytes + ctx->layers.bytes +
+                      ctx->f_heap.bytes + ctx->layer_heaps.bytes + ctx->states.bytes + ctx->transcripts.bytes;
+        budget = (size_t)((fr + held) * 0.7);
+    }
+    size_t per = per_proof_bytes(log_n);
+    size_t nb = budget / per;
+    if (nb < 1) nb = 1;
+    if (nb > 256) nb = 256;
+    if (nb > n_proofs) nb = n_proofs;
+    return (uint32_t)nb;
+}
+
+int check_log_n(zk_ctx* ctx, uint32_t log_n)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (log_n < ZK_MIN_LOG_N || log_n > ZK_MAX_LOG_N) return fail(ctx, ZK_ERR_INVALID, "log_n out of range [3, 27]");
+    return ZK_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* zk_version(void) { return "zkstark_b200 0.1 (sm_100a)"; }
+
+int zk_ctx_create_on_stream(int device, void* cuda_stream, zk_ctx** out)
+{
+    if (!out) return ZK_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ZK_ERR_CUDA;  // no CPU fallback
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return ZK_ERR_CUDA;
+    zk_ctx* ctx = new zk_ctx();
+    ctx->device = device;
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    for (int i = 0; i < 8; i++)
+        if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
+    int rc = init_tw(ctx);
+    if (rc) { delete ctx; return rc; }
+    *out = ctx;
+    return ZK_OK;
+}
+
+int zk_ctx_create(int device, zk_ctx** out) { return zk_ctx_create_on_stream(device, nullptr, out); }
+
+void zk_ctx_destroy(zk_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->tabs) { free_powtab(kv.second.h); free_powtab(kv.second.w); }
+    DevBuf* bufs[] = {&ctx->s0, &ctx->s1, &ctx->s2, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval,
+                      &ctx->layers, &ctx->f_heap, &ctx->layer_heaps, &ctx->states, &ctx->transcripts};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->tw_fwd) cudaFree(ctx->tw_fwd);
+    if (ctx->tw_inv) cudaFree(ctx->tw_inv);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* zk_last_error(const zk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int zk_ctx_synchronize(zk_ctx* ctx)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+int zk_ctx_set_stage_timing(zk_ctx* ctx, int on)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    ctx->stage_timing = on != 0;
+    return ZK_OK;
+}
+int zk_ctx_last_stage_ms(zk_ctx* ctx, float out_ms[7])
+{
+    if (!ctx || !out_ms) return ZK_ERR_INVALID;
+    for (int i = 0; i < 7; i++) out_ms[i] = ctx->stage_ms[i];
+    return ZK_OK;
+}
+int zk_ctx_set_memory_budget(zk_ctx* ctx, size_t bytes)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    ctx->mem_budget = bytes;
+    return ZK_OK;
+}
+
+// ------------------------------------------------------------------ device-pointer stages
+int zk_interpolate_subgroup_dev(zk_ctx* ctx, uint32_t* y, uint32_t n_points, uint32_t log_n, uint32_t* coeffs_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    const uint32_t n = 1u << log_n;
+    if (!y || !coeffs_out || (n_points != n && n_points != n - 1)) return fail(ctx, ZK_ERR_INVALID, "n_points must be n or n-1");
+    if (y == coeffs_out && log_n > 10) return fail(ctx, ZK_ERR_INVALID, "in-place interpolation needs log_n <= 10");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
+    int nl = 0;
+    CK(launch_interpolate(ctx->stream, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, n_points == n - 1, y, n,
+                          coeffs_out, n, 1, &nl));
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
+int zk_lde_coset_dev(zk_ctx* ctx, const uint32_t* coeffs, uint32_t log_n, uint32_t log_blowup, uint32_t shift,
+                     uint32_t* evals_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!coeffs || !evals_out) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (log_blowup != LOG_BLOWUP) return fail(ctx, ZK_ERR_INVALID, "log_blowup must be 3 (prover.rs:56-57)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)1 << (log_n + LOG_BLOWUP);
+    SizeTables* T;
+    if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
+    CK(ctx->s2.ensure(4 * N));
+    PowTab wtab = T->w.tab;
+    PowTabOwned tmp;
+    shift %= P;
+    if (shift != GEN) {
+        CK(build_powtab(tmp, shift, log_n, log_n + LOG_BLOWUP));
+        wtab = tmp.tab;
+    }
+    int nl = 0;
+    cudaError_t e = launch_lde(ctx->stream, ctx->tw_fwd, ctx->tw_inv, T->h.tab, wtab, log_n, coeffs, 0,
+                               (uint32_t*)ctx->s2.p, N, evals_out, N, 1, &nl);
+    if (shift != GEN) {
+        cudaStreamSynchronize(ctx->stream);
+        free_powtab(tmp);
+    }
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_lde");
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
+int zk_fri_fold_dev(zk_ctx* ctx, const uint32_t* cur, uint64_t len, uint32_t layer_k, uint32_t beta_raw, uint32_t* next_out)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!cur || !next_out || !is_pow2(len) || len < 2) return fail(ctx, ZK_ERR_INVALID, "len must be a power of two >= 2");
+    const uint32_t log_len = ilog2(len);
+    if (log_len + layer_k > 30) return fail(ctx, ZK_ERR_INVALID, "len << layer_k exceeds 2^30");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    int rc = get_tables(ctx, log_len + layer_k, &T);
+    if (rc) return rc;
+    FoldArgs f = make_fold_args(layer_k);
+    f.cur = cur;
+    f.cur_stride = 0;
+    f.beta_raw = beta_raw;
+    CK(launch_fold(ctx->stream, cur, next_out, log_len - 1, f, T->h.tab, 1, 0));
+    ctx->launches += 1;
+    return ZK_OK;
+}
+
+int zk_cp_eval_fibsq_dev(zk_ctx* ctx, const uint32_t* f_eval, uint32_t log_n, uint32_t log_blowup,
+                         const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last, uint32_t* cp_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!f_eval || !cp_out || !alpha_raw) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (log_blowup != LOG_BLOWUP) return fail(ctx, ZK_ERR_INVALID, "log_blowup must be 3");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
+    CpArgs c = make_cp_args(log_n);
+    c.f = f_eval;
+    c.f_stride = 0;
+    for (int j = 0; j < 3; j++) c.alpha_raw[j] = alpha_raw[j];
+    c.a_first = a_first % P;
+    c.a_last = a_last % P;
+    CK(launch_cp(ctx->stream, cp_out, c, T->h.tab, 1, 0));
+    ctx->launches += 1;
+    return ZK_OK;
+}
+
+int zk_merkle_build_dev(zk_ctx* ctx, const uint32_t* leaves, uint64_t size, uint8_t* heap_out)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!leaves || !heap_out) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (!is_pow2(size) || size > ((uint64_t)1 << 30)) return fail(ctx, ZK_ERR_INVALID, "size must be a power of two (merkle.rs:17-21)");
+    CK(cudaSetDevice(ctx->device));
+    TreeArgs a{};
+    a.vals = const_cast<uint32_t*>(leaves);
+    a.heap = heap_out;
+    a.log_size = ilog2(size);
+    a.post = POST_NONE;
+    int nl = 0;
+    CK(launch_merkle_tree(ctx->stream, SRC_VALUES, a, 1, &nl));
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer stages
+int zk_interpolate_subgroup(zk_ctx* ctx, const uint32_t* y, uint32_t n_points, uint32_t log_n, uint32_t* coeffs_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    const size_t n = (size_t)1 << log_n;
+    if (!y || !coeffs_out || (n_points != n && n_points != n - 1)) return fail(ctx, ZK_ERR_INVALID, "n_points must be n or n-1");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->s0.ensure(4 * n));
+    CK(ctx->s1.ensure(4 * n));
+    CK(cudaMemsetAsync(ctx->s0.p, 0, 4 * n, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->s0.p, y, 4 * (size_t)n_points, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = zk_interpolate_subgroup_dev(ctx, (uint32_t*)ctx->s0.p, n_points, log_n, (uint32_t*)ctx->s1.p))) return rc;
+    CK(cudaMemcpyAsync(coeffs_out, ctx->s1.p, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+int zk_lde_coset(zk_ctx* ctx, const uint32_t* coeffs, uint32_t log_n, uint32_t log_blowup, uint32_t shift,
+                 uint32_t* evals_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!coeffs || !evals_out) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (log_blowup != LOG_BLOWUP) return fail(ctx, ZK_ERR_INVALID, "log_blowup must be 3 (prover.rs:56-57)");
+    const size_t n = (size_t)1 << log_n, N = n << LOG_BLOWUP;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->s0.ensure(4 * n));
+    CK(ctx->s1.ensure(4 * N));
+    CK(cudaMemcpyAsync(ctx->s0.p, coeffs, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = zk_lde_coset_dev(ctx, (const uint32_t*)ctx->s0.p, log_n, log_blowup, shift, (uint32_t*)ctx->s1.p))) return rc;
+    CK(cudaMemcpyAsync(evals_out, ctx->s1.p, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+int zk_fri_fold(zk_ctx* ctx, const uint32_t* cur, uint64_t len, uint32_t layer_k, uint32_t beta_raw, uint32_t* next_out)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!cur || !next_out || !is_pow2(len) || len < 2) return fail(ctx, ZK_ERR_INVALID, "len must be a power of two >= 2");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->s0.ensure(4 * len));
+    CK(ctx->s1.ensure(2 * len));
+    CK(cudaMemcpyAsync(ctx->s0.p, cur, 4 * len, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = zk_fri_fold_dev(ctx, (const uint32_t*)ctx->s0.p, len, layer_k, beta_raw, (uint32_t*)ctx->s1.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(next_out, ctx->s1.p, 2 * len, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+int zk_cp_eval_fibsq(zk_ctx* ctx, const uint32_t* f_eval, uint32_t log_n, uint32_t log_blowup,
+                     const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last, uint32_t* cp_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!f_eval || !cp_out || !alpha_raw) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    const size_t N = (size_t)1 << (log_n + LOG_BLOWUP);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->s0.ensure(4 * N));
+    CK(ctx->s1.ensure(4 * N));
+    CK(cudaMemcpyAsync(ctx->s0.p, f_eval, 4 * N, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = zk_cp_eval_fibsq_dev(ctx, (const uint32_t*)ctx->s0.p, log_n, log_blowup, alpha_raw, a_first, a_last,
+                                   (uint32_t*)ctx->s1.p)))
+        return rc;
+    CK(cudaMemcpyAsync(cp_out, ctx->s1.p, 4 * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+static int merkle_host(zk_ctx* ctx, const uint32_t* leaves, uint64_t size, uint8_t* out, bool root_only)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!leaves || !out) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (!is_pow2(size) || size > ((uint64_t)1 << 30)) return fail(ctx, ZK_ERR_INVALID, "size must be a power of two (merkle.rs:17-21)");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->s0.ensure(4 * size));
+    CK(ctx->s1.ensure(64 * size));
+    CK(cudaMemcpyAsync(ctx->s0.p, leaves, 4 * size, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = zk_merkle_build_dev(ctx, (const uint32_t*)ctx->s0.p, size, (uint8_t*)ctx->s1.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->s1.p, root_only ? 32 : 32 * (2 * size - 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+int zk_merkle_build(zk_ctx* ctx, const uint32_t* leaves, uint64_t size, uint8_t* heap_out)
+{
+    return merkle_host(ctx, leaves, size, heap_out, false);
+}
+int zk_merkle_root(zk_ctx* ctx, const uint32_t* leaves, uint64_t size, uint8_t root_out[32])
+{
+    return merkle_host(ctx, leaves, size, root_out, true);
+}
+
+int zk_merkle_trace(const uint8_t* heap, uint64_t size, uint64_t index, uint8_t* path_out)
+{
+    if (!heap || !path_out || !is_pow2(size) || index >= size) return ZK_ERR_INVALID;
+    uint64_t i = index + size - 1;  // merkle.rs:55
+    int n = 0;
+    while (i != 0) {
+        uint64_t sib = (i % 2 == 0) ? i - 1 : i + 1;  // merkle.rs:58-66
+        memcpy(path_out + 32 * (size_t)n, heap + 32 * sib, 32);
+        i = (i - 1) >> 1;
+        n++;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ prove
+size_t zk_transcript_len(uint32_t log_n) { return transcript_len(log_n); }
+
+int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t* out)
+{
+    if (!out || log_n < 1 || log_n > 30) return ZK_ERR_INVALID;
+    const uint64_t n1 = ((uint64_t)1 << log_n) - 1;
+    // Montgomery domain for the sequential recurrence a_i = a_{i-2}^2 + a_{i-1}^2 (prover.rs:32-39)
+    uint32_t x = to_mont(1), y = to_mont(secret % P);
+    out[0] = 1;
+    if (n1 > 1) out[1] = secret % P;
+    for (uint64_t i = 2; i < n1; i++) {
+        uint32_t z = fadd(mont_mul(x, x), mont_mul(y, y));
+        out[i] = from_mont(z);
+        x = y;
+        y = z;
+    }
+    return ZK_OK;
+}
+
+int zk_prove_fibsq_resident(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t* traces_dev,
+                            uint8_t* transcripts_out, uint8_t* states_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!traces_dev || !transcripts_out || !states_out || n_proofs == 0) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << log_n, trl = transcript_len(log_n);
+    const uint32_t nbmax = pick_subbatch(ctx, log_n, n_proofs);
+    if ((rc = ensure_workspace(ctx, log_n, nbmax))) return rc;
+    for (uint32_t done = 0; done < n_proofs; done += nbmax) {
+        uint32_t nb = n_proofs - done < nbmax ? n_proofs - done : nbmax;
+        CK(cudaMemcpyAsync(ctx->traces.p, traces_dev + n * done, 4 * n * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done))) return rc;
+    }
+    return ZK_OK;
+}
+
+int zk_prove_fibsq_batch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t* traces,
+                         uint8_t* transcripts_out, uint8_t* states_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!traces || !transcripts_out || !states_out || n_proofs == 0) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << log_n, trl = transcript_len(log_n);
+    const uint32_t nbmax = pick_subbatch(ctx, log_n, n_proofs);
+    if ((rc = ensure_workspace(ctx, log_n, nbmax))) return rc;
+    for (uint32_t done = 0; done < n_proofs; done += nbmax) {
+        uint32_t nb = n_proofs - done < nbmax ? n_proofs - done : nbmax;
+        // rows of n-1 host values -> rows of n device words
+        CK(cudaMemcpy2DAsync(ctx->traces.p, 4 * n, traces + (n - 1) * done, 4 * (n - 1), 4 * (n - 1), nb,
+                             cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done))) return rc;
+    }
+    return ZK_OK;
+}
+
+int zk_prove_fibsq_from_trace(zk_ctx* ctx, uint32_t log_n, const uint32_t* trace, uint8_t* transcript_out, size_t cap,
+                              size_t* len_out, uint8_t state_out[32])
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!trace || !transcript_out || !state_out) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (cap < transcript_len(log_n)) return fail(ctx, ZK_ERR_BUFFER, "transcript buffer too small");
+    rc = zk_prove_fibsq_batch(ctx, log_n, 1, trace, transcript_out, state_out);
+    if (rc == ZK_OK && len_out) *len_out = transcript_len(log_n);
+    return rc;
+}
+
+int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transcript_out, size_t cap, size_t* len_out,
+                   uint8_t state_out[32])
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    std::vector<uint32_t> a(((size_t)1 << log_n) - 1);
+    zk_trace_fibsq(log_n, secret, a.data());
+    if (log_n == 10 && secret == 3141592u && a[1022] != 2338775057u)  // prover.rs:42
+        return fail(ctx, ZK_ERR_ASSERT, "a[1022] != 2338775057 (prover.rs:42)");
+    return zk_prove_fibsq_from_trace(ctx, log_n, a.data(), transcript_out, cap, len_out, state_out);
+}
+
+}  // extern "C"

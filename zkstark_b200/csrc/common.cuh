@@ -1,0 +1,140 @@
+// Shared declarations for the hot-path kernels: per-proof device state, power tables,
+// kernel parameter blocks and host-side launcher prototypes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "field.cuh"
+
+namespace zk {
+
+constexpr uint32_t LOG_BLOWUP = 3;  // 8192/1024 (prover.rs:56-57); literal +8/+16 at prover.rs:268-271
+constexpr uint32_t MAX_LOG_N = 27;  // N = 2^30 is the largest power-of-two subgroup of F_p^*
+constexpr uint32_t TOP_LOG = 10;    // a single CTA finishes trees of <= 2^TOP_LOG inputs
+constexpr uint32_t TOP_THREADS = 512;
+constexpr uint32_t PASS_THREADS = 128;
+constexpr uint32_t MAX_PASS_K = 5;
+
+// Two-level table of powers of h (generator of the order-N LDE subgroup, prover.rs:49):
+//   h^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits],   both halves in Montgomery form.
+// Inverse powers are read at the negated exponent (h^-e = h^(N-e)).
+struct PowTab {
+    const uint32_t* lo;
+    const uint32_t* hi;
+    uint32_t lo_bits;
+    uint32_t log_N;
+};
+
+// Per-proof Fiat-Shamir state kept on the device between kernels (channel.rs:6-9) plus
+// the challenges already drawn and the public inputs of the FibonacciSq statement.
+struct ProofState {
+    uint32_t chan[8];       // channel.rs:7 `state`, as native words H0..H7
+    uint32_t alpha_raw[3];  // prover.rs:163-165 (un-reduced, channel.rs:28-32)
+    uint32_t free_term;     // prover.rs:254
+    uint32_t beta_raw[32];  // prover.rs:200
+    uint32_t query_raw;     // prover.rs:263
+    uint32_t a_first;       // a[0]   (prover.rs:33)
+    uint32_t a_last;        // a[n-2] (prover.rs:42)
+    uint32_t chan_at_query[8];  // channel state right after the query draw (host finishes the tail)
+    uint32_t pad[9];
+};
+static_assert(sizeof(ProofState) == 64 * 4, "ProofState layout");
+
+// What the tree-top kernel does with the root it just computed (prover.rs commit order).
+enum PostOp : int {
+    POST_NONE = 0,
+    POST_F = 1,    // prover.rs:85 commit f root; :163-165 draw alpha0..2
+    POST_CP = 2,   // prover.rs:180 commit cp root; :200 draw beta_0
+    POST_FRI = 3,  // prover.rs:224 commit layer root; next beta, or (:254,:263) free term + query
+};
+
+enum SrcKind : int { SRC_VALUES = 0, SRC_DIGESTS = 1, SRC_FOLD = 2, SRC_CP = 3 };
+
+// Fused leaf sources.  `vals` is where leaf values live (or are produced into).
+struct FoldArgs {           // polynomial.rs:385-400 + prover.rs:204-211 in evaluation form
+    const uint32_t* cur;    // layer k, len = 2*half (batch stride cur_stride)
+    uint64_t cur_stride;
+    uint32_t layer_k;       // index of `cur`
+    uint32_t log_half;      // log2(len/2)
+    uint32_t winv2k_m;      // Montgomery form of (5^(2^k))^-1
+    uint32_t inv2_m;        // Montgomery form of 2^-1
+    int beta_from_state;    // read beta_raw[layer_k] from ProofState, else use beta_raw below
+    uint32_t beta_raw;
+};
+struct CpArgs {             // prover.rs:101-173 pointwise
+    const uint32_t* f;      // f_eval, N values (batch stride f_stride)
+    uint64_t f_stride;
+    uint32_t log_n;
+    uint32_t g1, g2, g3;    // g^(n-1), g^(n-2), g^(n-3) canonical
+    uint32_t zinv_m[8];     // 1/(x^n - 1) for i mod 8, Montgomery form
+    int alpha_from_state;
+    uint32_t alpha_raw[3];
+    uint32_t a_first, a_last;  // used when !alpha_from_state (stand-alone API)
+};
+
+struct TreeArgs {
+    uint32_t* vals;         // leaf values of this tree (read, or written by a fused source)
+    uint64_t vals_stride;   // elements between consecutive proofs of the batch
+    uint8_t* heap;          // 32*(2*size-1) bytes per proof, root first (merkle.rs:14-51)
+    uint64_t heap_stride;   // bytes
+    uint32_t log_size;      // tree has 2^log_size leaves
+    uint32_t in_level;      // level the kernel consumes (== log_size for leaf passes)
+    uint32_t k;             // levels produced by one thread of a pass kernel
+    ProofState* state;      // per proof (may be null for POST_NONE)
+    uint8_t* transcript;    // per proof
+    uint64_t transcript_stride;
+    int post;               // PostOp
+    uint32_t fri_layer;     // POST_FRI: index i (1..L) of the layer whose tree this is
+    uint32_t n_layers;      // L
+    PowTab pow;
+    FoldArgs fold;
+    CpArgs cp;
+};
+
+// ---- launchers (tree.cu)
+// Builds the whole tree over 2^log_size leaves taken from `src_kind`, per proof of the batch.
+cudaError_t launch_merkle_tree(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, int* n_launches);
+cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
+                            const uint8_t* f_heap, uint64_t f_heap_stride,
+                            const uint32_t* layers, uint64_t layers_stride,
+                            const uint8_t* layer_heaps, uint64_t layer_heaps_stride,
+                            ProofState* state, uint8_t* transcript, uint64_t transcript_stride,
+                            uint32_t batch);
+cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
+                              uint32_t log_n, uint32_t batch);
+// stand-alone element-wise stages (stages in isolation, for the per-function C-ABI)
+cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uint32_t log_half,
+                        FoldArgs f, PowTab pow, uint32_t batch, uint64_t next_stride);
+cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch,
+                      uint64_t out_stride);
+
+// offsets inside the bincode transcript (channel.rs:19-26 appends in commit order)
+inline size_t tr_off_alpha() { return 32; }
+inline size_t tr_off_cp_root() { return 44; }
+inline size_t tr_off_beta(uint32_t i) { return 76 + 36 * (size_t)i; }
+inline size_t tr_off_fri_root(uint32_t i /*1..L*/) { return 80 + 36 * (size_t)(i - 1); }
+inline size_t tr_off_free(uint32_t L) { return 76 + 36 * (size_t)L; }
+inline size_t tr_off_query(uint32_t L) { return 80 + 36 * (size_t)L; }
+inline size_t tr_off_decommit(uint32_t L) { return 84 + 36 * (size_t)L; }
+inline size_t transcript_len(uint32_t k)
+{
+    size_t len = tr_off_decommit(k) + 4 * (12 + 32 * (size_t)(k + LOG_BLOWUP));
+    for (uint32_t i = 0; i < k; i++) len += 24 + 64 * (size_t)(k + LOG_BLOWUP - i);
+    return len;
+}
+// byte offset of layer i's heap inside the per-proof layer-heap arena; layer i has N>>i leaves
+inline size_t layer_heap_off(uint32_t log_N, uint32_t i)
+{
+    size_t off = 0;
+    for (uint32_t j = 0; j < i; j++) off += 32 * (((size_t)2 << (log_N - j)) - 1) + 32;  // +32 keeps 64B alignment
+    return off;
+}
+inline size_t layer_vals_off(uint32_t log_N, uint32_t i)
+{
+    size_t off = 0;
+    for (uint32_t j = 0; j < i; j++) off += (size_t)1 << (log_N - j);
+    return off;
+}
+
+}  // namespace zk

@@ -1,0 +1,178 @@
+// SHA-256 for the Merkle kernels (K5) and the device-side Fiat-Shamir channel.
+//
+// Replaces sha2::Sha256 as used by merkle.rs:30-34 (leaf = SHA256(4-byte big-endian u32)),
+// merkle.rs:40-46 (node = SHA256(left || right)) and channel.rs:21-24.
+// Everything is fully unrolled so the round constants become immediates; the two
+// fixed-shape messages of the tree get dedicated entry points:
+//   leaf : one block  W0 = v, W1 = 0x80000000, W2..14 = 0, W15 = 32   (most of the
+//          schedule and the first rounds constant-fold at compile time)
+//   node : data block (16 digest words) + the CONSTANT padding block
+//          (W0 = 0x80000000, W15 = 512) whose K[i]+W[i] are compile-time constants.
+// Digest words are kept as native u32 (H0..H7); byte order is applied on store/load.
+#pragma once
+#include <stdint.h>
+
+namespace zk {
+namespace sha {
+
+struct Consts {
+    uint32_t k[64];
+    uint32_t kw_pad[64];  // K[i] + W[i] of the node padding block
+};
+
+constexpr uint32_t c_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+constexpr Consts make_consts()
+{
+    Consts c{};
+    const uint32_t k[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+        0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+        0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+        0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+        0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+        0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+        0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    uint32_t w[64] = {};
+    w[0] = 0x80000000u;
+    w[15] = 512u;
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = c_rotr(w[i - 15], 7) ^ c_rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = c_rotr(w[i - 2], 17) ^ c_rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    for (int i = 0; i < 64; i++) {
+        c.k[i] = k[i];
+        c.kw_pad[i] = k[i] + w[i];
+    }
+    return c;
+}
+
+#define ZK_SHA_IV0 0x6a09e667u
+#define ZK_SHA_IV1 0xbb67ae85u
+#define ZK_SHA_IV2 0x3c6ef372u
+#define ZK_SHA_IV3 0xa54ff53au
+#define ZK_SHA_IV4 0x510e527fu
+#define ZK_SHA_IV5 0x9b05688cu
+#define ZK_SHA_IV6 0x1f83d9abu
+#define ZK_SHA_IV7 0x5be0cd19u
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t bsig0(uint32_t x) { return rotr(x, 2) ^ rotr(x, 13) ^ rotr(x, 22); }
+__device__ __forceinline__ uint32_t bsig1(uint32_t x) { return rotr(x, 6) ^ rotr(x, 11) ^ rotr(x, 25); }
+__device__ __forceinline__ uint32_t ssig0(uint32_t x) { return rotr(x, 7) ^ rotr(x, 18) ^ (x >> 3); }
+__device__ __forceinline__ uint32_t ssig1(uint32_t x) { return rotr(x, 17) ^ rotr(x, 19) ^ (x >> 10); }
+__device__ __forceinline__ uint32_t ch(uint32_t e, uint32_t f, uint32_t g) { return (e & f) ^ (~e & g); }
+__device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) ^ (a & c) ^ (b & c); }
+
+#define ZK_SHA_ROUND(a, b, c, d, e, f, g, h, kw)                 \
+    {                                                            \
+        uint32_t t1 = h + bsig1(e) + ch(e, f, g) + (kw);         \
+        uint32_t t2 = bsig0(a) + maj(a, b, c);                   \
+        d += t1;                                                 \
+        h = t1 + t2;                                             \
+    }
+
+// One compression of a data block.  st: chaining value in/out.  w: 16 message words (clobbered).
+__device__ __forceinline__ void compress(uint32_t st[8], uint32_t w[16])
+{
+    constexpr Consts C = make_consts();
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+        if (i >= 16) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int t = i + j;
+                w[t & 15] += ssig1(w[(t - 2) & 15]) + w[(t - 7) & 15] + ssig0(w[(t - 15) & 15]);
+            }
+        }
+        ZK_SHA_ROUND(a, b, c, d, e, f, g, h, C.k[i + 0] + w[(i + 0) & 15]);
+        ZK_SHA_ROUND(h, a, b, c, d, e, f, g, C.k[i + 1] + w[(i + 1) & 15]);
+        ZK_SHA_ROUND(g, h, a, b, c, d, e, f, C.k[i + 2] + w[(i + 2) & 15]);
+        ZK_SHA_ROUND(f, g, h, a, b, c, d, e, C.k[i + 3] + w[(i + 3) & 15]);
+        ZK_SHA_ROUND(e, f, g, h, a, b, c, d, C.k[i + 4] + w[(i + 4) & 15]);
+        ZK_SHA_ROUND(d, e, f, g, h, a, b, c, C.k[i + 5] + w[(i + 5) & 15]);
+        ZK_SHA_ROUND(c, d, e, f, g, h, a, b, C.k[i + 6] + w[(i + 6) & 15]);
+        ZK_SHA_ROUND(b, c, d, e, f, g, h, a, C.k[i + 7] + w[(i + 7) & 15]);
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// The constant padding block that follows a 64-byte message (node second block).
+__device__ __forceinline__ void compress_pad64(uint32_t st[8])
+{
+    constexpr Consts C = make_consts();
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+        ZK_SHA_ROUND(a, b, c, d, e, f, g, h, C.kw_pad[i + 0]);
+        ZK_SHA_ROUND(h, a, b, c, d, e, f, g, C.kw_pad[i + 1]);
+        ZK_SHA_ROUND(g, h, a, b, c, d, e, f, C.kw_pad[i + 2]);
+        ZK_SHA_ROUND(f, g, h, a, b, c, d, e, C.kw_pad[i + 3]);
+        ZK_SHA_ROUND(e, f, g, h, a, b, c, d, C.kw_pad[i + 4]);
+        ZK_SHA_ROUND(d, e, f, g, h, a, b, c, C.kw_pad[i + 5]);
+        ZK_SHA_ROUND(c, d, e, f, g, h, a, b, C.kw_pad[i + 6]);
+        ZK_SHA_ROUND(b, c, d, e, f, g, h, a, C.kw_pad[i + 7]);
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+__device__ __forceinline__ void init_iv(uint32_t st[8])
+{
+    st[0] = ZK_SHA_IV0; st[1] = ZK_SHA_IV1; st[2] = ZK_SHA_IV2; st[3] = ZK_SHA_IV3;
+    st[4] = ZK_SHA_IV4; st[5] = ZK_SHA_IV5; st[6] = ZK_SHA_IV6; st[7] = ZK_SHA_IV7;
+}
+
+// merkle.rs:30-34: digest of the 4-byte big-endian encoding of v.  The BE bytes of a u32
+// read back as a BE message word are the number itself: W0 = v.
+__device__ __forceinline__ void hash_leaf(uint32_t v, uint32_t out[8])
+{
+    uint32_t w[16];
+    w[0] = v; w[1] = 0x80000000u;
+#pragma unroll
+    for (int i = 2; i < 15; i++) w[i] = 0u;
+    w[15] = 32u;
+    init_iv(out);
+    compress(out, w);
+}
+
+// merkle.rs:40-46: digest of left || right (two native-word digests).
+__device__ __forceinline__ void hash_node(const uint32_t l[8], const uint32_t r[8], uint32_t out[8])
+{
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w[i] = l[i]; w[8 + i] = r[i]; }
+    init_iv(out);
+    compress(out, w);
+    compress_pad64(out);
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// Digests live in global memory as the 32 raw bytes sha2 emits (merkle.rs:9): word i
+// big-endian.  32-byte aligned, moved as two 128-bit accesses.
+__device__ __forceinline__ void store_digest(uint8_t* dst, const uint32_t d[8])
+{
+    uint4* p = reinterpret_cast<uint4*>(dst);
+    p[0] = make_uint4(bswap32(d[0]), bswap32(d[1]), bswap32(d[2]), bswap32(d[3]));
+    p[1] = make_uint4(bswap32(d[4]), bswap32(d[5]), bswap32(d[6]), bswap32(d[7]));
+}
+__device__ __forceinline__ void load_digest(const uint8_t* src, uint32_t d[8])
+{
+    const uint4* p = reinterpret_cast<const uint4*>(src);
+    uint4 a = p[0], b = p[1];
+    d[0] = bswap32(a.x); d[1] = bswap32(a.y); d[2] = bswap32(a.z); d[3] = bswap32(a.w);
+    d[4] = bswap32(b.x); d[5] = bswap32(b.y); d[6] = bswap32(b.z); d[7] = bswap32(b.w);
+}
+
+#endif  // __CUDACC__
+
+// ---- host SHA-256 (generic length) for the host-side tail of the channel
+void host_sha256(const uint8_t* data, size_t len, uint8_t out[32]);
+
+}  // namespace sha
+}  // namespace zk

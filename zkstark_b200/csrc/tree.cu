@@ -1,0 +1,582 @@
+// K3 + K4 + K5 -- bottom-up SHA-256 Merkle trees with fused leaf sources.
+//
+// Reproduces Merkle::new (merkle.rs:14-51): implicit heap, root at 0, children of i at
+// 2i+1 / 2i+2, leaves at [size-1, 2size-1); leaf = SHA256(BE32(v)), node = SHA256(L||R).
+//
+// Work decomposition (B200: 148 SMs, hashing is INT-pipe bound, ~3 compressions / leaf):
+//   * pass kernel: ONE THREAD owns 2^k consecutive inputs and hashes the whole 2^k-subtree
+//     above them serially (binary-counter merge, left siblings parked in a small per-thread
+//     stack).  No inter-thread communication, every lane busy on every level; k adapts so
+//     that the grid still fills the machine.  Inputs are leaf values (hashed lane-per-leaf)
+//     or digests of a previous pass.
+//   * top kernel: one CTA finishes the last <= 2^TOP_LOG inputs level by level in shared
+//     memory and then runs the Fiat-Shamir step (channel.rs:19-32) on the root, so the
+//     next stage's challenge never leaves the device.
+// Leaf values can be produced in-kernel (north_star items 3/4): the FRI fold of the previous
+// layer (polynomial.rs:385-400 in evaluation form, proof.rs:110-112) or the composition
+// polynomial (prover.rs:101-173); the produced layer is written once and hashed from L1.
+#include "common.cuh"
+#include "sha256.cuh"
+
+namespace zk {
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ uint32_t pow_h_m(const PowTab& t, uint32_t e)
+{
+    return mont_mul(__ldg(t.lo + (e & ((1u << t.lo_bits) - 1u))), __ldg(t.hi + (e >> t.lo_bits)));
+}
+
+// ---------------------------------------------------------------- fused sources
+// FRI fold, evaluation form.  next[i] = 2^-1 * [ (u+v) + beta * x_i^-1 * (u-v) ],
+//   u = cur[i], v = cur[i+half], x_i = (5 h^i)^(2^k)  =>  x_i^-1 = 5^-(2^k) * h^(-i 2^k).
+template <int C>
+__device__ __forceinline__ void fold_chunk(const FoldArgs& f, const PowTab& pw, const uint32_t* cur,
+                                           uint32_t* next, uint32_t base, uint32_t beta_raw)
+{
+    const uint32_t half = 1u << f.log_half;
+    const uint32_t N = 1u << pw.log_N;
+    const uint32_t beta_m = to_mont(reduce_u32(beta_raw));                // field.rs:20-24
+    const uint32_t cb_m = mont_mul(beta_m, f.winv2k_m);                   // beta * 5^-(2^k)
+    const uint32_t step_m = pow_h_m(pw, (N - (1u << f.layer_k)) & (N - 1));  // h^-(2^k)
+    uint32_t e = (N - ((base << f.layer_k) & (N - 1))) & (N - 1);
+    uint32_t t_m = mont_mul(cb_m, pow_h_m(pw, e));                        // beta * x_base^-1
+    uint32_t u[C], v[C];
+    if (C >= 4) {
+#pragma unroll
+        for (int j = 0; j < C; j += 4) {
+            uint4 a = *reinterpret_cast<const uint4*>(cur + base + j);
+            uint4 b = *reinterpret_cast<const uint4*>(cur + base + half + j);
+            u[j] = a.x; u[j + 1] = a.y; u[j + 2] = a.z; u[j + 3] = a.w;
+            v[j] = b.x; v[j + 1] = b.y; v[j + 2] = b.z; v[j + 3] = b.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < C; j++) { u[j] = cur[base + j]; v[j] = cur[base + half + j]; }
+    }
+    uint32_t o[C];
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        uint32_t s = fadd(u[j], v[j]);
+        uint32_t d = mont_mul(fsub(u[j], v[j]), t_m);
+        o[j] = mont_mul(fadd(s, d), f.inv2_m);
+        t_m = mont_mul(t_m, step_m);
+    }
+    if (C >= 4) {
+#pragma unroll
+        for (int j = 0; j < C; j += 4)
+            *reinterpret_cast<uint4*>(next + base + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < C; j++) next[base + j] = o[j];
+    }
+}
+
+// Composition polynomial at x = 5 h^i (prover.rs:101-173):
+//  cp = a0 (f(x)-a_first)/(x-1) + a1 (f(x)-a_last)/(x-g^(n-2))
+//     + a2 (f(g^2 x) - f(g x)^2 - f(x)^2) (x-g^(n-3))(x-g^(n-2))(x-g^(n-1)) / (x^n-1)
+// f(g x) = f_eval[i+8], f(g^2 x) = f_eval[i+16] (indices mod N: cp_poly is evaluated on the
+// whole coset, prover.rs:172-173).  x^n - 1 depends on i mod 8 only; the two linear
+// denominators are inverted with one batched inversion per C points.
+template <int C>
+__device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, const uint32_t* f,
+                                         uint32_t* out, uint32_t base, const uint32_t al_m[3],
+                                         uint32_t a_first, uint32_t a_last)
+{
+    const uint32_t N = 1u << pw.log_N, B = 1u << LOG_BLOWUP;
+    const uint32_t h_m = pow_h_m(pw, 1);
+    uint32_t x = mont_mul(GEN, pow_h_m(pw, base));  // canonical 5 h^base
+    uint32_t xs[C], den[2 * C], pre[2 * C];
+    uint32_t acc = R1;  // Montgomery 1
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        xs[j] = x;
+        den[2 * j] = fsub(x, 1u);
+        den[2 * j + 1] = fsub(x, c.g2);
+        pre[2 * j] = acc;
+        acc = mont_mul(acc, to_mont(den[2 * j]));
+        pre[2 * j + 1] = acc;
+        acc = mont_mul(acc, to_mont(den[2 * j + 1]));
+        x = mont_mul(x, h_m);
+    }
+    acc = mont_inv(acc);  // no denominator vanishes on the coset
+    uint32_t inv_m[2 * C];
+#pragma unroll
+    for (int j = 2 * C - 1; j >= 0; j--) {
+        inv_m[j] = mont_mul(acc, pre[j]);                // Montgomery form of 1/den[j]
+        acc = mont_mul(acc, to_mont(den[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        uint32_t i = base + j;
+        uint32_t fx = f[i], fgx = f[(i + B) & (N - 1)], fggx = f[(i + 2 * B) & (N - 1)];
+        uint32_t p0 = mont_mul(fsub(fx, a_first), inv_m[2 * j]);
+        uint32_t p1 = mont_mul(fsub(fx, a_last), inv_m[2 * j + 1]);
+        uint32_t fx_m = to_mont(fx), fgx_m = to_mont(fgx);
+        uint32_t num = fsub(fsub(fggx, mont_mul(fgx, fgx_m)), mont_mul(fx, fx_m));
+        uint32_t cub_m = mont_mul(mont_mul(to_mont(fsub(xs[j], c.g3)), to_mont(fsub(xs[j], c.g2))),
+                                  to_mont(fsub(xs[j], c.g1)));
+        uint32_t p2 = mont_mul(mont_mul(num, cub_m), c.zinv_m[i & 7]);
+        out[i] = fadd(fadd(mont_mul(p0, al_m[0]), mont_mul(p1, al_m[1])), mont_mul(p2, al_m[2]));
+    }
+}
+
+template <int SRC>
+__device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, uint32_t base, uint32_t count)
+{
+    if (SRC == SRC_FOLD) {
+        const uint32_t* cur = a.fold.cur + (size_t)b * a.fold.cur_stride;
+        uint32_t* next = a.vals + (size_t)b * a.vals_stride;
+        uint32_t beta = a.fold.beta_from_state ? a.state[b].beta_raw[a.fold.layer_k] : a.fold.beta_raw;
+        if (count >= 8) { for (uint32_t o = 0; o < count; o += 8) fold_chunk<8>(a.fold, a.pow, cur, next, base + o, beta); }
+        else if (count == 4) fold_chunk<4>(a.fold, a.pow, cur, next, base, beta);
+        else if (count == 2) fold_chunk<2>(a.fold, a.pow, cur, next, base, beta);
+        else fold_chunk<1>(a.fold, a.pow, cur, next, base, beta);
+    } else if (SRC == SRC_CP) {
+        const uint32_t* f = a.cp.f + (size_t)b * a.cp.f_stride;
+        uint32_t* out = a.vals + (size_t)b * a.vals_stride;
+        uint32_t al_m[3], a_first, a_last;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint32_t raw = a.cp.alpha_from_state ? a.state[b].alpha_raw[j] : a.cp.alpha_raw[j];
+            al_m[j] = to_mont(reduce_u32(raw));
+        }
+        a_first = a.cp.alpha_from_state ? a.state[b].a_first : a.cp.a_first;
+        a_last = a.cp.alpha_from_state ? a.state[b].a_last : a.cp.a_last;
+        if (count >= 8) { for (uint32_t o = 0; o < count; o += 8) cp_chunk<8>(a.cp, a.pow, f, out, base + o, al_m, a_first, a_last); }
+        else if (count == 4) cp_chunk<4>(a.cp, a.pow, f, out, base, al_m, a_first, a_last);
+        else if (count == 2) cp_chunk<2>(a.cp, a.pow, f, out, base, al_m, a_first, a_last);
+        else cp_chunk<1>(a.cp, a.pow, f, out, base, al_m, a_first, a_last);
+    }
+}
+
+// ---------------------------------------------------------------- pass kernel
+// Thread t of proof b owns inputs [t*2^k, (t+1)*2^k) at heap level `in_level` and writes
+// every node of the subtree above them (levels in_level-1 .. in_level-k); for value
+// sources also the leaf digests themselves.
+template <int SRC>
+__global__ void __launch_bounds__(PASS_THREADS) tree_pass_kernel(const TreeArgs a)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t t = blockIdx.x * PASS_THREADS + threadIdx.x;
+    const uint32_t n_threads = 1u << (a.in_level - a.k);
+    if (t >= n_threads) return;
+    const uint32_t cnt = 1u << a.k;
+    const uint32_t base = t << a.k;
+    uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
+
+    if (SRC == SRC_FOLD || SRC == SRC_CP) produce_values<SRC>(a, b, base, cnt);
+    const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
+
+    uint32_t stack[MAX_PASS_K][8];
+    uint32_t d[8];
+    const size_t lvl0 = ((size_t)1 << a.in_level) - 1;
+    for (uint32_t i = 0; i < cnt; i++) {
+        if (SRC == SRC_DIGESTS) {
+            sha::load_digest(heap + 32 * (lvl0 + base + i), d);
+        } else {
+            sha::hash_leaf(vals[base + i], d);                              // merkle.rs:30-34
+            sha::store_digest(heap + 32 * (lvl0 + base + i), d);
+        }
+        uint32_t m = i, lvl = 0, idx = base + i;
+        while (m & 1u) {                                                    // right child: merge with parked left
+            uint32_t l[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) l[w] = stack[lvl][w];
+            sha::hash_node(l, d, d);                                        // merkle.rs:40-46
+            idx >>= 1; m >>= 1; lvl++;
+            sha::store_digest(heap + 32 * ((((size_t)1 << (a.in_level - lvl)) - 1) + idx), d);
+        }
+        if (lvl < a.k) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) stack[lvl][w] = d[w];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- device channel
+// channel.rs:19-26 for a 32-byte value: state = SHA256(state || v) -- a 64-byte message,
+// i.e. exactly the node hash.
+__device__ __noinline__ void chan_commit_digest(uint32_t st[8], const uint32_t v[8])
+{
+    uint32_t out[8];
+    sha::hash_node(st, v, out);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = out[i];
+}
+// channel.rs:19-26 for a u32: bincode writes it little-endian (4 bytes); the 36-byte message
+// state || le(v) is one padded block.
+__device__ __noinline__ void chan_commit_u32(uint32_t st[8], uint32_t v)
+{
+    uint32_t w[16], out[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = st[i];
+    w[8] = sha::bswap32(v);
+    w[9] = 0x80000000u;
+#pragma unroll
+    for (int i = 10; i < 15; i++) w[i] = 0u;
+    w[15] = 36u * 8u;
+    sha::init_iv(out);
+    sha::compress(out, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = out[i];
+}
+// channel.rs:28-32
+__device__ __forceinline__ uint32_t chan_get_u32(uint32_t st[8])
+{
+    uint32_t f = st[0];  // be32(state[0..4]) == H0
+    chan_commit_u32(st, f);
+    return f;
+}
+__device__ __forceinline__ void tr_put_u32(uint8_t* tr, size_t off, uint32_t v)
+{
+    *reinterpret_cast<uint32_t*>(tr + off) = v;  // little-endian host/device, 4-byte aligned offsets
+}
+__device__ __forceinline__ void tr_put_digest(uint8_t* tr, size_t off, const uint32_t d[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) tr_put_u32(tr, off + 4 * i, sha::bswap32(d[i]));
+}
+
+__device__ void post_root(const TreeArgs& a, uint32_t b, const uint32_t root[8])
+{
+    ProofState* ps = a.state + b;
+    uint8_t* tr = a.transcript + (size_t)b * a.transcript_stride;
+    uint32_t st[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = ps->chan[i];
+    const uint32_t L = a.n_layers;
+    if (a.post == POST_F) {
+        tr_put_digest(tr, 0, root);
+        chan_commit_digest(st, root);                                       // prover.rs:85
+        for (int j = 0; j < 3; j++) {                                       // prover.rs:163-165
+            uint32_t v = chan_get_u32(st);
+            ps->alpha_raw[j] = v;
+            tr_put_u32(tr, 32 + 4 * j, v);
+        }
+    } else if (a.post == POST_CP) {
+        tr_put_digest(tr, 44, root);
+        chan_commit_digest(st, root);                                       // prover.rs:180
+        uint32_t v = chan_get_u32(st);                                      // prover.rs:200 (first layer)
+        ps->beta_raw[0] = v;
+        tr_put_u32(tr, 76, v);
+    } else if (a.post == POST_FRI) {
+        const uint32_t i = a.fri_layer;
+        tr_put_digest(tr, 80 + 36 * (size_t)(i - 1), root);
+        chan_commit_digest(st, root);                                       // prover.rs:224
+        if (i < L) {
+            uint32_t v = chan_get_u32(st);                                  // prover.rs:200
+            ps->beta_raw[i] = v;
+            tr_put_u32(tr, 76 + 36 * (size_t)i, v);
+        } else {
+            uint32_t ft = a.vals[(size_t)b * a.vals_stride];                // prover.rs:254
+            ps->free_term = ft;
+            chan_commit_u32(st, ft);
+            tr_put_u32(tr, 76 + 36 * (size_t)L, ft);
+            uint32_t q = chan_get_u32(st);                                  // prover.rs:263
+            ps->query_raw = q;
+            tr_put_u32(tr, 80 + 36 * (size_t)L, q);
+#pragma unroll
+            for (int w = 0; w < 8; w++) ps->chan_at_query[w] = st[w];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) ps->chan[i] = st[i];
+}
+
+// ---------------------------------------------------------------- top kernel
+// One CTA per proof: consumes 2^in_level (<= 2^TOP_LOG) inputs, finishes the tree, then the
+// channel step.  One node per thread per level (TOP_THREADS >= 2^(TOP_LOG-1)).
+template <int SRC>
+__global__ void __launch_bounds__(TOP_THREADS) tree_top_kernel(const TreeArgs a)
+{
+    extern __shared__ uint32_t sm[];  // [2^in_level][8]
+    const uint32_t b = blockIdx.x, t = threadIdx.x;
+    const uint32_t n_in = 1u << a.in_level;
+    uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
+
+    if (SRC == SRC_FOLD || SRC == SRC_CP) {
+        // two consecutive points per thread (every layer has an even number of points >= 8)
+        if (n_in >= 2 * TOP_THREADS) { if (2 * t < n_in) produce_values<SRC>(a, b, 2 * t, 2); }
+        else if (t < n_in) produce_values<SRC>(a, b, t, 1);
+        __syncthreads();
+    }
+    const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
+    const size_t lvl0 = ((size_t)1 << a.in_level) - 1;
+    for (uint32_t i = t; i < n_in; i += TOP_THREADS) {
+        uint32_t d[8];
+        if (SRC == SRC_DIGESTS) {
+            sha::load_digest(heap + 32 * (lvl0 + i), d);
+        } else {
+            sha::hash_leaf(vals[i], d);
+            sha::store_digest(heap + 32 * (lvl0 + i), d);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++) sm[8 * i + w] = d[w];
+    }
+    __syncthreads();
+    for (int lvl = (int)a.in_level - 1; lvl >= 0; lvl--) {
+        const uint32_t cnt = 1u << lvl;
+        uint32_t d[8];
+        if (t < cnt) {
+            uint32_t l[8], r[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) { l[w] = sm[16 * t + w]; r[w] = sm[16 * t + 8 + w]; }
+            sha::hash_node(l, r, d);
+            sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + t), d);
+        }
+        __syncthreads();
+        if (t < cnt) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) sm[8 * t + w] = d[w];
+        }
+        __syncthreads();
+    }
+    if (t == 0 && a.post != POST_NONE) {
+        uint32_t root[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) root[w] = sm[w];
+        post_root(a, b, root);
+    }
+}
+
+// ---------------------------------------------------------------- stand-alone stage kernels
+__global__ void __launch_bounds__(256) fold_kernel(const uint32_t* cur, uint32_t* next, FoldArgs f, PowTab pw,
+                                                   uint64_t next_stride)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t half = 1u << f.log_half;
+    const uint32_t* c = cur + (size_t)b * f.cur_stride;
+    uint32_t* o = next + (size_t)b * next_stride;
+    if (half >= 4) {
+        uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
+        if (base < half) fold_chunk<4>(f, pw, c, o, base, f.beta_raw);
+    } else {
+        uint32_t base = blockIdx.x * 256 + threadIdx.x;
+        if (base < half) fold_chunk<1>(f, pw, c, o, base, f.beta_raw);
+    }
+}
+
+__global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab pw, uint64_t out_stride)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t N = 1u << pw.log_N;
+    const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (base >= N) return;
+    uint32_t al_m[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) al_m[j] = to_mont(reduce_u32(c.alpha_raw[j]));
+    cp_chunk<4>(c, pw, c.f + (size_t)b * c.f_stride, out + (size_t)b * out_stride, base, al_m,
+                reduce_u32(c.a_first), reduce_u32(c.a_last));
+}
+
+// ---------------------------------------------------------------- decommit gather (prover.rs:263-289)
+// One CTA per proof.  Writes the bincode records of Part 4 straight into the transcript:
+//   4 x (u32 value | u64 len | len digests)          f[x], f[x+8], f[x+16], cp[x]
+//   L x (u32 cp_i[x_i] | u32 cp_i[nx_i] | u64 len | path(x_i) | u64 len | path(nx_i))
+// merkle.rs:54-71 `trace`: sibling of heap index i is i-1 (i even) or i+1 (i odd), leaf -> root.
+struct DecommitArgs {
+    uint32_t log_n;
+    const uint32_t* f_eval; uint64_t f_stride;
+    const uint8_t* f_heap; uint64_t f_heap_stride;
+    const uint32_t* layers; uint64_t layers_stride;
+    const uint8_t* layer_heaps; uint64_t layer_heaps_stride;
+    ProofState* state;
+    uint8_t* transcript; uint64_t transcript_stride;
+};
+
+__device__ __forceinline__ void copy_sibling(uint8_t* dst, const uint8_t* heap, uint32_t log_size,
+                                             uint32_t leaf, uint32_t step)
+{
+    // heap index of the ancestor `step` levels above the leaf, then its sibling
+    size_t i = ((((size_t)1 << log_size) - 1) + leaf);
+    for (uint32_t s = 0; s < step; s++) i = (i - 1) >> 1;
+    size_t sib = (i & 1) ? i + 1 : i - 1;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(heap + 32 * sib);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);  // transcript offsets are 4-byte aligned
+#pragma unroll
+    for (int w = 0; w < 8; w++) d[w] = src[w];
+}
+
+__global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
+{
+    const uint32_t b = blockIdx.x;
+    const uint32_t k = a.log_n, L = k, log_N = k + LOG_BLOWUP, N = 1u << log_N, B = 1u << LOG_BLOWUP;
+    ProofState* ps = a.state + b;
+    uint8_t* tr = a.transcript + (size_t)b * a.transcript_stride;
+    const uint32_t* f = a.f_eval + (size_t)b * a.f_stride;
+    const uint8_t* fh = a.f_heap + (size_t)b * a.f_heap_stride;
+    const uint32_t* lay = a.layers + (size_t)b * a.layers_stride;
+    const uint8_t* lh = a.layer_heaps + (size_t)b * a.layer_heaps_stride;
+    const uint32_t x = (uint32_t)((size_t)ps->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
+    size_t off = 84 + 36 * (size_t)L;
+    if (threadIdx.x == 0) {
+        // prover.rs:238: the last FRI polynomial has degree 0, i.e. its 8 evaluations are equal
+        size_t voff = 0;
+        for (uint32_t j = 0; j < L; j++) voff += (size_t)1 << (log_N - j);
+        uint32_t bad = 0;
+        for (uint32_t j = 1; j < (N >> L); j++) bad |= (lay[voff + j] != lay[voff]);
+        ps->pad[0] = bad;
+    }
+    // records 0..3
+    const size_t rec0 = 12 + 32 * (size_t)log_N;
+    for (uint32_t r = 0; r < 4; r++) {
+        const uint32_t idx = (r < 3) ? x + r * B : x;
+        const uint32_t* vals = (r < 3) ? f : lay;
+        const uint8_t* heap = (r < 3) ? fh : lh;
+        uint8_t* rec = tr + off + r * rec0;
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<uint32_t*>(rec) = vals[idx];
+            *reinterpret_cast<uint32_t*>(rec + 4) = log_N;   // u64 LE length
+            *reinterpret_cast<uint32_t*>(rec + 8) = 0;
+        }
+        for (uint32_t s = threadIdx.x; s < log_N; s += blockDim.x)
+            copy_sibling(rec + 12 + 32 * (size_t)s, heap, log_N, idx, s);
+    }
+    off += 4 * rec0;
+    // FRI layer records (prover.rs:280-289)
+    for (uint32_t i = 0; i < L; i++) {
+        const uint32_t lg = log_N - i, len = 1u << lg;
+        const uint32_t xi = x & (len - 1), nx = (xi + len / 2) & (len - 1);
+        size_t voff = 0, hoff = 0;
+        for (uint32_t j = 0; j < i; j++) { voff += (size_t)1 << (log_N - j); hoff += (size_t)64 << (log_N - j); }
+        const uint32_t* vals = lay + voff;
+        const uint8_t* heap = lh + hoff;
+        uint8_t* rec = tr + off;
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<uint32_t*>(rec) = vals[xi];
+            *reinterpret_cast<uint32_t*>(rec + 4) = vals[nx];
+            *reinterpret_cast<uint32_t*>(rec + 8) = lg;
+            *reinterpret_cast<uint32_t*>(rec + 12) = 0;
+            *reinterpret_cast<uint32_t*>(rec + 16 + 32 * (size_t)lg) = lg;
+            *reinterpret_cast<uint32_t*>(rec + 20 + 32 * (size_t)lg) = 0;
+        }
+        for (uint32_t s = threadIdx.x; s < 2 * lg; s += blockDim.x) {
+            if (s < lg) copy_sibling(rec + 16 + 32 * (size_t)s, heap, lg, xi, s);
+            else copy_sibling(rec + 24 + 32 * (size_t)lg + 32 * (size_t)(s - lg), heap, lg, nx, s - lg);
+        }
+        off += 24 + 64 * (size_t)lg;
+    }
+}
+
+// channel.rs:12-17 + public inputs: zero state, a[0], a[n-2]
+__global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64_t trace_stride,
+                                  uint32_t log_n, uint32_t batch)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    ProofState s;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&s);
+    for (int i = 0; i < 64; i++) w[i] = 0;
+    const uint32_t* tr = traces + (size_t)b * trace_stride;
+    s.a_first = tr[0];
+    s.a_last = tr[(1u << log_n) - 2];
+    st[b] = s;
+}
+
+// ---------------------------------------------------------------- launchers
+template <int SRC>
+static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch)
+{
+    uint32_t n_threads = 1u << (a.in_level - a.k);
+    dim3 grid((n_threads + PASS_THREADS - 1) / PASS_THREADS, batch);
+    tree_pass_kernel<SRC><<<grid, PASS_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <int SRC>
+static cudaError_t launch_top(cudaStream_t s, const TreeArgs& a, uint32_t batch)
+{
+    size_t smem = (size_t)32 << a.in_level;
+    tree_top_kernel<SRC><<<batch, TOP_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+static uint32_t ilog2(uint64_t v)
+{
+    uint32_t l = 0;
+    while (((uint64_t)1 << (l + 1)) <= v) l++;
+    return l;
+}
+
+cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t batch, int* n_launches)
+{
+    cudaError_t e = cudaSuccess;
+    int launches = 0;
+    a.in_level = a.log_size;
+    if (a.log_size <= TOP_LOG) {
+        switch (src) {
+            case SRC_VALUES: e = launch_top<SRC_VALUES>(s, a, batch); break;
+            case SRC_FOLD: e = launch_top<SRC_FOLD>(s, a, batch); break;
+            case SRC_CP: e = launch_top<SRC_CP>(s, a, batch); break;
+            default: return cudaErrorInvalidValue;
+        }
+        launches++;
+    } else {
+        // leaf pass: enough threads to fill 148 SMs several times over, else fewer levels per thread
+        const uint32_t lb = ilog2(batch);
+        int k = (int)a.log_size + (int)lb - 18;
+        if (k < 1) k = 1;
+        if (k > (int)MAX_PASS_K) k = MAX_PASS_K;
+        if (k > (int)(a.log_size - TOP_LOG)) k = a.log_size - TOP_LOG;
+        a.k = k;
+        switch (src) {
+            case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
+            case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
+            case SRC_CP: e = launch_pass<SRC_CP>(s, a, batch); break;
+            default: return cudaErrorInvalidValue;
+        }
+        launches++;
+        if (e != cudaSuccess) return e;
+        a.in_level -= k;
+        while (a.in_level > TOP_LOG) {
+            uint32_t rem = a.in_level - TOP_LOG;
+            a.k = rem >= 2 ? 2 : 1;
+            e = launch_pass<SRC_DIGESTS>(s, a, batch);
+            launches++;
+            if (e != cudaSuccess) return e;
+            a.in_level -= a.k;
+        }
+        e = launch_top<SRC_DIGESTS>(s, a, batch);
+        launches++;
+    }
+    if (n_launches) *n_launches += launches;
+    return e;
+}
+
+cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
+                            const uint8_t* f_heap, uint64_t f_heap_stride, const uint32_t* layers,
+                            uint64_t layers_stride, const uint8_t* layer_heaps, uint64_t layer_heaps_stride,
+                            ProofState* state, uint8_t* transcript, uint64_t transcript_stride, uint32_t batch)
+{
+    DecommitArgs a{log_n, f_eval, f_stride, f_heap, f_heap_stride, layers, layers_stride,
+                   layer_heaps, layer_heaps_stride, state, transcript, transcript_stride};
+    decommit_kernel<<<batch, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
+                              uint32_t log_n, uint32_t batch)
+{
+    state_init_kernel<<<(batch + 127) / 128, 128, 0, s>>>(st, traces, trace_stride, log_n, batch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uint32_t log_half, FoldArgs f,
+                        PowTab pow, uint32_t batch, uint64_t next_stride)
+{
+    uint32_t half = 1u << log_half;
+    uint32_t work = half >= 4 ? half / 4 : half;
+    dim3 grid((work + 255) / 256, batch);
+    f.log_half = log_half;
+    fold_kernel<<<grid, 256, 0, s>>>(cur, next, f, pow, next_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch, uint64_t out_stride)
+{
+    uint32_t N = 1u << pow.log_N;
+    dim3 grid((N / 4 + 255) / 256, batch);
+    cp_kernel<<<grid, 256, 0, s>>>(cp_out, c, pow, out_stride);
+    return cudaGetLastError();
+}
+
+}  // namespace zk
