@@ -126,6 +126,17 @@ int zk_merkle_build_dev(zk_ctx *ctx, const uint32_t *leaves, uint64_t size, uint
 int zk_prove_fibsq_resident(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t *traces_dev,
                             uint8_t *transcripts_out, uint8_t *states_out);
 
+/* ---- measurement support (bench.py): runs ONE hot-path kernel (or kernel group) `iters` times on
+ * the ctx stream, each launch bracketed by CUDA events (optionally after an L2 flush that is not
+ * timed), on synthetic canonical residues it generates on the device.  ms_out[0] = mean ms per
+ * launch, ms_out[1] = min ms.  which:
+ *   0 Merkle leaf pass only (tree_pass_kernel<values>, 2^log_size leaves, 5 levels per thread)
+ *   1 whole Merkle tree over 2^log_size leaves (all passes + top)
+ *   2 coset LDE, all passes (log_size = log_n)          3 interpolation, all passes (log_n)
+ *   4 FRI fold of 2^log_size values (layer 0)            5 CP evaluation (log_size = log_n)
+ *   6 integer-pipe microbenchmark (SHF/LOP3/IADD3 mix): ms_out[2] = achieved Tiop/s             */
+int zk_bench_kernel(zk_ctx *ctx, int which, uint32_t log_size, uint32_t iters, int flush_l2, float ms_out[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,7 @@ def lib():
         "zk_cp_eval_fibsq_dev": ([vp, vp, u32, u32, vp, u32, u32, vp], i32),
         "zk_merkle_build_dev": ([vp, vp, u64, vp], i32),
         "zk_prove_fibsq_resident": ([vp, u32, u32, vp, vp, vp], i32),
+        "zk_bench_kernel": ([vp, i32, u32, u32, i32, vp], i32),
     }
     for name, (argt, rest) in sig.items():
         fn = getattr(L, name)
@@ -259,6 +260,12 @@ class Context:
         self._ck(lib().zk_ctx_last_stage_ms(self._h, arr))
         names = ["interpolate", "lde", "f_tree", "cp_tree", "fri", "decommit", "total"]
         return dict(zip(names, [float(x) for x in arr]))
+
+    def bench_kernel(self, which, log_size, iters=10, flush_l2=True):
+        """-> (mean ms, min ms, Tiop/s for the int-pipe microbenchmark)"""
+        arr = (C.c_float * 3)()
+        self._ck(lib().zk_bench_kernel(self._h, which, log_size, iters, int(flush_l2), arr))
+        return float(arr[0]), float(arr[1]), float(arr[2])
 
     def set_memory_budget(self, nbytes):
         self._ck(lib().zk_ctx_set_memory_budget(self._h, nbytes))

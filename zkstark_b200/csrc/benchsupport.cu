@@ -1,0 +1,64 @@
+// Measurement support for bench.py (zk_bench_kernel): times single hot-path kernels with CUDA
+// events on the ctx stream.  Not on the proving path.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace zk {
+
+__global__ void fill_kernel(uint32_t* p, size_t n, uint32_t seed)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint64_t x = (i + 1) * 0x9E3779B97F4A7C15ull + seed;
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        p[i] = (uint32_t)(x % P);
+    }
+}
+
+__global__ void flush_kernel(uint4* p, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = make_uint4((uint32_t)i, 1u, 2u, 3u);
+}
+
+// 4 independent chains of {SHF, LOP3, IADD3}: the instruction mix of SHA-256 on the ALU pipe.
+constexpr int INT_ITERS = 4096;
+__global__ void __launch_bounds__(256) intpipe_kernel(uint32_t* out, uint32_t seed)
+{
+    uint32_t a0 = seed + threadIdx.x, b0 = a0 * 3u, c0 = a0 ^ 0x55u;
+    uint32_t a1 = a0 + 1, b1 = b0 + 1, c1 = c0 + 1, a2 = a0 + 2, b2 = b0 + 2, c2 = c0 + 2, a3 = a0 + 3, b3 = b0 + 3, c3 = c0 + 3;
+#pragma unroll 8
+    for (int i = 0; i < INT_ITERS; i++) {
+        a0 = __funnelshift_r(a0, b0, 7);  b0 = b0 ^ c0 ^ a0;  c0 = c0 + a0 + b0;
+        a1 = __funnelshift_r(a1, b1, 11); b1 = b1 ^ c1 ^ a1;  c1 = c1 + a1 + b1;
+        a2 = __funnelshift_r(a2, b2, 13); b2 = b2 ^ c2 ^ a2;  c2 = c2 + a2 + b2;
+        a3 = __funnelshift_r(a3, b3, 17); b3 = b3 ^ c3 ^ a3;  c3 = c3 + a3 + b3;
+    }
+    uint32_t r = c0 ^ c1 ^ c2 ^ c3 ^ a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
+    if (r == 0x12345678u) out[0] = r;  // practically never: keeps the chains alive
+}
+
+cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed)
+{
+    fill_kernel<<<1184, 256, 0, s>>>(p, n, seed);
+    return cudaGetLastError();
+}
+cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes)
+{
+    flush_kernel<<<1184, 256, 0, s>>>((uint4*)p, bytes / 16);
+    return cudaGetLastError();
+}
+// returns the number of integer-pipe thread-instructions one launch executes
+double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm)
+{
+    int blocks = n_sm * 8;
+    intpipe_kernel<<<blocks, 256, 0, s>>>(out, 12345u);
+    return (double)blocks * 256.0 * INT_ITERS * 12.0;
+}
+
+}  // namespace zk

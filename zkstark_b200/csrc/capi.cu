@@ -21,6 +21,9 @@ cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* t
                        uint32_t log_n, const uint32_t* coeffs, uint64_t coeffs_stride, uint32_t* work,
                        uint64_t work_stride, uint32_t* evals, uint64_t evals_stride, uint32_t batch,
                        int* n_launches);
+cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
+cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
+double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm);
 }  // namespace zk
 
 using namespace zk;
@@ -71,6 +74,7 @@ struct zk_ctx {
     uint32_t* tw_inv = nullptr;
     std::map<uint32_t, SizeTables> tabs;  // by log_N
     DevBuf s0, s1, s2;                    // scratch for the host-buffer stage calls
+    DevBuf flushbuf;
     // prove work space
     uint32_t w_log_n = 0, w_batch = 0;
     DevBuf traces, coeffs, work, f_eval, layers, f_heap, layer_heaps, states, transcripts;
@@ -356,6 +360,8 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
 
 uint32_t pick_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs)
 {
+    // fast path: the work space already fits this request (cudaMemGetInfo costs ~1 ms)
+    if (!ctx->mem_budget && ctx->w_log_n == log_n && ctx->w_batch >= n_proofs) return n_proofs;
     size_t budget = ctx->mem_budget;
     if (!budget) {
         size_t fr = 0, tot = 0;
@@ -421,7 +427,7 @@ void zk_ctx_destroy(zk_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->tabs) { free_powtab(kv.second.h); free_powtab(kv.second.w); }
-    DevBuf* bufs[] = {&ctx->s0, &ctx->s1, &ctx->s2, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval,
+    DevBuf* bufs[] = {&ctx->flushbuf, &ctx->s0, &ctx->s1, &ctx->s2, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval,
                       &ctx->layers, &ctx->f_heap, &ctx->layer_heaps, &ctx->states, &ctx->transcripts};
     for (DevBuf* b : bufs) b->release();
     if (ctx->tw_fwd) cudaFree(ctx->tw_fwd);
@@ -723,9 +729,11 @@ int zk_prove_fibsq_batch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const u
     if ((rc = ensure_workspace(ctx, log_n, nbmax))) return rc;
     for (uint32_t done = 0; done < n_proofs; done += nbmax) {
         uint32_t nb = n_proofs - done < nbmax ? n_proofs - done : nbmax;
-        // rows of n-1 host values -> rows of n device words
-        CK(cudaMemcpy2DAsync(ctx->traces.p, 4 * n, traces + (n - 1) * done, 4 * (n - 1), 4 * (n - 1), nb,
-                             cudaMemcpyHostToDevice, ctx->stream));
+        // rows of n-1 host values -> rows of n device words (one plain copy per row: a pitched 2-D copy
+        // of rows this wide falls off the DMA fast path)
+        for (uint32_t b = 0; b < nb; b++)
+            CK(cudaMemcpyAsync((uint32_t*)ctx->traces.p + n * b, traces + (n - 1) * (size_t)(done + b), 4 * (n - 1),
+                               cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done))) return rc;
     }
     return ZK_OK;
@@ -753,6 +761,107 @@ int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transc
     if (log_n == 10 && secret == 3141592u && a[1022] != 2338775057u)  // prover.rs:42
         return fail(ctx, ZK_ERR_ASSERT, "a[1022] != 2338775057 (prover.rs:42)");
     return zk_prove_fibsq_from_trace(ctx, log_n, a.data(), transcript_out, cap, len_out, state_out);
+}
+
+// ------------------------------------------------------------------ measurement support
+int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, int flush_l2, float ms_out[3])
+{
+    if (!ctx || !ms_out || iters == 0 || iters > 1000) return ZK_ERR_INVALID;
+    if (which < 0 || which > 6) return fail(ctx, ZK_ERR_INVALID, "unknown kernel id");
+    if (which != 6 && (log_size < 3 || log_size > 30)) return fail(ctx, ZK_ERR_INVALID, "log_size out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int rc = ZK_OK;
+    const size_t flush_bytes = (size_t)512 << 20;
+    if (flush_l2) CK(ctx->flushbuf.ensure(flush_bytes));
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    SizeTables* T = nullptr;
+    size_t n_in = (size_t)1 << log_size, N8 = n_in << LOG_BLOWUP;
+    TreeArgs ta{};
+    FoldArgs fa{};
+    CpArgs ca{};
+    switch (which) {
+        case 0: case 1:
+            CK(ctx->s0.ensure(4 * n_in)); CK(ctx->s1.ensure(64 * n_in));
+            CK(bench_fill(s, (uint32_t*)ctx->s0.p, n_in, 1));
+            ta.vals = (uint32_t*)ctx->s0.p; ta.heap = (uint8_t*)ctx->s1.p; ta.log_size = log_size; ta.post = POST_NONE;
+            break;
+        case 2:
+            if ((rc = check_log_n(ctx, log_size))) return rc;
+            if ((rc = get_tables(ctx, log_size + LOG_BLOWUP, &T))) return rc;
+            CK(ctx->s0.ensure(4 * n_in)); CK(ctx->s1.ensure(4 * N8)); CK(ctx->s2.ensure(4 * N8));
+            CK(bench_fill(s, (uint32_t*)ctx->s0.p, n_in, 2));
+            break;
+        case 3:
+            if ((rc = check_log_n(ctx, log_size))) return rc;
+            if ((rc = get_tables(ctx, log_size + LOG_BLOWUP, &T))) return rc;
+            CK(ctx->s0.ensure(4 * n_in)); CK(ctx->s1.ensure(4 * n_in));
+            break;
+        case 4:
+            if ((rc = get_tables(ctx, log_size, &T))) return rc;
+            CK(ctx->s0.ensure(4 * n_in)); CK(ctx->s1.ensure(2 * n_in));
+            CK(bench_fill(s, (uint32_t*)ctx->s0.p, n_in, 4));
+            fa = make_fold_args(0); fa.cur = (const uint32_t*)ctx->s0.p; fa.beta_raw = 0x9abcdef1u;
+            break;
+        case 5:
+            if ((rc = check_log_n(ctx, log_size))) return rc;
+            if ((rc = get_tables(ctx, log_size + LOG_BLOWUP, &T))) return rc;
+            CK(ctx->s0.ensure(4 * N8)); CK(ctx->s1.ensure(4 * N8));
+            CK(bench_fill(s, (uint32_t*)ctx->s0.p, N8, 5));
+            ca = make_cp_args(log_size); ca.f = (const uint32_t*)ctx->s0.p;
+            ca.alpha_raw[0] = 361545003u; ca.alpha_raw[1] = 3235878091u; ca.alpha_raw[2] = 2708123352u;
+            ca.a_first = 1; ca.a_last = 2338775057u;
+            break;
+        default:
+            CK(ctx->s0.ensure(4096));
+            break;
+    }
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    double ops = 0;
+    int nl = 0;
+    for (uint32_t it = 0; it < iters + 1 && rc == ZK_OK; it++) {  // iteration 0 is an untimed warm-up
+        if (which == 3) {  // the inverse transform works in place: refill its input every time
+            CK(bench_fill(s, (uint32_t*)ctx->s0.p, n_in, 3 + it));
+        }
+        if (flush_l2) CK(bench_flush(s, ctx->flushbuf.p, flush_bytes));
+        if (it) CK(cudaEventRecord(ev[2 * (it - 1)], s));
+        cudaError_t e = cudaSuccess;
+        switch (which) {
+            case 0: {
+                TreeArgs a = ta; a.in_level = log_size; a.k = log_size > 15 ? 5 : 1;
+                e = launch_tree_leaf_pass(s, a, 1); nl++;
+                break;
+            }
+            case 1: e = launch_merkle_tree(s, SRC_VALUES, ta, 1, &nl); break;
+            case 2: e = launch_lde(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_size, (const uint32_t*)ctx->s0.p, 0,
+                                   (uint32_t*)ctx->s2.p, N8, (uint32_t*)ctx->s1.p, N8, 1, &nl); break;
+            case 3: e = launch_interpolate(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_size, true,
+                                           (uint32_t*)ctx->s0.p, n_in, (uint32_t*)ctx->s1.p, n_in, 1, &nl); break;
+            case 4: e = launch_fold(s, (const uint32_t*)ctx->s0.p, (uint32_t*)ctx->s1.p, log_size - 1, fa, T->h.tab, 1, 0); nl++; break;
+            case 5: e = launch_cp(s, (uint32_t*)ctx->s1.p, ca, T->h.tab, 1, 0); nl++; break;
+            default: ops = bench_intpipe(s, (uint32_t*)ctx->s0.p, n_sm); e = cudaGetLastError(); nl++; break;
+        }
+        if (e != cudaSuccess) { rc = fail_cuda(ctx, e, "bench launch"); break; }
+        if (it) CK(cudaEventRecord(ev[2 * (it - 1) + 1], s));
+    }
+    if (rc == ZK_OK) {
+        CK(cudaStreamSynchronize(s));
+        double sum = 0, mn = 1e30;
+        for (uint32_t it = 0; it < iters; it++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[2 * it], ev[2 * it + 1]);
+            sum += ms;
+            if (ms < mn) mn = ms;
+        }
+        ms_out[0] = (float)(sum / iters);
+        ms_out[1] = (float)mn;
+        ms_out[2] = which == 6 ? (float)(ops / (mn * 1e-3) / 1e12) : 0.f;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    ctx->launches += nl;
+    return rc;
 }
 
 }  // extern "C"

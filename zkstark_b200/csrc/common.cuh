@@ -95,6 +95,8 @@ struct TreeArgs {
 // ---- launchers (tree.cu)
 // Builds the whole tree over 2^log_size leaves taken from `src_kind`, per proof of the batch.
 cudaError_t launch_merkle_tree(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, int* n_launches);
+// the leaf pass alone (bench support): a.in_level / a.k preset by the caller
+cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch);
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
                             const uint8_t* f_heap, uint64_t f_heap_stride,
                             const uint32_t* layers, uint64_t layers_stride,

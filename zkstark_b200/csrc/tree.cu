@@ -542,6 +542,11 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
     return e;
 }
 
+cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch)
+{
+    return launch_pass<SRC_VALUES>(s, a, batch);
+}
+
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
                             const uint8_t* f_heap, uint64_t f_heap_stride, const uint32_t* layers,
                             uint64_t layers_stride, const uint8_t* layer_heaps, uint64_t layer_heaps_stride,
