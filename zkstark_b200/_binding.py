@@ -73,6 +73,7 @@ def lib():
         "zk_merkle_build_dev": ([vp, vp, u64, vp], i32),
         "zk_prove_fibsq_resident": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_bench_kernel": ([vp, i32, u32, u32, i32, vp], i32),
+        "zk_bench_set": ([vp, i32, u32], i32),
     }
     for name, (argt, rest) in sig.items():
         fn = getattr(L, name)
@@ -266,6 +267,9 @@ class Context:
         arr = (C.c_float * 3)()
         self._ck(lib().zk_bench_kernel(self._h, which, log_size, iters, int(flush_l2), arr))
         return float(arr[0]), float(arr[1]), float(arr[2])
+
+    def bench_set(self, sha_variant=-1, leaf_pass_k=0):
+        self._ck(lib().zk_bench_set(self._h, sha_variant, leaf_pass_k))
 
     def set_memory_budget(self, nbytes):
         self._ck(lib().zk_ctx_set_memory_budget(self._h, nbytes))

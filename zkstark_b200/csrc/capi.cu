@@ -23,7 +23,7 @@ cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* t
                        int* n_launches);
 cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
-double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm);
+double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
 }  // namespace zk
 
 using namespace zk;
@@ -75,6 +75,8 @@ struct zk_ctx {
     std::map<uint32_t, SizeTables> tabs;  // by log_N
     DevBuf s0, s1, s2;                    // scratch for the host-buffer stage calls
     DevBuf flushbuf;
+    int bench_variant = -1;
+    uint32_t bench_k = 0;
     // prove work space
     uint32_t w_log_n = 0, w_batch = 0;
     DevBuf traces, coeffs, work, f_eval, layers, f_heap, layer_heaps, states, transcripts;
@@ -414,6 +416,7 @@ int zk_ctx_create_on_stream(int device, void* cuda_stream, zk_ctx** out)
     for (int i = 0; i < 8; i++)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
     int rc = init_tw(ctx);
+    if (rc == ZK_OK && sha_init_constants() != cudaSuccess) rc = ZK_ERR_CUDA;
     if (rc) { delete ctx; return rc; }
     *out = ctx;
     return ZK_OK;
@@ -764,6 +767,14 @@ int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transc
 }
 
 // ------------------------------------------------------------------ measurement support
+int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    ctx->bench_variant = sha_variant;
+    ctx->bench_k = leaf_pass_k;
+    return ZK_OK;
+}
+
 int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, int flush_l2, float ms_out[3])
 {
     if (!ctx || !ms_out || iters == 0 || iters > 1000) return ZK_ERR_INVALID;
@@ -830,8 +841,9 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
         cudaError_t e = cudaSuccess;
         switch (which) {
             case 0: {
-                TreeArgs a = ta; a.in_level = log_size; a.k = log_size > 15 ? 5 : 1;
-                e = launch_tree_leaf_pass(s, a, 1); nl++;
+                TreeArgs a = ta; a.in_level = log_size;
+                a.k = ctx->bench_k ? ctx->bench_k : (log_size > 15 ? 5 : 1);
+                e = launch_tree_leaf_pass(s, a, 1, ctx->bench_variant); nl++;
                 break;
             }
             case 1: e = launch_merkle_tree(s, SRC_VALUES, ta, 1, &nl); break;
@@ -841,7 +853,7 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
                                            (uint32_t*)ctx->s0.p, n_in, (uint32_t*)ctx->s1.p, n_in, 1, &nl); break;
             case 4: e = launch_fold(s, (const uint32_t*)ctx->s0.p, (uint32_t*)ctx->s1.p, log_size - 1, fa, T->h.tab, 1, 0); nl++; break;
             case 5: e = launch_cp(s, (uint32_t*)ctx->s1.p, ca, T->h.tab, 1, 0); nl++; break;
-            default: ops = bench_intpipe(s, (uint32_t*)ctx->s0.p, n_sm); e = cudaGetLastError(); nl++; break;
+            default: ops = bench_intpipe(s, (uint32_t*)ctx->s0.p, n_sm, (int)log_size); e = cudaGetLastError(); nl++; break;
         }
         if (e != cudaSuccess) { rc = fail_cuda(ctx, e, "bench launch"); break; }
         if (it) CK(cudaEventRecord(ev[2 * (it - 1) + 1], s));

@@ -14,7 +14,13 @@ constexpr uint32_t MAX_LOG_N = 27;  // N = 2^30 is the largest power-of-two subg
 constexpr uint32_t TOP_LOG = 10;    // a single CTA finishes trees of <= 2^TOP_LOG inputs
 constexpr uint32_t TOP_THREADS = 512;
 constexpr uint32_t PASS_THREADS = 128;
-constexpr uint32_t MAX_PASS_K = 5;
+constexpr uint32_t MAX_PASS_K = 6;
+#ifndef ZK_SHA_UNI
+#define ZK_SHA_UNI 1  // leaf and node hashes share one copy of the data-block compression
+#endif
+#ifndef ZK_SHA_V
+#define ZK_SHA_V 3  // SHA-256 pipe-balancing variant used by the production kernels (sha256.cuh)
+#endif
 
 // Two-level table of powers of h (generator of the order-N LDE subgroup, prover.rs:49):
 //   h^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits],   both halves in Montgomery form.
@@ -96,7 +102,8 @@ struct TreeArgs {
 // Builds the whole tree over 2^log_size leaves taken from `src_kind`, per proof of the batch.
 cudaError_t launch_merkle_tree(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, int* n_launches);
 // the leaf pass alone (bench support): a.in_level / a.k preset by the caller
-cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch);
+cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant);
+cudaError_t sha_init_constants();
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
                             const uint8_t* f_heap, uint64_t f_heap_stride,
                             const uint32_t* layers, uint64_t layers_stride,

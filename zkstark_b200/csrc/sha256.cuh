@@ -58,65 +58,146 @@ constexpr Consts make_consts()
 #define ZK_SHA_IV6 0x1f83d9abu
 #define ZK_SHA_IV7 0x5be0cd19u
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(ZK_SHA_DEVICE)
+
+// ---- pipe balancing --------------------------------------------------------------------------
+// ncu (profiles/r1a): the hashing kernels saturate the ALU pipe (SHF/LOP3/IADD3, 84 %) while the FMA
+// pipe idles (5 %).  Both pipes issue one warp-instruction per 2 cycles per SM sub-partition, so work
+// moved to IMAD is free until the pipes balance.  ptxas would turn `x*1 + y` or `x * 2^k` back into
+// ALU ops, so the multipliers are read from the constant bank (opaque to the compiler):
+//   add       a + b                 ->  IMAD      a * c[ONE] + b
+//   shift     x >> k                ->  IMAD.HI   hi(x * c[2^(32-k)])
+//   rotate    rotr(x, k) = hi | lo  ->  IMAD.WIDE x * c[2^(32-k)]   (hi, lo disjoint: OR == XOR)
+// `V` is a bit mask choosing which groups of operations move (tuned on the GPU):
+//   1 round adds   2 schedule adds   4 Sigma1 rotations   8 Sigma0 rotations   16 sigma0/1 shifts
+enum ShaConst { SC_ONE = 0, SC_R6, SC_R11, SC_R2, SC_R13, SC_S3, SC_S10, SC_R18, SC_R19, SC_COUNT };
+__constant__ uint32_t c_sha[16];  // one translation unit (tree.cu) owns the hashing kernels
 
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
-__device__ __forceinline__ uint32_t bsig0(uint32_t x) { return rotr(x, 2) ^ rotr(x, 13) ^ rotr(x, 22); }
-__device__ __forceinline__ uint32_t bsig1(uint32_t x) { return rotr(x, 6) ^ rotr(x, 11) ^ rotr(x, 25); }
-__device__ __forceinline__ uint32_t ssig0(uint32_t x) { return rotr(x, 7) ^ rotr(x, 18) ^ (x >> 3); }
-__device__ __forceinline__ uint32_t ssig1(uint32_t x) { return rotr(x, 17) ^ rotr(x, 19) ^ (x >> 10); }
+template <int V, int BIT>
+__device__ __forceinline__ uint32_t addv(uint32_t a, uint32_t b)
+{
+    if (V & BIT) return a * c_sha[SC_ONE] + b;  // IMAD (FMA pipe)
+    return a + b;
+}
+__device__ __forceinline__ void mulwide(uint32_t x, int ci, uint32_t& lo, uint32_t& hi)
+{
+    uint64_t p = (uint64_t)x * c_sha[ci];  // IMAD.WIDE.U32
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+}
+template <int V>
+__device__ __forceinline__ uint32_t bsig0(uint32_t x)
+{
+    if (V & 8) {
+        uint32_t l2, h2, l13, h13;
+        mulwide(x, SC_R2, l2, h2);
+        mulwide(x, SC_R13, l13, h13);
+        return (l2 ^ h2 ^ l13) ^ h13 ^ rotr(x, 22);
+    }
+    return rotr(x, 2) ^ rotr(x, 13) ^ rotr(x, 22);
+}
+template <int V>
+__device__ __forceinline__ uint32_t bsig1(uint32_t x)
+{
+    if (V & 4) {
+        uint32_t l6, h6, l11, h11;
+        mulwide(x, SC_R6, l6, h6);
+        mulwide(x, SC_R11, l11, h11);
+        return (l6 ^ h6 ^ l11) ^ h11 ^ rotr(x, 25);
+    }
+    return rotr(x, 6) ^ rotr(x, 11) ^ rotr(x, 25);
+}
+template <int V>
+__device__ __forceinline__ uint32_t ssig0(uint32_t x)
+{
+    if (V & 16) return rotr(x, 7) ^ rotr(x, 18) ^ __umulhi(x, c_sha[SC_S3]);
+    return rotr(x, 7) ^ rotr(x, 18) ^ (x >> 3);
+}
+template <int V>
+__device__ __forceinline__ uint32_t ssig1(uint32_t x)
+{
+    if (V & 16) return rotr(x, 17) ^ rotr(x, 19) ^ __umulhi(x, c_sha[SC_S10]);
+    return rotr(x, 17) ^ rotr(x, 19) ^ (x >> 10);
+}
 __device__ __forceinline__ uint32_t ch(uint32_t e, uint32_t f, uint32_t g) { return (e & f) ^ (~e & g); }
 __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) ^ (a & c) ^ (b & c); }
 
-#define ZK_SHA_ROUND(a, b, c, d, e, f, g, h, kw)                 \
-    {                                                            \
-        uint32_t t1 = h + bsig1(e) + ch(e, f, g) + (kw);         \
-        uint32_t t2 = bsig0(a) + maj(a, b, c);                   \
-        d += t1;                                                 \
-        h = t1 + t2;                                             \
+#define ZK_SHA_ROUND(V, a, b, c, d, e, f, g, h, kw)                                          \
+    {                                                                                        \
+        uint32_t t1 = addv<V, 1>(addv<V, 1>(addv<V, 1>(h, bsig1<V>(e)), ch(e, f, g)), (kw)); \
+        uint32_t t2 = addv<V, 1>(bsig0<V>(a), maj(a, b, c));                                 \
+        d = addv<V, 1>(d, t1);                                                               \
+        h = addv<V, 1>(t1, t2);                                                              \
     }
 
+// Round constants for the rolled loops (indexed by the loop counter: a uniform constant-bank load).
+__constant__ uint32_t c_k[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+__constant__ uint32_t c_kwpad[64];  // K[i] + W[i] of the node padding block (filled by sha_init_constants)
+
+#define ZK_SHA_16ROUNDS(V, KW)                                        \
+    ZK_SHA_ROUND(V, a, b, c, d, e, f, g, h, KW(0));                   \
+    ZK_SHA_ROUND(V, h, a, b, c, d, e, f, g, KW(1));                   \
+    ZK_SHA_ROUND(V, g, h, a, b, c, d, e, f, KW(2));                   \
+    ZK_SHA_ROUND(V, f, g, h, a, b, c, d, e, KW(3));                   \
+    ZK_SHA_ROUND(V, e, f, g, h, a, b, c, d, KW(4));                   \
+    ZK_SHA_ROUND(V, d, e, f, g, h, a, b, c, KW(5));                   \
+    ZK_SHA_ROUND(V, c, d, e, f, g, h, a, b, KW(6));                   \
+    ZK_SHA_ROUND(V, b, c, d, e, f, g, h, a, KW(7));                   \
+    ZK_SHA_ROUND(V, a, b, c, d, e, f, g, h, KW(8));                   \
+    ZK_SHA_ROUND(V, h, a, b, c, d, e, f, g, KW(9));                   \
+    ZK_SHA_ROUND(V, g, h, a, b, c, d, e, f, KW(10));                  \
+    ZK_SHA_ROUND(V, f, g, h, a, b, c, d, e, KW(11));                  \
+    ZK_SHA_ROUND(V, e, f, g, h, a, b, c, d, KW(12));                  \
+    ZK_SHA_ROUND(V, d, e, f, g, h, a, b, c, KW(13));                  \
+    ZK_SHA_ROUND(V, c, d, e, f, g, h, a, b, KW(14));                  \
+    ZK_SHA_ROUND(V, b, c, d, e, f, g, h, a, KW(15));
+
 // One compression of a data block.  st: chaining value in/out.  w: 16 message words (clobbered).
+// ROLLED: rounds 0-15 are straight-line (round constants as immediates, constant message words fold);
+// rounds 16-63 are a 3-trip loop of {16 schedule updates, 16 rounds}.  The fully unrolled form is
+// ~1400 instructions (22 KB) per compression and made the hashing kernels instruction-fetch bound
+// (ncu r1a: stall_no_instruction was the top stall with 48 warps/SM walking 58 KB of code).
+template <int V>
 __device__ __forceinline__ void compress(uint32_t st[8], uint32_t w[16])
 {
     constexpr Consts C = make_consts();
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#define ZK_KW_FIRST(j) (C.k[j] + w[j])
+    ZK_SHA_16ROUNDS(V, ZK_KW_FIRST)
+#undef ZK_KW_FIRST
+#pragma unroll 1
+    for (int i = 16; i < 64; i += 16) {
 #pragma unroll
-    for (int i = 0; i < 64; i += 8) {
-        if (i >= 16) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                int t = i + j;
-                w[t & 15] += ssig1(w[(t - 2) & 15]) + w[(t - 7) & 15] + ssig0(w[(t - 15) & 15]);
-            }
-        }
-        ZK_SHA_ROUND(a, b, c, d, e, f, g, h, C.k[i + 0] + w[(i + 0) & 15]);
-        ZK_SHA_ROUND(h, a, b, c, d, e, f, g, C.k[i + 1] + w[(i + 1) & 15]);
-        ZK_SHA_ROUND(g, h, a, b, c, d, e, f, C.k[i + 2] + w[(i + 2) & 15]);
-        ZK_SHA_ROUND(f, g, h, a, b, c, d, e, C.k[i + 3] + w[(i + 3) & 15]);
-        ZK_SHA_ROUND(e, f, g, h, a, b, c, d, C.k[i + 4] + w[(i + 4) & 15]);
-        ZK_SHA_ROUND(d, e, f, g, h, a, b, c, C.k[i + 5] + w[(i + 5) & 15]);
-        ZK_SHA_ROUND(c, d, e, f, g, h, a, b, C.k[i + 6] + w[(i + 6) & 15]);
-        ZK_SHA_ROUND(b, c, d, e, f, g, h, a, C.k[i + 7] + w[(i + 7) & 15]);
+        for (int j = 0; j < 16; j++)
+            w[j] = addv<V, 2>(addv<V, 2>(addv<V, 2>(w[j], ssig1<V>(w[(j + 14) & 15])), w[(j + 9) & 15]),
+                              ssig0<V>(w[(j + 1) & 15]));
+#define ZK_KW_LOOP(j) (c_k[i + j] + w[j])
+        ZK_SHA_16ROUNDS(V, ZK_KW_LOOP)
+#undef ZK_KW_LOOP
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
-// The constant padding block that follows a 64-byte message (node second block).
+// The constant padding block that follows a 64-byte message (node second block): no schedule work,
+// K[i]+W[i] comes from the constant bank.
+template <int V>
 __device__ __forceinline__ void compress_pad64(uint32_t st[8])
 {
-    constexpr Consts C = make_consts();
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-#pragma unroll
-    for (int i = 0; i < 64; i += 8) {
-        ZK_SHA_ROUND(a, b, c, d, e, f, g, h, C.kw_pad[i + 0]);
-        ZK_SHA_ROUND(h, a, b, c, d, e, f, g, C.kw_pad[i + 1]);
-        ZK_SHA_ROUND(g, h, a, b, c, d, e, f, C.kw_pad[i + 2]);
-        ZK_SHA_ROUND(f, g, h, a, b, c, d, e, C.kw_pad[i + 3]);
-        ZK_SHA_ROUND(e, f, g, h, a, b, c, d, C.kw_pad[i + 4]);
-        ZK_SHA_ROUND(d, e, f, g, h, a, b, c, C.kw_pad[i + 5]);
-        ZK_SHA_ROUND(c, d, e, f, g, h, a, b, C.kw_pad[i + 6]);
-        ZK_SHA_ROUND(b, c, d, e, f, g, h, a, C.kw_pad[i + 7]);
+#pragma unroll 1
+    for (int i = 0; i < 64; i += 16) {
+#define ZK_KW_PAD(j) (c_kwpad[i + j])
+        ZK_SHA_16ROUNDS(V, ZK_KW_PAD)
+#undef ZK_KW_PAD
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
@@ -129,6 +210,7 @@ __device__ __forceinline__ void init_iv(uint32_t st[8])
 
 // merkle.rs:30-34: digest of the 4-byte big-endian encoding of v.  The BE bytes of a u32
 // read back as a BE message word are the number itself: W0 = v.
+template <int V = 0>
 __device__ __forceinline__ void hash_leaf(uint32_t v, uint32_t out[8])
 {
     uint32_t w[16];
@@ -137,18 +219,19 @@ __device__ __forceinline__ void hash_leaf(uint32_t v, uint32_t out[8])
     for (int i = 2; i < 15; i++) w[i] = 0u;
     w[15] = 32u;
     init_iv(out);
-    compress(out, w);
+    compress<V>(out, w);
 }
 
 // merkle.rs:40-46: digest of left || right (two native-word digests).
+template <int V = 0>
 __device__ __forceinline__ void hash_node(const uint32_t l[8], const uint32_t r[8], uint32_t out[8])
 {
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) { w[i] = l[i]; w[8 + i] = r[i]; }
     init_iv(out);
-    compress(out, w);
-    compress_pad64(out);
+    compress<V>(out, w);
+    compress_pad64<V>(out);
 }
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -169,7 +252,7 @@ __device__ __forceinline__ void load_digest(const uint8_t* src, uint32_t d[8])
     d[4] = bswap32(b.x); d[5] = bswap32(b.y); d[6] = bswap32(b.z); d[7] = bswap32(b.w);
 }
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ && ZK_SHA_DEVICE
 
 // ---- host SHA-256 (generic length) for the host-side tail of the channel
 void host_sha256(const uint8_t* data, size_t len, uint8_t out[32]);

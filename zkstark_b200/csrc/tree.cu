@@ -16,6 +16,7 @@
 // layer (polynomial.rs:385-400 in evaluation form, proof.rs:110-112) or the composition
 // polynomial (prover.rs:101-173); the produced layer is written once and hashed from L1.
 #include "common.cuh"
+#define ZK_SHA_DEVICE
 #include "sha256.cuh"
 
 namespace zk {
@@ -153,7 +154,7 @@ __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, ui
 // Thread t of proof b owns inputs [t*2^k, (t+1)*2^k) at heap level `in_level` and writes
 // every node of the subtree above them (levels in_level-1 .. in_level-k); for value
 // sources also the leaf digests themselves.
-template <int SRC>
+template <int SRC, int V = ZK_SHA_V, int UNI = ZK_SHA_UNI>
 __global__ void __launch_bounds__(PASS_THREADS) tree_pass_kernel(const TreeArgs a)
 {
     const uint32_t b = blockIdx.y;
@@ -170,11 +171,40 @@ __global__ void __launch_bounds__(PASS_THREADS) tree_pass_kernel(const TreeArgs 
     uint32_t stack[MAX_PASS_K][8];
     uint32_t d[8];
     const size_t lvl0 = ((size_t)1 << a.in_level) - 1;
+    if (UNI && SRC != SRC_DIGESTS) {
+        // One shared copy of the data-block compression for leaves and nodes (smaller instruction footprint):
+        // the message is set up first, then the same code hashes it; nodes add the constant padding block.
+        for (uint32_t i = 0; i < cnt; i++) {
+            uint32_t w[16];
+            w[0] = vals[base + i]; w[1] = 0x80000000u;                      // merkle.rs:30-34
+#pragma unroll
+            for (int j = 2; j < 15; j++) w[j] = 0u;
+            w[15] = 32u;
+            uint32_t m = i, lvl = 0, idx = base + i;
+            bool node = false;
+            for (;;) {
+                sha::init_iv(d);
+                sha::compress<V>(d, w);
+                if (node) sha::compress_pad64<V>(d);                        // merkle.rs:40-46
+                sha::store_digest(heap + 32 * ((((size_t)1 << (a.in_level - lvl)) - 1) + idx), d);
+                if (!(m & 1u)) break;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { w[j] = stack[lvl][j]; w[8 + j] = d[j]; }
+                node = true;
+                idx >>= 1; m >>= 1; lvl++;
+            }
+            if (lvl < a.k) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) stack[lvl][j] = d[j];
+            }
+        }
+        return;
+    }
     for (uint32_t i = 0; i < cnt; i++) {
         if (SRC == SRC_DIGESTS) {
             sha::load_digest(heap + 32 * (lvl0 + base + i), d);
         } else {
-            sha::hash_leaf(vals[base + i], d);                              // merkle.rs:30-34
+            sha::hash_leaf<V>(vals[base + i], d);                           // merkle.rs:30-34
             sha::store_digest(heap + 32 * (lvl0 + base + i), d);
         }
         uint32_t m = i, lvl = 0, idx = base + i;
@@ -182,7 +212,7 @@ __global__ void __launch_bounds__(PASS_THREADS) tree_pass_kernel(const TreeArgs 
             uint32_t l[8];
 #pragma unroll
             for (int w = 0; w < 8; w++) l[w] = stack[lvl][w];
-            sha::hash_node(l, d, d);                                        // merkle.rs:40-46
+            sha::hash_node<V>(l, d, d);                                     // merkle.rs:40-46
             idx >>= 1; m >>= 1; lvl++;
             sha::store_digest(heap + 32 * ((((size_t)1 << (a.in_level - lvl)) - 1) + idx), d);
         }
@@ -199,7 +229,7 @@ __global__ void __launch_bounds__(PASS_THREADS) tree_pass_kernel(const TreeArgs 
 __device__ __noinline__ void chan_commit_digest(uint32_t st[8], const uint32_t v[8])
 {
     uint32_t out[8];
-    sha::hash_node(st, v, out);
+    sha::hash_node<ZK_SHA_V>(st, v, out);
 #pragma unroll
     for (int i = 0; i < 8; i++) st[i] = out[i];
 }
@@ -216,7 +246,7 @@ __device__ __noinline__ void chan_commit_u32(uint32_t st[8], uint32_t v)
     for (int i = 10; i < 15; i++) w[i] = 0u;
     w[15] = 36u * 8u;
     sha::init_iv(out);
-    sha::compress(out, w);
+    sha::compress<0>(out, w);
 #pragma unroll
     for (int i = 0; i < 8; i++) st[i] = out[i];
 }
@@ -307,7 +337,7 @@ __global__ void __launch_bounds__(TOP_THREADS) tree_top_kernel(const TreeArgs a)
         if (SRC == SRC_DIGESTS) {
             sha::load_digest(heap + 32 * (lvl0 + i), d);
         } else {
-            sha::hash_leaf(vals[i], d);
+            sha::hash_leaf<ZK_SHA_V>(vals[i], d);
             sha::store_digest(heap + 32 * (lvl0 + i), d);
         }
 #pragma unroll
@@ -321,7 +351,7 @@ __global__ void __launch_bounds__(TOP_THREADS) tree_top_kernel(const TreeArgs a)
             uint32_t l[8], r[8];
 #pragma unroll
             for (int w = 0; w < 8; w++) { l[w] = sm[16 * t + w]; r[w] = sm[16 * t + 8 + w]; }
-            sha::hash_node(l, r, d);
+            sha::hash_node<ZK_SHA_V>(l, r, d);
             sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + t), d);
         }
         __syncthreads();
@@ -542,9 +572,33 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
     return e;
 }
 
-cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch)
+cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant)
 {
-    return launch_pass<SRC_VALUES>(s, a, batch);
+    uint32_t n_threads = 1u << (a.in_level - a.k);
+    dim3 grid((n_threads + PASS_THREADS - 1) / PASS_THREADS, batch);
+    switch (variant) {
+#ifdef ZK_SHA_EXPERIMENTS
+#define ZK_VCASE(v) \
+        case v: tree_pass_kernel<SRC_VALUES, v, 0><<<grid, PASS_THREADS, 0, s>>>(a); break; \
+        case 100 + v: tree_pass_kernel<SRC_VALUES, v, 1><<<grid, PASS_THREADS, 0, s>>>(a); break;
+        ZK_VCASE(0) ZK_VCASE(1) ZK_VCASE(17) ZK_VCASE(3) ZK_VCASE(19) ZK_VCASE(21)
+#endif
+        default: tree_pass_kernel<SRC_VALUES><<<grid, PASS_THREADS, 0, s>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+// multipliers of the FMA-pipe forms in sha256.cuh (2^(32-k) for a right shift / rotate by k)
+cudaError_t sha_init_constants()
+{
+    uint32_t h[16] = {0};
+    h[sha::SC_ONE] = 1u;
+    h[sha::SC_R6] = 1u << 26; h[sha::SC_R11] = 1u << 21; h[sha::SC_R2] = 1u << 30; h[sha::SC_R13] = 1u << 19;
+    h[sha::SC_S3] = 1u << 29; h[sha::SC_S10] = 1u << 22; h[sha::SC_R18] = 1u << 14; h[sha::SC_R19] = 1u << 13;
+    cudaError_t e = cudaMemcpyToSymbol(sha::c_sha, h, sizeof h);
+    if (e != cudaSuccess) return e;
+    constexpr sha::Consts C = sha::make_consts();
+    return cudaMemcpyToSymbol(sha::c_kwpad, C.kw_pad, sizeof C.kw_pad);
 }
 
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
