@@ -135,7 +135,9 @@ int zk_prove_fibsq_resident(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, cons
  *   2 coset LDE, all passes (log_size = log_n)          3 interpolation, all passes (log_n)
  *   4 FRI fold of 2^log_size values (layer 0)            5 CP evaluation (log_size = log_n)
  *   6 integer-pipe microbenchmark: ms_out[2] = achieved Tiop/s; log_size selects the mix:
- *     0 = ALU pipe (SHF/LOP3/IADD3), 1 = FMA pipe (IMAD), 2 = 1:1 ALU/IMAD                        */
+ *     0 = ALU pipe (SHF/LOP3/IADD3), 1 = FMA pipe (IMAD), 2 = 1:1 ALU/IMAD
+ *   7 node-hash latency probe: one CTA of `log_size` warps hashes a chain of `iters` nodes;
+ *     ms_out[2] = SM cycles per node hash                                                        */
 /* tuning knobs of zk_bench_kernel(0): SHA-256 pipe-balancing variant (-1 = production) and levels per thread */
 int zk_bench_set(zk_ctx *ctx, int sha_variant, uint32_t leaf_pass_k);
 int zk_bench_kernel(zk_ctx *ctx, int which, uint32_t log_size, uint32_t iters, int flush_l2, float ms_out[3]);

@@ -778,6 +778,20 @@ int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
 int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, int flush_l2, float ms_out[3])
 {
     if (!ctx || !ms_out || iters == 0 || iters > 1000) return ZK_ERR_INVALID;
+    if (which == 7) {  // single-CTA node-hash latency: log_size = warps, iters = chain length; ms_out[2] = cycles per node
+        CK(cudaSetDevice(ctx->device));
+        CK(ctx->s0.ensure(4096));
+        CK(cudaMemsetAsync(ctx->s0.p, 1, 4096, ctx->stream));
+        long long* cyc = (long long*)((char*)ctx->s0.p + 2048);
+        CK(launch_node_latency(ctx->stream, (uint32_t*)ctx->s0.p, iters, log_size ? log_size : 1, ctx->bench_variant, cyc));
+        long long h = 0;
+        CK(cudaMemcpyAsync(&h, cyc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ms_out[0] = ms_out[1] = 0.f;
+        ms_out[2] = (float)((double)h / iters);
+        ctx->launches += 1;
+        return ZK_OK;
+    }
     if (which < 0 || which > 6) return fail(ctx, ZK_ERR_INVALID, "unknown kernel id");
     if (which != 6 && (log_size < 3 || log_size > 30)) return fail(ctx, ZK_ERR_INVALID, "log_size out of range");
     CK(cudaSetDevice(ctx->device));

@@ -13,7 +13,10 @@ constexpr uint32_t LOG_BLOWUP = 3;  // 8192/1024 (prover.rs:56-57); literal +8/+
 constexpr uint32_t MAX_LOG_N = 27;  // N = 2^30 is the largest power-of-two subgroup of F_p^*
 constexpr uint32_t TOP_LOG = 10;    // a single CTA finishes trees of <= 2^TOP_LOG inputs
 constexpr uint32_t TOP_THREADS = 512;
-constexpr uint32_t PASS_THREADS = 128;
+#ifndef ZK_PASS_THREADS
+#define ZK_PASS_THREADS 128
+#endif
+constexpr uint32_t PASS_THREADS = ZK_PASS_THREADS;
 constexpr uint32_t MAX_PASS_K = 6;
 #ifndef ZK_SHA_UNI
 #define ZK_SHA_UNI 1  // leaf and node hashes share one copy of the data-block compression
@@ -104,6 +107,7 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src_kind, TreeArgs a, uint32_
 // the leaf pass alone (bench support): a.in_level / a.k preset by the caller
 cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant);
 cudaError_t sha_init_constants();
+cudaError_t launch_node_latency(cudaStream_t s, uint32_t* out, uint32_t reps, uint32_t warps, int variant, long long* cycles);
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
                             const uint8_t* f_heap, uint64_t f_heap_stride,
                             const uint32_t* layers, uint64_t layers_stride,

@@ -37,7 +37,8 @@ struct NttPassArgs {
     uint32_t log_Q2;     // final pass: second-pass radix (0 unless three passes)
 };
 
-constexpr int NTT_THREADS = 256;
+constexpr int NTT_MAX_THREADS = 1024;  // block size is chosen per radix: 32 * clamp(R/16, 2, 32)
+constexpr int NTT_UNR = 4;             // independent global loads in flight per thread
 constexpr int TP = 33;  // padded tile pitch
 
 __device__ __forceinline__ uint32_t pw(const PowTab& t, uint32_t e)
@@ -47,22 +48,59 @@ __device__ __forceinline__ uint32_t pw(const PowTab& t, uint32_t e)
 
 __device__ __forceinline__ uint32_t brev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
 
+// One register-blocked round of the in-place DIF: stages s .. s+LR-1 of the size-R transform along
+// the row index of sm[R][TP].  A thread owns one column (its lane) of one radix-2^LR group: it pulls
+// the 2^LR rows into registers, runs LR butterfly stages there, and writes them back -- one shared
+// memory round trip per LR stages.  Twiddles are warp-uniform (they depend on the row group only):
+// stage s' butterfly with in-group position j uses w_R^((j*stride + lo) << s'), a broadcast LDS.
+template <int LR>
+__device__ __forceinline__ void dif_round(uint32_t* sm, const uint32_t* tws, uint32_t log_R, uint32_t s)
+{
+    constexpr int RAD = 1 << LR;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t log_stride = log_R - s - LR;
+    const uint32_t n_mini = 1u << (log_R - LR);
+    for (uint32_t q = warp; q < n_mini; q += nw) {
+        const uint32_t lo = q & ((1u << log_stride) - 1u), hi = q >> log_stride;
+        const uint32_t base = (hi << (log_R - s)) + lo;
+        uint32_t x[RAD];
+#pragma unroll
+        for (int d = 0; d < RAD; d++) x[d] = sm[(base + ((uint32_t)d << log_stride)) * TP + lane];
+#pragma unroll
+        for (int t = 0; t < LR; t++) {
+            const int half = RAD >> (t + 1);
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+                const uint32_t tw = tws[(((uint32_t)j << log_stride) + lo) << (s + t)];
+#pragma unroll
+                for (int blk = 0; blk < RAD / (2 * half); blk++) {
+                    const int i0 = blk * 2 * half + j, i1 = i0 + half;
+                    const uint32_t u = x[i0], v = x[i1];
+                    x[i0] = fadd(u, v);
+                    x[i1] = mont_mul(fsub(u, v), tw);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < RAD; d++) sm[(base + ((uint32_t)d << log_stride)) * TP + lane] = x[d];
+    }
+    __syncthreads();
+}
+
 // In-place DIF over the row index of sm[R][TP], all 32 columns; leaves X[c] at row brev(c).
 __device__ __forceinline__ void cta_dif(uint32_t* sm, const uint32_t* tws, uint32_t log_R)
 {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = NTT_THREADS / 32;
-    const uint32_t halfR = 1u << (log_R - 1);
-    for (uint32_t s = 0; s < log_R; s++) {
-        const uint32_t lh = log_R - 1 - s, half = 1u << lh;
-        for (uint32_t bf = warp; bf < halfR; bf += nw) {
-            uint32_t j = bf & (half - 1), blk = bf >> lh;
-            uint32_t i0 = (blk << (lh + 1)) + j, i1 = i0 + half;
-            uint32_t u = sm[i0 * TP + lane], v = sm[i1 * TP + lane];
-            uint32_t t = tws[j << s];
-            sm[i0 * TP + lane] = fadd(u, v);
-            sm[i1 * TP + lane] = mont_mul(fsub(u, v), t);
+    uint32_t s = 0;
+    while (s < log_R) {
+        const uint32_t rem = log_R - s;
+        const uint32_t r = rem > 4 ? (rem == 5 ? 3u : 4u) : rem;
+        switch (r) {
+            case 4: dif_round<4>(sm, tws, log_R, s); break;
+            case 3: dif_round<3>(sm, tws, log_R, s); break;
+            case 2: dif_round<2>(sm, tws, log_R, s); break;
+            default: dif_round<1>(sm, tws, log_R, s); break;
         }
-        __syncthreads();
+        s += r;
     }
 }
 
@@ -74,13 +112,13 @@ __device__ __forceinline__ uint32_t coset_scale(const NttPassArgs& a, uint32_t c
     return v;
 }
 
-__global__ void __launch_bounds__(NTT_THREADS) ntt_strided_kernel(const NttPassArgs a)
+__global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_strided_kernel(const NttPassArgs a)
 {
     extern __shared__ uint32_t smem[];
     const uint32_t R = 1u << a.log_R, S = 1u << a.log_S;
     uint32_t* sm = smem;
     uint32_t* tws = smem + R * TP;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = NTT_THREADS / 32;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint32_t tiles_per_blk = S >> 5, n_blk = 1u << (a.log_M - a.log_Msub);
     uint32_t tile = blockIdx.x;
     const uint32_t per_array = tiles_per_blk * n_blk;
@@ -92,23 +130,35 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_strided_kernel(const NttPassA
     uint32_t* dst = a.dst + (size_t)blockIdx.y * a.dst_stride + r * M;
     const size_t base = ((size_t)blk << a.log_Msub) + b;
 
-    for (uint32_t i = threadIdx.x; i < R / 2; i += NTT_THREADS) tws[i] = a.tw[i];
-    for (uint32_t row = warp; row < R; row += nw) {
-        size_t k = base + ((size_t)row << a.log_S);
-        uint32_t v = src[k];
-        if (a.coset_scale) v = coset_scale(a, v, (uint32_t)k, r);
-        sm[row * TP + lane] = v;
+    for (uint32_t i = threadIdx.x; i < R / 2; i += blockDim.x) tws[i] = a.tw[i];
+    // load (rows of 32 consecutive words = 128 B), NTT_UNR independent loads in flight per thread
+    for (uint32_t row0 = warp * NTT_UNR; row0 < R; row0 += nw * NTT_UNR) {
+        uint32_t v[NTT_UNR];
+#pragma unroll
+        for (int u = 0; u < NTT_UNR; u++) v[u] = src[base + ((size_t)(row0 + u) << a.log_S)];
+#pragma unroll
+        for (int u = 0; u < NTT_UNR; u++) {
+            if (a.coset_scale) v[u] = coset_scale(a, v[u], (uint32_t)(base + ((size_t)(row0 + u) << a.log_S)), r);
+            sm[(row0 + u) * TP + lane] = v[u];
+        }
     }
     __syncthreads();
     cta_dif(sm, tws, a.log_R);
     // twiddle w_Msub^(b c) and store (c,b)
     const uint32_t N1 = (1u << a.hpow.log_N) - 1u, sh = a.hpow.log_N - a.log_Msub;
-    for (uint32_t c = warp; c < R; c += nw) {
-        uint32_t v = sm[brev(c, a.log_R) * TP + lane];
-        uint32_t e = (b * c) << sh;
-        if (a.inverse) e = ((N1 + 1u) - e) & N1;
-        if (e) v = mont_mul(v, pw(a.hpow, e));
-        dst[((size_t)blk << a.log_Msub) + ((size_t)c << a.log_S) + b] = v;
+    for (uint32_t c0 = warp * NTT_UNR; c0 < R; c0 += nw * NTT_UNR) {
+        uint32_t v[NTT_UNR], t[NTT_UNR];
+#pragma unroll
+        for (int u = 0; u < NTT_UNR; u++) {
+            const uint32_t c = c0 + u;
+            uint32_t e = (b * c) << sh;
+            if (a.inverse) e = ((N1 + 1u) - e) & N1;
+            t[u] = pw(a.hpow, e);
+            v[u] = sm[brev(c, a.log_R) * TP + lane];
+        }
+#pragma unroll
+        for (int u = 0; u < NTT_UNR; u++)
+            dst[((size_t)blk << a.log_Msub) + ((size_t)(c0 + u) << a.log_S) + b] = mont_mul(v[u], t[u]);
     }
 }
 
@@ -116,13 +166,13 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_strided_kernel(const NttPassA
 // that for every output digit c the 32 lanes write 32 consecutive words:
 //   lane = u * CS + r   (r = coset, u = index along the first-pass digit c1)
 //   out[(rho_nat + (M/R) c) * CS + r],  rho_nat = c1 + R1 c2
-__global__ void __launch_bounds__(NTT_THREADS) ntt_final_kernel(const NttPassArgs a)
+__global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_final_kernel(const NttPassArgs a)
 {
     extern __shared__ uint32_t smem[];
     const uint32_t R = 1u << a.log_R;
     uint32_t* sm = smem;
     uint32_t* tws = smem + R * TP;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = NTT_THREADS / 32;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint32_t CS = a.n_cosets, R1 = 1u << a.log_R1, Q2 = 1u << a.log_Q2;
     uint32_t U = 32 / CS;           // lanes along c1
     if (U > R1) U = R1;
@@ -132,17 +182,34 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_final_kernel(const NttPassArg
     const uint32_t* srcb = a.src + (size_t)blockIdx.y * a.src_stride;
     uint32_t* dstb = a.dst + (size_t)blockIdx.y * a.dst_stride;
 
-    for (uint32_t i = threadIdx.x; i < R / 2; i += NTT_THREADS) tws[i] = a.tw[i];
-    // load: warp w takes rows l = w, w+nw, ...; within a row the warp reads 32 consecutive words
-    const uint32_t n_rows = U * CS;
-    for (uint32_t l = warp; l < n_rows; l += nw) {
-        const uint32_t r = l % CS, u = l / CS;
-        const size_t q = (size_t)(c1_0 + u) * Q2 + c2;
-        const uint32_t* row = srcb + (a.coset_scale ? 0 : r * M) + (q << a.log_R);
-        for (uint32_t a0 = lane; a0 < R; a0 += 32) {
-            uint32_t v = row[a0];
-            if (a.coset_scale) v = coset_scale(a, v, (uint32_t)((q << a.log_R) + a0), r);
-            sm[a0 * TP + l] = v;
+    for (uint32_t i = threadIdx.x; i < R / 2; i += blockDim.x) tws[i] = a.tw[i];
+    // load: the tile is n_rows contiguous rows of R words; flat index f = l * R + a0, a warp reads 32
+    // consecutive words of one row per access (R >= 32), NTT_UNR accesses in flight
+    const uint32_t n_rows = U * CS, total = n_rows << a.log_R;
+    for (uint32_t f0 = threadIdx.x; f0 < total; f0 += blockDim.x * NTT_UNR) {
+        uint32_t v[NTT_UNR];
+#pragma unroll
+        for (int u = 0; u < NTT_UNR; u++) {
+            const uint32_t f = f0 + u * blockDim.x;
+            if (f < total) {
+                const uint32_t l = f >> a.log_R, a0 = f & (R - 1);
+                const uint32_t rr = l % CS, uu = l / CS;
+                const size_t q = (size_t)(c1_0 + uu) * Q2 + c2;
+                v[u] = srcb[(a.coset_scale ? 0 : rr * M) + (q << a.log_R) + a0];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NTT_UNR; u++) {
+            const uint32_t f = f0 + u * blockDim.x;
+            if (f < total) {
+                const uint32_t l = f >> a.log_R, a0 = f & (R - 1);
+                if (a.coset_scale) {
+                    const uint32_t rr = l % CS, uu = l / CS;
+                    const size_t q = (size_t)(c1_0 + uu) * Q2 + c2;
+                    v[u] = coset_scale(a, v[u], (uint32_t)((q << a.log_R) + a0), rr);
+                }
+                sm[a0 * TP + l] = v[u];
+            }
         }
     }
     __syncthreads();
@@ -185,13 +252,32 @@ struct NttPlan {
     uint32_t n_pass;
     uint32_t log_r[3];
 };
-static NttPlan make_plan(uint32_t mu)
+// Radix choice: CTA-local radix <= 2^10 (shared-memory tile [R][33] words), and small enough that a pass
+// has at least ~2^NTT_LOG_TILES tiles of 32 columns so every SM holds several CTAs (one CTA's global
+// load/store phase overlaps another's butterflies).  At most three passes (mu <= 30).
+#ifndef NTT_LOG_TILES
+#define NTT_LOG_TILES 10
+#endif
+static NttPlan make_plan(uint32_t mu, uint32_t log_arrays)
 {
     NttPlan p{};
-    if (mu <= 10) { p.n_pass = 1; p.log_r[0] = mu; }
-    else if (mu <= 20) { p.n_pass = 2; p.log_r[0] = (mu + 1) / 2; p.log_r[1] = mu / 2; }
-    else { p.n_pass = 3; p.log_r[0] = (mu + 2) / 3; p.log_r[1] = (mu + 1) / 3; p.log_r[2] = mu / 3; }
+    int cap = (int)(mu + log_arrays) - 5 - NTT_LOG_TILES;
+    if (cap > 10) cap = 10;
+    if (cap < 5) cap = 5;
+    uint32_t np = mu <= 10 ? 1 : (mu + cap - 1) / cap;
+    if (np > 3) np = 3;
+    if (np > mu / 5) np = mu / 5;  // every pass needs radix >= 32: strides of >= 32 words (128 B rows)
+    if (np < 1) np = 1;
+    p.n_pass = np;
+    for (uint32_t i = 0; i < np; i++) p.log_r[i] = (mu + np - 1 - i) / np;  // as even as possible, larger first
     return p;
+}
+static inline uint32_t ntt_threads(uint32_t log_R)
+{
+    uint32_t nw = (1u << log_R) >> 4;
+    if (nw < 2) nw = 2;
+    if (nw > 32) nw = 32;
+    return nw * 32;
 }
 
 // tw tables: for radix 2^m the R/2 entries start at offset 2^(m-1) - 1 (m >= 1)
@@ -217,7 +303,9 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
                            uint64_t work_stride, uint32_t* dst, uint64_t dst_stride, bool use_scale,
                            uint32_t scale_m, uint32_t batch, int* n_launches)
 {
-    NttPlan p = make_plan(mu);
+    uint32_t log_arrays = 0;
+    while ((1u << log_arrays) < n_cosets * batch) log_arrays++;
+    NttPlan p = make_plan(mu, log_arrays);
     NttPassArgs a{};
     a.log_M = mu;
     a.n_cosets = n_cosets;
@@ -242,7 +330,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
         if ((e = set_smem((const void*)ntt_strided_kernel, smem)) != cudaSuccess) return e;
         uint32_t tiles = (1u << (mu - 5)) >> a.log_R;  // (M / (R*S)) * (S/32)
         dim3 grid(tiles * n_cosets, batch);
-        ntt_strided_kernel<<<grid, NTT_THREADS, smem, s>>>(a);
+        ntt_strided_kernel<<<grid, ntt_threads(a.log_R), smem, s>>>(a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
     }
@@ -266,7 +354,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
         if (U > R1) U = R1;
         uint32_t tiles = (R1 / U) << a.log_Q2;
         dim3 grid(tiles, batch);
-        ntt_final_kernel<<<grid, NTT_THREADS, smem, s>>>(a);
+        ntt_final_kernel<<<grid, ntt_threads(a.log_R), smem, s>>>(a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
     }

@@ -123,16 +123,21 @@ __device__ __forceinline__ uint32_t ssig1(uint32_t x)
 __device__ __forceinline__ uint32_t ch(uint32_t e, uint32_t f, uint32_t g) { return (e & f) ^ (~e & g); }
 __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) ^ (a & c) ^ (b & c); }
 
-#define ZK_SHA_ROUND(V, a, b, c, d, e, f, g, h, kw)                                          \
-    {                                                                                        \
-        uint32_t t1 = addv<V, 1>(addv<V, 1>(addv<V, 1>(h, bsig1<V>(e)), ch(e, f, g)), (kw)); \
-        uint32_t t2 = addv<V, 1>(bsig0<V>(a), maj(a, b, c));                                 \
-        d = addv<V, 1>(d, t1);                                                               \
-        h = addv<V, 1>(t1, t2);                                                              \
+// One round.  The adds are ordered so that the newest value (e, via Sigma1/Ch) enters last: the chain from
+// e to the next e is SHF -> LOP3 -> add -> add, everything else (h + K + W, d + h + K + W, Sigma0 + Maj)
+// is off the critical path.  Matters for the latency-bound upper levels of a tree (one warp per SM).
+#define ZK_SHA_ROUND(V, a, b, c, d, e, f, g, h, kw)                      \
+    {                                                                    \
+        uint32_t hk = addv<V, 1>(h, (kw));                               \
+        uint32_t dhk = addv<V, 1>(d, hk);                                \
+        uint32_t y = addv<V, 1>(ch(e, f, g), bsig1<V>(e));               \
+        uint32_t s0m = addv<V, 1>(bsig0<V>(a), maj(a, b, c));            \
+        d = addv<V, 1>(dhk, y);                                          \
+        h = addv<V, 1>(addv<V, 1>(hk, y), s0m);                          \
     }
 
 // Round constants for the rolled loops (indexed by the loop counter: a uniform constant-bank load).
-__constant__ uint32_t c_k[64] = {
+__constant__ __align__(16) uint32_t c_k[64] = {
     0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
     0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
     0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
@@ -141,7 +146,7 @@ __constant__ uint32_t c_k[64] = {
     0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
     0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
-__constant__ uint32_t c_kwpad[64];  // K[i] + W[i] of the node padding block (filled by sha_init_constants)
+__constant__ __align__(16) uint32_t c_kwpad[64];  // K[i] + W[i] of the node padding block (filled by sha_init_constants)
 
 #define ZK_SHA_16ROUNDS(V, KW)                                        \
     ZK_SHA_ROUND(V, a, b, c, d, e, f, g, h, KW(0));                   \
@@ -180,7 +185,18 @@ __device__ __forceinline__ void compress(uint32_t st[8], uint32_t w[16])
         for (int j = 0; j < 16; j++)
             w[j] = addv<V, 2>(addv<V, 2>(addv<V, 2>(w[j], ssig1<V>(w[(j + 14) & 15])), w[(j + 9) & 15]),
                               ssig0<V>(w[(j + 1) & 15]));
-#define ZK_KW_LOOP(j) (c_k[i + j] + w[j])
+        // fetch the 16 round constants of this trip up front (4 x 128-bit constant loads): loaded one per
+        // round right before use, their latency is exposed 48 times per compression when a single warp runs
+        uint32_t kk[16];
+        {
+            const uint4* kp = reinterpret_cast<const uint4*>(c_k + i);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 t = kp[q];
+                kk[4 * q] = t.x; kk[4 * q + 1] = t.y; kk[4 * q + 2] = t.z; kk[4 * q + 3] = t.w;
+            }
+        }
+#define ZK_KW_LOOP(j) (kk[j] + w[j])
         ZK_SHA_16ROUNDS(V, ZK_KW_LOOP)
 #undef ZK_KW_LOOP
     }
@@ -195,7 +211,16 @@ __device__ __forceinline__ void compress_pad64(uint32_t st[8])
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll 1
     for (int i = 0; i < 64; i += 16) {
-#define ZK_KW_PAD(j) (c_kwpad[i + j])
+        uint32_t kk[16];
+        {
+            const uint4* kp = reinterpret_cast<const uint4*>(c_kwpad + i);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 t = kp[q];
+                kk[4 * q] = t.x; kk[4 * q + 1] = t.y; kk[4 * q + 2] = t.z; kk[4 * q + 3] = t.w;
+            }
+        }
+#define ZK_KW_PAD(j) (kk[j])
         ZK_SHA_16ROUNDS(V, ZK_KW_PAD)
 #undef ZK_KW_PAD
     }

@@ -588,6 +588,30 @@ cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, in
     return cudaGetLastError();
 }
 
+// Latency probe (bench support): `warps` warps of one CTA each hash a chain of `reps` nodes; returns cycles.
+template <int V>
+__global__ void node_latency_kernel(uint32_t* out, uint32_t reps, long long* cycles)
+{
+    uint32_t l[8], r[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { l[i] = threadIdx.x * 8 + i; r[i] = out[i]; }
+    long long t0 = clock64();
+    for (uint32_t k = 0; k < reps; k++) {
+        sha::hash_node<V>(l, r, d);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = d[i];
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+    if (d[0] == 0x12345678u) out[0] = d[1];
+}
+cudaError_t launch_node_latency(cudaStream_t s, uint32_t* out, uint32_t reps, uint32_t warps, int variant, long long* cycles)
+{
+    if (variant == 0) node_latency_kernel<0><<<1, 32 * warps, 0, s>>>(out, reps, cycles);
+    else node_latency_kernel<ZK_SHA_V><<<1, 32 * warps, 0, s>>>(out, reps, cycles);
+    return cudaGetLastError();
+}
+
 // multipliers of the FMA-pipe forms in sha256.cuh (2^(32-k) for a right shift / rotate by k)
 cudaError_t sha_init_constants()
 {
