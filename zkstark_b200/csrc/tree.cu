@@ -607,8 +607,13 @@ __global__ void node_latency_kernel(uint32_t* out, uint32_t reps, long long* cyc
 }
 cudaError_t launch_node_latency(cudaStream_t s, uint32_t* out, uint32_t reps, uint32_t warps, int variant, long long* cycles)
 {
-    if (variant == 0) node_latency_kernel<0><<<1, 32 * warps, 0, s>>>(out, reps, cycles);
-    else node_latency_kernel<ZK_SHA_V><<<1, 32 * warps, 0, s>>>(out, reps, cycles);
+    switch (variant) {
+#ifdef ZK_SHA_EXPERIMENTS
+#define ZK_LCASE(v) case v: node_latency_kernel<v><<<1, 32 * warps, 0, s>>>(out, reps, cycles); break;
+        ZK_LCASE(0) ZK_LCASE(1) ZK_LCASE(3) ZK_LCASE(7) ZK_LCASE(11) ZK_LCASE(15) ZK_LCASE(19) ZK_LCASE(23) ZK_LCASE(31) ZK_LCASE(28) ZK_LCASE(12)
+#endif
+        default: node_latency_kernel<ZK_SHA_V><<<1, 32 * warps, 0, s>>>(out, reps, cycles); break;
+    }
     return cudaGetLastError();
 }
 
