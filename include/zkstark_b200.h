@@ -126,6 +126,37 @@ int zk_merkle_build_dev(zk_ctx *ctx, const uint32_t *leaves, uint64_t size, uint
 int zk_prove_fibsq_resident(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t *traces_dev,
                             uint8_t *transcripts_out, uint8_t *states_out);
 
+/* ---- one proof sharded over several GPUs (BASELINE configs[4]; driver: zkstark_b200/sharded.py) ------------
+ * Ownership of every evaluation array is blocked-cyclic: global index i lives on rank (i >> log_block) % n_ranks
+ * at local index ((i >> log_block) / n_ranks) << log_block | (i & (2^log_block - 1)).  FRI folds (partner
+ * i + len/2) and the bottom log_block Merkle levels are then rank-local; what crosses NVLink is one all-to-all
+ * after the LDE (cosets -> blocks), the block roots of every tree and a 16-value halo per block for the CP.
+ * All pointers are device memory; calls enqueue on the ctx stream.  state_dev: 256-byte per-proof Fiat-Shamir
+ * state kept on the device and replicated on every rank; transcript_dev: zk_transcript_len bytes (+64). */
+int zk_shard_state_init_dev(zk_ctx *ctx, void *state_dev, uint32_t a_first, uint32_t a_last);
+/* out[j] = f(5 h^(8 j + coset)), j < 2^log_n: one of the 8 coset transforms of the LDE; work: 2^log_n scratch */
+int zk_shard_lde_coset_dev(zk_ctx *ctx, const uint32_t *coeffs, uint32_t log_n, uint32_t coset, uint32_t *work,
+                           uint32_t *out);
+/* Merkle levels of the rank-local array up to its 2^log_block-leaf block roots, in heap order of the local
+ * array: the block roots are the local_len >> log_block digests of heap level log2(local_len) - log_block */
+int zk_shard_merkle_blocks_dev(zk_ctx *ctx, const uint32_t *vals_local, uint64_t local_len, uint32_t log_block,
+                               uint8_t *heap_local);
+/* upper part of a tree: upper_heap holds 2^log_count digests at heap level log_count (all block roots, global
+ * order); builds the levels above them, then runs the channel step post_op (0 none, 1 f root + alphas,
+ * 2 cp root + beta_0, 3 FRI layer `fri_layer` root + next beta) on state_dev / transcript_dev */
+int zk_shard_upper_tree_dev(zk_ctx *ctx, uint8_t *upper_heap, uint32_t log_count, int post_op, uint32_t fri_layer,
+                            uint32_t n_layers, void *state_dev, uint8_t *transcript_dev);
+/* composition polynomial on the rank-local points; halo: 16 values per local block = head of the next block */
+int zk_shard_cp_dev(zk_ctx *ctx, const uint32_t *f_local, const uint32_t *halo, uint64_t local_len, uint32_t log_n,
+                    uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void *state_dev, uint32_t *cp_local);
+/* FRI fold of the rank-local part of layer layer_k (beta from state_dev); log_N0 = log2 of the LDE size */
+int zk_shard_fold_dev(zk_ctx *ctx, const uint32_t *cur_local, uint64_t local_len, uint32_t layer_k, uint32_t log_N0,
+                      uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void *state_dev, uint32_t *next_local);
+/* replicated tail once a layer is too small to shard: layer first_layer is complete at layers_arena[0..);
+ * layers first_layer+1..L (values, heaps at 64 bytes per value of the preceding layers) are appended */
+int zk_shard_fri_tail_dev(zk_ctx *ctx, uint32_t log_n, uint32_t first_layer, uint32_t *layers_arena,
+                          uint8_t *heaps_arena, void *state_dev, uint8_t *transcript_dev);
+
 /* ---- measurement support (bench.py): runs ONE hot-path kernel (or kernel group) `iters` times on
  * the ctx stream, each launch bracketed by CUDA events (optionally after an L2 flush that is not
  * timed), on synthetic canonical residues it generates on the device.  ms_out[0] = mean ms per

@@ -73,6 +73,13 @@ def lib():
         "zk_merkle_build_dev": ([vp, vp, u64, vp], i32),
         "zk_prove_fibsq_resident": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_bench_kernel": ([vp, i32, u32, u32, i32, vp], i32),
+        "zk_shard_state_init_dev": ([vp, vp, u32, u32], i32),
+        "zk_shard_lde_coset_dev": ([vp, vp, u32, u32, vp, vp], i32),
+        "zk_shard_merkle_blocks_dev": ([vp, vp, u64, u32, vp], i32),
+        "zk_shard_upper_tree_dev": ([vp, vp, u32, i32, u32, u32, vp, vp], i32),
+        "zk_shard_cp_dev": ([vp, vp, vp, u64, u32, u32, u32, u32, vp, vp], i32),
+        "zk_shard_fold_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp], i32),
+        "zk_shard_fri_tail_dev": ([vp, u32, u32, vp, vp, vp, vp], i32),
         "zk_bench_set": ([vp, i32, u32], i32),
     }
     for name, (argt, rest) in sig.items():
@@ -246,6 +253,32 @@ class Context:
 
     def merkle_build_dev(self, leaves_ptr, size, heap_ptr):
         self._ck(lib().zk_merkle_build_dev(self._h, C.c_void_p(leaves_ptr), size, C.c_void_p(heap_ptr)))
+
+    # ---- building blocks of a proof sharded over GPUs (zkstark_b200/sharded.py)
+    def shard_state_init(self, state_ptr, a_first, a_last):
+        self._ck(lib().zk_shard_state_init_dev(self._h, C.c_void_p(state_ptr), a_first, a_last))
+
+    def shard_lde_coset(self, coeffs_ptr, log_n, coset, work_ptr, out_ptr):
+        self._ck(lib().zk_shard_lde_coset_dev(self._h, C.c_void_p(coeffs_ptr), log_n, coset, C.c_void_p(work_ptr), C.c_void_p(out_ptr)))
+
+    def shard_merkle_blocks(self, vals_ptr, local_len, log_block, heap_ptr):
+        self._ck(lib().zk_shard_merkle_blocks_dev(self._h, C.c_void_p(vals_ptr), local_len, log_block, C.c_void_p(heap_ptr)))
+
+    def shard_upper_tree(self, upper_heap_ptr, log_count, post_op, fri_layer, n_layers, state_ptr, transcript_ptr):
+        self._ck(lib().zk_shard_upper_tree_dev(self._h, C.c_void_p(upper_heap_ptr), log_count, post_op, fri_layer, n_layers,
+                                               C.c_void_p(state_ptr), C.c_void_p(transcript_ptr)))
+
+    def shard_cp(self, f_ptr, halo_ptr, local_len, log_n, n_ranks, rank, log_block, state_ptr, cp_ptr):
+        self._ck(lib().zk_shard_cp_dev(self._h, C.c_void_p(f_ptr), C.c_void_p(halo_ptr), local_len, log_n, n_ranks, rank, log_block,
+                                       C.c_void_p(state_ptr), C.c_void_p(cp_ptr)))
+
+    def shard_fold(self, cur_ptr, local_len, layer_k, log_N0, n_ranks, rank, log_block, state_ptr, next_ptr):
+        self._ck(lib().zk_shard_fold_dev(self._h, C.c_void_p(cur_ptr), local_len, layer_k, log_N0, n_ranks, rank, log_block,
+                                         C.c_void_p(state_ptr), C.c_void_p(next_ptr)))
+
+    def shard_fri_tail(self, log_n, first_layer, layers_ptr, heaps_ptr, state_ptr, transcript_ptr):
+        self._ck(lib().zk_shard_fri_tail_dev(self._h, log_n, first_layer, C.c_void_p(layers_ptr), C.c_void_p(heaps_ptr),
+                                             C.c_void_p(state_ptr), C.c_void_p(transcript_ptr)))
 
     def synchronize(self):
         self._ck(lib().zk_ctx_synchronize(self._h))

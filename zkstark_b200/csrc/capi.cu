@@ -21,6 +21,9 @@ cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* t
                        uint32_t log_n, const uint32_t* coeffs, uint64_t coeffs_stride, uint32_t* work,
                        uint64_t work_stride, uint32_t* evals, uint64_t evals_stride, uint32_t batch,
                        int* n_launches);
+cudaError_t launch_lde_one_coset(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
+                                 uint32_t log_n, uint32_t r, const uint32_t* coeffs, uint32_t* work, uint32_t* out,
+                                 int* n_launches);
 cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
 double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
@@ -192,6 +195,7 @@ CpArgs make_cp_args(uint32_t log_n)
     const uint64_t n = (uint64_t)1 << log_n;
     const uint32_t g = h_root(log_n), h = h_root(log_N);
     c.log_n = log_n;
+    c.log_len = log_N;
     c.g1 = h_pow(g, n - 1);
     c.g2 = h_pow(g, n - 2);
     c.g3 = h_pow(g, n - 3);
@@ -764,6 +768,153 @@ int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transc
     if (log_n == 10 && secret == 3141592u && a[1022] != 2338775057u)  // prover.rs:42
         return fail(ctx, ZK_ERR_ASSERT, "a[1022] != 2338775057 (prover.rs:42)");
     return zk_prove_fibsq_from_trace(ctx, log_n, a.data(), transcript_out, cap, len_out, state_out);
+}
+
+// ------------------------------------------------------------------ one proof sharded over several GPUs
+// Building blocks for zkstark_b200/sharded.py (one process per GPU; torch.distributed moves the data).
+int zk_shard_state_init_dev(zk_ctx* ctx, void* state_dev, uint32_t a_first, uint32_t a_last)
+{
+    if (!ctx || !state_dev) return ZK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_state_set(ctx->stream, (ProofState*)state_dev, a_first % P, a_last % P));
+    ctx->launches += 1;
+    return ZK_OK;
+}
+
+int zk_shard_lde_coset_dev(zk_ctx* ctx, const uint32_t* coeffs, uint32_t log_n, uint32_t coset, uint32_t* work, uint32_t* out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!coeffs || !work || !out || coset >= (1u << LOG_BLOWUP)) return fail(ctx, ZK_ERR_INVALID, "bad coset/buffer");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
+    int nl = 0;
+    CK(launch_lde_one_coset(ctx->stream, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, coset, coeffs, work, out, &nl));
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
+int zk_shard_merkle_blocks_dev(zk_ctx* ctx, const uint32_t* vals_local, uint64_t local_len, uint32_t log_block, uint8_t* heap_local)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!vals_local || !heap_local || !is_pow2(local_len)) return fail(ctx, ZK_ERR_INVALID, "local_len must be a power of two");
+    const uint32_t lg = ilog2(local_len);
+    if (lg < log_block || log_block < 1) return fail(ctx, ZK_ERR_INVALID, "local_len smaller than a block");
+    CK(cudaSetDevice(ctx->device));
+    TreeArgs a{};
+    a.vals = const_cast<uint32_t*>(vals_local);
+    a.heap = heap_local;
+    a.log_size = lg;
+    int nl = 0;
+    CK(launch_merkle_partial(ctx->stream, SRC_VALUES, a, 1, lg - log_block, &nl));
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
+int zk_shard_upper_tree_dev(zk_ctx* ctx, uint8_t* upper_heap, uint32_t log_count, int post_op, uint32_t fri_layer,
+                            uint32_t n_layers, void* state_dev, uint8_t* transcript_dev)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!upper_heap || log_count > 30 || post_op < POST_NONE || post_op > POST_FRI) return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    if (post_op != POST_NONE && (!state_dev || !transcript_dev)) return fail(ctx, ZK_ERR_INVALID, "post op needs state and transcript");
+    if (post_op == POST_FRI && fri_layer >= n_layers) return fail(ctx, ZK_ERR_INVALID, "the last layer belongs to the replicated tail");
+    CK(cudaSetDevice(ctx->device));
+    TreeArgs a{};
+    a.heap = upper_heap;
+    a.log_size = log_count;
+    a.in_level = log_count;
+    a.post = post_op;
+    a.fri_layer = fri_layer;
+    a.n_layers = n_layers;
+    a.state = (ProofState*)state_dev;
+    a.transcript = transcript_dev;
+    int nl = 0;
+    CK(launch_merkle_upper(ctx->stream, a, 1, &nl));
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
+int zk_shard_cp_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, uint64_t local_len, uint32_t log_n,
+                    uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev, uint32_t* cp_local)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!f_local || !halo || !state_dev || !cp_local || !is_pow2(local_len) || n_ranks == 0 || rank >= n_ranks)
+        return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    if ((local_len * n_ranks) != ((uint64_t)1 << (log_n + LOG_BLOWUP)) || local_len < ((uint64_t)1 << log_block) || log_block < 5)
+        return fail(ctx, ZK_ERR_INVALID, "local_len * n_ranks must be 8n and hold at least one block of >= 32");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
+    CpArgs c = make_cp_args(log_n);
+    c.f = f_local;
+    c.halo = halo;
+    c.log_len = ilog2(local_len);
+    c.shard = ShardMap{n_ranks, rank, log_block, 0};
+    c.alpha_from_state = 1;
+    CK(launch_cp(ctx->stream, cp_local, c, T->h.tab, 1, 0, (const ProofState*)state_dev));
+    ctx->launches += 1;
+    return ZK_OK;
+}
+
+int zk_shard_fold_dev(zk_ctx* ctx, const uint32_t* cur_local, uint64_t local_len, uint32_t layer_k, uint32_t log_N0,
+                      uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev, uint32_t* next_local)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!cur_local || !next_local || !state_dev || !is_pow2(local_len) || local_len < 2 || n_ranks == 0 || rank >= n_ranks || log_N0 > 30)
+        return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    if (n_ranks > 1 && (local_len >> 1) < ((uint64_t)1 << log_block))
+        return fail(ctx, ZK_ERR_INVALID, "a sharded fold needs at least two blocks per rank");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    int rc = get_tables(ctx, log_N0, &T);
+    if (rc) return rc;
+    FoldArgs f = make_fold_args(layer_k);
+    f.cur = cur_local;
+    f.beta_from_state = 1;
+    f.shard = ShardMap{n_ranks, rank, log_block, 0};
+    CK(launch_fold(ctx->stream, cur_local, next_local, ilog2(local_len) - 1, f, T->h.tab, 1, 0, (const ProofState*)state_dev));
+    ctx->launches += 1;
+    return ZK_OK;
+}
+
+// Replicated tail: layer `first_layer` (its tree already committed) is complete in layers_arena[0 .. N>>first_layer);
+// folds + trees + channel steps of layers first_layer+1 .. L follow, appended in the arenas.
+int zk_shard_fri_tail_dev(zk_ctx* ctx, uint32_t log_n, uint32_t first_layer, uint32_t* layers_arena, uint8_t* heaps_arena,
+                          void* state_dev, uint8_t* transcript_dev)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    const uint32_t L = log_n, log_N = log_n + LOG_BLOWUP;
+    if (!layers_arena || !heaps_arena || !state_dev || !transcript_dev || first_layer >= L) return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    if ((rc = get_tables(ctx, log_N, &T))) return rc;
+    TreeArgs a{};
+    a.state = (ProofState*)state_dev;
+    a.transcript = transcript_dev;
+    a.n_layers = L;
+    a.pow = T->h.tab;
+    int nl = 0;
+    size_t voff = 0, hoff = 0;
+    for (uint32_t i = first_layer + 1; i <= L; i++) {
+        const size_t prev_len = (size_t)1 << (log_N - (i - 1));
+        a.fold = make_fold_args(i - 1);
+        a.fold.cur = layers_arena + voff;
+        a.fold.log_half = log_N - i;
+        a.fold.beta_from_state = 1;
+        voff += prev_len;
+        hoff += 64 * prev_len;
+        a.vals = layers_arena + voff;
+        a.heap = heaps_arena + hoff;
+        a.log_size = log_N - i;
+        a.post = POST_FRI;
+        a.fri_layer = i;
+        CK(launch_merkle_tree(ctx->stream, SRC_FOLD, a, 1, &nl));
+    }
+    ctx->launches += nl;
+    return ZK_OK;
 }
 
 // ------------------------------------------------------------------ measurement support

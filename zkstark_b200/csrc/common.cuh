@@ -60,6 +60,22 @@ enum PostOp : int {
 
 enum SrcKind : int { SRC_VALUES = 0, SRC_DIGESTS = 1, SRC_FOLD = 2, SRC_CP = 3 };
 
+// Blocked-cyclic ownership of an evaluation array across ranks (single proof sharded over GPUs):
+// global index i lives on rank (i >> log_block) % n_ranks at local index
+//   ((i >> log_block) / n_ranks) << log_block | (i & (2^log_block - 1)).
+// Keeps every FRI fold (partner i + len/2) and the bottom log_block Merkle levels rank-local.
+struct ShardMap {
+    uint32_t n_ranks;    // 0 or 1: not sharded
+    uint32_t rank;
+    uint32_t log_block;
+    uint32_t pad;
+};
+__host__ __device__ inline uint32_t shard_global(const ShardMap& m, uint32_t local)
+{
+    if (m.n_ranks <= 1) return local;
+    return ((((local >> m.log_block) * m.n_ranks) + m.rank) << m.log_block) | (local & ((1u << m.log_block) - 1u));
+}
+
 // Fused leaf sources.  `vals` is where leaf values live (or are produced into).
 struct FoldArgs {           // polynomial.rs:385-400 + prover.rs:204-211 in evaluation form
     const uint32_t* cur;    // layer k, len = 2*half (batch stride cur_stride)
@@ -70,6 +86,7 @@ struct FoldArgs {           // polynomial.rs:385-400 + prover.rs:204-211 in eval
     uint32_t inv2_m;        // Montgomery form of 2^-1
     int beta_from_state;    // read beta_raw[layer_k] from ProofState, else use beta_raw below
     uint32_t beta_raw;
+    ShardMap shard;         // local -> global index (domain point) when the layer is sharded
 };
 struct CpArgs {             // prover.rs:101-173 pointwise
     const uint32_t* f;      // f_eval, N values (batch stride f_stride)
@@ -80,6 +97,9 @@ struct CpArgs {             // prover.rs:101-173 pointwise
     int alpha_from_state;
     uint32_t alpha_raw[3];
     uint32_t a_first, a_last;  // used when !alpha_from_state (stand-alone API)
+    ShardMap shard;            // sharded: f is the rank-local array, x comes from the global index
+    const uint32_t* halo;      // sharded: first 16 values of the block that follows each local block
+    uint32_t log_len;          // log2 of the number of local points (== log_N when not sharded)
 };
 
 struct TreeArgs {
@@ -104,6 +124,10 @@ struct TreeArgs {
 // ---- launchers (tree.cu)
 // Builds the whole tree over 2^log_size leaves taken from `src_kind`, per proof of the batch.
 cudaError_t launch_merkle_tree(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, int* n_launches);
+// levels log_size .. stop_level only (no top kernel, no channel step): used for the rank-local block subtrees
+cudaError_t launch_merkle_partial(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, uint32_t stop_level, int* n_launches);
+// upper part of a tree whose level `in_level` digests are already in the heap: digest passes + top (+ channel)
+cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int* n_launches);
 // the leaf pass alone (bench support): a.in_level / a.k preset by the caller
 cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant);
 cudaError_t sha_init_constants();
@@ -118,9 +142,10 @@ cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* tr
                               uint32_t log_n, uint32_t batch);
 // stand-alone element-wise stages (stages in isolation, for the per-function C-ABI)
 cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uint32_t log_half,
-                        FoldArgs f, PowTab pow, uint32_t batch, uint64_t next_stride);
+                        FoldArgs f, PowTab pow, uint32_t batch, uint64_t next_stride, const ProofState* st = nullptr);
 cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch,
-                      uint64_t out_stride);
+                      uint64_t out_stride, const ProofState* st = nullptr);
+cudaError_t launch_state_set(cudaStream_t s, ProofState* st, uint32_t a_first, uint32_t a_last);
 
 // offsets inside the bincode transcript (channel.rs:19-26 appends in commit order)
 inline size_t tr_off_alpha() { return 32; }

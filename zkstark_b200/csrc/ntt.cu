@@ -35,6 +35,7 @@ struct NttPassArgs {
     PowTab wpow;         // powers of 5, exponents < 2^wpow.log_N
     uint32_t log_R1;     // final pass: first-pass radix (0 when single pass)
     uint32_t log_Q2;     // final pass: second-pass radix (0 unless three passes)
+    uint32_t coset_base; // index of the first coset of this launch (sharded LDE: one coset per launch)
 };
 
 constexpr int NTT_MAX_THREADS = 1024;  // block size is chosen per radix: 32 * clamp(R/16, 2, 32)
@@ -108,6 +109,7 @@ __device__ __forceinline__ void cta_dif(uint32_t* sm, const uint32_t* tws, uint3
 __device__ __forceinline__ uint32_t coset_scale(const NttPassArgs& a, uint32_t c, uint32_t k, uint32_t r)
 {
     uint32_t v = mont_mul(c, pw(a.wpow, k));
+    r += a.coset_base;
     if (r) v = mont_mul(v, pw(a.hpow, (uint32_t)(((uint64_t)r * k) & ((1u << a.hpow.log_N) - 1u))));
     return v;
 }
@@ -301,7 +303,7 @@ static cudaError_t set_smem(const void* fn, size_t bytes)
 static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint32_t n_cosets, bool coset_scale,
                            bool inverse, const uint32_t* coeffs, uint64_t coeffs_stride, uint32_t* work,
                            uint64_t work_stride, uint32_t* dst, uint64_t dst_stride, bool use_scale,
-                           uint32_t scale_m, uint32_t batch, int* n_launches)
+                           uint32_t scale_m, uint32_t batch, int* n_launches, uint32_t coset_base = 0)
 {
     uint32_t log_arrays = 0;
     while ((1u << log_arrays) < n_cosets * batch) log_arrays++;
@@ -312,6 +314,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     a.inverse = inverse;
     a.hpow = T.hpow;
     a.wpow = T.wpow;
+    a.coset_base = coset_base;
     const uint32_t* twb = inverse ? T.tw_inv : T.tw_fwd;
     uint32_t log_S = mu;
     cudaError_t e;
@@ -402,6 +405,15 @@ cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* t
     NttTables T{tw_fwd, tw_inv, hpow, wpow};
     return run_ntt(s, T, log_n, 1u << LOG_BLOWUP, true, false, coeffs, coeffs_stride, work, work_stride, evals,
                    evals_stride, false, 0, batch, n_launches);
+}
+
+// One coset of the LDE on its own: out[j] = f(5 h^(8 j + r)), j < n (sharded LDE: ranks split the cosets).
+cudaError_t launch_lde_one_coset(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
+                                 uint32_t log_n, uint32_t r, const uint32_t* coeffs, uint32_t* work, uint32_t* out,
+                                 int* n_launches)
+{
+    NttTables T{tw_fwd, tw_inv, hpow, wpow};
+    return run_ntt(s, T, log_n, 1, true, false, coeffs, 0, work, 0, out, 0, false, 0, 1, n_launches, r);
 }
 
 }  // namespace zk

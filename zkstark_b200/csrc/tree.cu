@@ -39,7 +39,8 @@ __device__ __forceinline__ void fold_chunk(const FoldArgs& f, const PowTab& pw, 
     const uint32_t beta_m = to_mont(reduce_u32(beta_raw));                // field.rs:20-24
     const uint32_t cb_m = mont_mul(beta_m, f.winv2k_m);                   // beta * 5^-(2^k)
     const uint32_t step_m = pow_h_m(pw, (N - (1u << f.layer_k)) & (N - 1));  // h^-(2^k)
-    uint32_t e = (N - ((base << f.layer_k) & (N - 1))) & (N - 1);
+    const uint32_t gbase = shard_global(f.shard, base);                   // chunks never straddle a shard block
+    uint32_t e = (N - ((gbase << f.layer_k) & (N - 1))) & (N - 1);
     uint32_t t_m = mont_mul(cb_m, pow_h_m(pw, e));                        // beta * x_base^-1
     uint32_t u[C], v[C];
     if (C >= 4) {
@@ -83,9 +84,12 @@ __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, cons
                                          uint32_t* out, uint32_t base, const uint32_t al_m[3],
                                          uint32_t a_first, uint32_t a_last)
 {
-    const uint32_t N = 1u << pw.log_N, B = 1u << LOG_BLOWUP;
+    const uint32_t B = 1u << LOG_BLOWUP;
+    const uint32_t len_mask = (1u << c.log_len) - 1u;
+    const bool sharded = c.shard.n_ranks > 1 || c.halo != nullptr;
+    const uint32_t blk_mask = (1u << c.shard.log_block) - 1u;
     const uint32_t h_m = pow_h_m(pw, 1);
-    uint32_t x = mont_mul(GEN, pow_h_m(pw, base));  // canonical 5 h^base
+    uint32_t x = mont_mul(GEN, pow_h_m(pw, shard_global(c.shard, base)));  // canonical 5 h^i, i global
     uint32_t xs[C], den[2 * C], pre[2 * C];
     uint32_t acc = R1;  // Montgomery 1
 #pragma unroll
@@ -109,7 +113,16 @@ __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, cons
 #pragma unroll
     for (int j = 0; j < C; j++) {
         uint32_t i = base + j;
-        uint32_t fx = f[i], fgx = f[(i + B) & (N - 1)], fggx = f[(i + 2 * B) & (N - 1)];
+        uint32_t fx = f[i], fgx, fggx;
+        if (!sharded) {
+            fgx = f[(i + B) & len_mask];
+            fggx = f[(i + 2 * B) & len_mask];
+        } else {
+            // inside the local block, else in the 16-value head of the block that follows it globally
+            const uint32_t t = i & blk_mask, bl = i >> c.shard.log_block;
+            fgx = (t + B <= blk_mask) ? f[i + B] : c.halo[bl * 16 + (t + B - blk_mask - 1)];
+            fggx = (t + 2 * B <= blk_mask) ? f[i + 2 * B] : c.halo[bl * 16 + (t + 2 * B - blk_mask - 1)];
+        }
         uint32_t p0 = mont_mul(fsub(fx, a_first), inv_m[2 * j]);
         uint32_t p1 = mont_mul(fsub(fx, a_last), inv_m[2 * j + 1]);
         uint32_t fx_m = to_mont(fx), fgx_m = to_mont(fgx);
@@ -371,32 +384,35 @@ __global__ void __launch_bounds__(TOP_THREADS) tree_top_kernel(const TreeArgs a)
 
 // ---------------------------------------------------------------- stand-alone stage kernels
 __global__ void __launch_bounds__(256) fold_kernel(const uint32_t* cur, uint32_t* next, FoldArgs f, PowTab pw,
-                                                   uint64_t next_stride)
+                                                   uint64_t next_stride, const ProofState* st)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t half = 1u << f.log_half;
     const uint32_t* c = cur + (size_t)b * f.cur_stride;
     uint32_t* o = next + (size_t)b * next_stride;
+    const uint32_t beta = (f.beta_from_state && st) ? st[b].beta_raw[f.layer_k] : f.beta_raw;
     if (half >= 4) {
         uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
-        if (base < half) fold_chunk<4>(f, pw, c, o, base, f.beta_raw);
+        if (base < half) fold_chunk<4>(f, pw, c, o, base, beta);
     } else {
         uint32_t base = blockIdx.x * 256 + threadIdx.x;
-        if (base < half) fold_chunk<1>(f, pw, c, o, base, f.beta_raw);
+        if (base < half) fold_chunk<1>(f, pw, c, o, base, beta);
     }
 }
 
-__global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab pw, uint64_t out_stride)
+__global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab pw, uint64_t out_stride,
+                                                 const ProofState* st)
 {
     const uint32_t b = blockIdx.y;
-    const uint32_t N = 1u << pw.log_N;
+    const uint32_t N = 1u << c.log_len;
     const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (base >= N) return;
     uint32_t al_m[3];
+    const bool from_state = c.alpha_from_state && st;
 #pragma unroll
-    for (int j = 0; j < 3; j++) al_m[j] = to_mont(reduce_u32(c.alpha_raw[j]));
+    for (int j = 0; j < 3; j++) al_m[j] = to_mont(reduce_u32(from_state ? st[b].alpha_raw[j] : c.alpha_raw[j]));
     cp_chunk<4>(c, pw, c.f + (size_t)b * c.f_stride, out + (size_t)b * out_stride, base, al_m,
-                reduce_u32(c.a_first), reduce_u32(c.a_last));
+                reduce_u32(from_state ? st[b].a_first : c.a_first), reduce_u32(from_state ? st[b].a_last : c.a_last));
 }
 
 // ---------------------------------------------------------------- decommit gather (prover.rs:263-289)
@@ -572,6 +588,72 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
     return e;
 }
 
+cudaError_t launch_merkle_partial(cudaStream_t s, int src, TreeArgs a, uint32_t batch, uint32_t stop_level, int* n_launches)
+{
+    if (a.log_size <= stop_level) return cudaErrorInvalidValue;
+    cudaError_t e = cudaSuccess;
+    int launches = 0;
+    a.in_level = a.log_size;
+    a.post = POST_NONE;
+    const uint32_t lb = ilog2(batch);
+    int k = (int)a.log_size + (int)lb - 18;
+    if (k < 1) k = 1;
+    if (k > 5) k = 5;
+    if (k > (int)(a.log_size - stop_level)) k = a.log_size - stop_level;
+    a.k = k;
+    switch (src) {
+        case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
+        case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
+        case SRC_CP: e = launch_pass<SRC_CP>(s, a, batch); break;
+        default: return cudaErrorInvalidValue;
+    }
+    launches++;
+    a.in_level -= k;
+    while (e == cudaSuccess && a.in_level > stop_level) {
+        uint32_t rem = a.in_level - stop_level;
+        int kk = (int)a.in_level + (int)lb - 18;   // still plenty of subtrees: keep several levels per thread
+        if (kk < 1) kk = 1;
+        if (kk > 5) kk = 5;
+        a.k = rem < (uint32_t)kk ? rem : (uint32_t)kk;
+        e = launch_pass<SRC_DIGESTS>(s, a, batch);
+        launches++;
+        a.in_level -= a.k;
+    }
+    if (n_launches) *n_launches += launches;
+    return e;
+}
+
+cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int* n_launches)
+{
+    cudaError_t e = cudaSuccess;
+    int launches = 0;
+    while (a.in_level > TOP_LOG) {
+        uint32_t rem = a.in_level - TOP_LOG;
+        a.k = rem >= 2 ? 2 : 1;
+        e = launch_pass<SRC_DIGESTS>(s, a, batch);
+        launches++;
+        if (e != cudaSuccess) return e;
+        a.in_level -= a.k;
+    }
+    e = launch_top<SRC_DIGESTS>(s, a, batch);
+    launches++;
+    if (n_launches) *n_launches += launches;
+    return e;
+}
+
+__global__ void state_set_kernel(ProofState* st, uint32_t a_first, uint32_t a_last)
+{
+    uint32_t* w = reinterpret_cast<uint32_t*>(st);
+    for (int i = 0; i < 64; i++) w[i] = 0;
+    st->a_first = a_first;
+    st->a_last = a_last;
+}
+cudaError_t launch_state_set(cudaStream_t s, ProofState* st, uint32_t a_first, uint32_t a_last)
+{
+    state_set_kernel<<<1, 1, 0, s>>>(st, a_first, a_last);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant)
 {
     uint32_t n_threads = 1u << (a.in_level - a.k);
@@ -649,21 +731,23 @@ cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* tr
 }
 
 cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uint32_t log_half, FoldArgs f,
-                        PowTab pow, uint32_t batch, uint64_t next_stride)
+                        PowTab pow, uint32_t batch, uint64_t next_stride, const ProofState* st)
 {
     uint32_t half = 1u << log_half;
     uint32_t work = half >= 4 ? half / 4 : half;
     dim3 grid((work + 255) / 256, batch);
     f.log_half = log_half;
-    fold_kernel<<<grid, 256, 0, s>>>(cur, next, f, pow, next_stride);
+    fold_kernel<<<grid, 256, 0, s>>>(cur, next, f, pow, next_stride, st);
     return cudaGetLastError();
 }
 
-cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch, uint64_t out_stride)
+cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch, uint64_t out_stride,
+                      const ProofState* st)
 {
-    uint32_t N = 1u << pow.log_N;
+    if (c.log_len == 0) c.log_len = pow.log_N;
+    uint32_t N = 1u << c.log_len;
     dim3 grid((N / 4 + 255) / 256, batch);
-    cp_kernel<<<grid, 256, 0, s>>>(cp_out, c, pow, out_stride);
+    cp_kernel<<<grid, 256, 0, s>>>(cp_out, c, pow, out_stride, st);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,319 @@
+"""One FibonacciSq proof sharded over several GPUs (BASELINE configs[4]).
+
+SPMD, one process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch) for the exchanges, the C-ABI
+`zk_shard_*_dev` kernels for all field / hash work.  The transcript is byte-identical to the single-GPU one.
+
+Layout.  Ranks first split the LDE by COSET (f_eval[8j+r] = NTT_n(c_k (5 h^r)^k)[j]: eight independent
+size-n transforms, no communication inside a transform); ONE all-to-all then re-owns the evaluations
+blocked-cyclically: global index i -> rank (i >> log_block) % G.  With that ownership
+  * every FRI fold pairs i with i + len/2 on the same rank (no exchange per layer),
+  * the bottom log_block levels of every Merkle tree are rank-local; only the block roots travel
+    (all-gather of len/2^log_block digests), the small upper tree and the Fiat-Shamir step run replicated
+    on every rank's device, so all ranks draw identical challenges without a host round trip,
+  * the composition polynomial needs a 16-value halo per block (all-gather of block heads).
+When a layer no longer has two blocks per rank it is all-gathered and the tail of FRI runs replicated.
+
+The same code runs G "virtual ranks" inside one process on one GPU (LocalComm) -- that is how the single-GPU
+test tier covers the multi-rank logic; TorchComm is the real multi-process path.
+"""
+import hashlib
+import struct
+
+import numpy as np
+
+P = 3221225473
+POST_NONE, POST_F, POST_CP, POST_FRI = 0, 1, 2, 3
+
+
+class LocalComm:
+    """G virtual ranks in one process: collectives are tensor shuffles on one device."""
+
+    def __init__(self, world_size):
+        self.world_size = world_size
+        self.my_ranks = list(range(world_size))
+
+    def all_to_all(self, send):  # send[r]: tensor whose dim 0 is split evenly by destination
+        import torch
+        G = self.world_size
+        chunks = [s.chunk(G, dim=0) for s in send]
+        return [torch.cat([chunks[src][dst] for src in range(G)], dim=0) for dst in range(G)]
+
+    def all_gather(self, xs):  # -> per local rank: tensor [G, ...]
+        import torch
+        full = torch.stack(list(xs), dim=0)
+        return [full for _ in xs]
+
+    def all_gather_object(self, objs):
+        return [list(objs) for _ in objs]
+
+
+class TorchComm:
+    """One real rank per process (torch.distributed already initialised, NCCL on GPUs)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.my_ranks = [dist.get_rank(group)]
+
+    def all_to_all(self, send):
+        import torch
+        out = torch.empty_like(send[0])
+        self.dist.all_to_all_single(out, send[0].contiguous(), group=self.group)
+        return [out]
+
+    def all_gather(self, xs):
+        import torch
+        x = xs[0].contiguous()
+        out = torch.empty((self.world_size,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        self.dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group)
+        return [out]
+
+    def all_gather_object(self, objs):
+        out = [None] * self.world_size
+        self.dist.all_gather_object(out, objs[0], group=self.group)
+        return [out]
+
+
+class _Tree:
+    """One committed layer on one rank: local values, local heap (bottom levels), replicated upper heap."""
+    def __init__(self, vals, heap, upper, length, distributed):
+        self.vals, self.heap, self.upper, self.length, self.distributed = vals, heap, upper, length, distributed
+
+
+class ShardedProver:
+    def __init__(self, ctx, log_n, comm, log_block=10, device=None):
+        import torch
+        self.torch = torch
+        self.ctx, self.k, self.comm, self.lb = ctx, log_n, comm, log_block
+        self.G = comm.world_size
+        self.log_N = log_n + 3
+        self.N = 1 << self.log_N
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        if self.G not in (1, 2, 4, 8):
+            raise ValueError("world size must be 1, 2, 4 or 8 (the LDE has 8 cosets)")
+        if log_block < 5 or (self.N // self.G) < (1 << (log_block + 1)):
+            raise ValueError("proof too small to shard: need at least two blocks per rank")
+        self.comm_bytes = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _i32(self, *shape):
+        return self.torch.empty(shape, dtype=self.torch.int32, device=self.dev)
+
+    def _u8(self, *shape):
+        return self.torch.empty(shape, dtype=self.torch.uint8, device=self.dev)
+
+    def _commit_tree(self, vals_by_rank, length, post, fri_layer, states, transcripts):
+        """Distributed Merkle tree of a layer of global length `length`; returns per-rank _Tree."""
+        t, lb, G = self.torch, self.lb, self.G
+        local_len = length // G
+        nbl = local_len >> lb
+        nbt = length >> lb
+        heaps, roots = [], []
+        for idx, r in enumerate(self.comm.my_ranks):
+            heap = self._u8(32 * (2 * local_len - 1))
+            self.ctx.shard_merkle_blocks(vals_by_rank[idx].data_ptr(), local_len, lb, heap.data_ptr())
+            heaps.append(heap)
+            roots.append(heap[32 * (nbl - 1): 32 * (2 * nbl - 1)].view(nbl, 32))
+        gathered = self.comm.all_gather(roots)           # [G, nbl, 32] on every rank
+        self.comm_bytes += 32 * nbt
+        trees = []
+        log_nbt = nbt.bit_length() - 1
+        for idx, r in enumerate(self.comm.my_ranks):
+            upper = self._u8(32 * (2 * nbt - 1))
+            upper[32 * (nbt - 1):] = gathered[idx].permute(1, 0, 2).reshape(-1)   # global block b = bl*G + g
+            self.ctx.shard_upper_tree(upper.data_ptr(), log_nbt, post, fri_layer, self.k,
+                                      states[idx].data_ptr(), transcripts[idx].data_ptr())
+            trees.append(_Tree(vals_by_rank[idx], heaps[idx], upper, length, True))
+        return trees
+
+    # ------------------------------------------------------------------ the proof
+    def prove(self, trace):
+        """trace: numpy uint32 array of 2^k - 1 values (identical on every rank).  Returns (transcript, state)."""
+        t, ctx, k, lb, G = self.torch, self.ctx, self.k, self.lb, self.G
+        n, N, log_N = 1 << k, self.N, self.log_N
+        ranks = self.comm.my_ranks
+        nr = len(ranks)
+        tl = ctx_transcript_len(k)
+        trace = np.ascontiguousarray(trace, dtype=np.uint32)
+        assert len(trace) == n - 1
+        self.comm_bytes = 0
+
+        states = [t.zeros(64, dtype=t.int32, device=self.dev) for _ in ranks]
+        transcripts = [t.zeros(tl + 64, dtype=t.uint8, device=self.dev) for _ in ranks]
+        for i in range(nr):
+            ctx.shard_state_init(states[i].data_ptr(), int(trace[0]), int(trace[n - 2]))
+
+        # Part 1a: interpolation, replicated (1/8 of the transform work)
+        y = self._i32(n)
+        y.zero_()
+        y[: n - 1] = t.from_numpy(trace.view(np.int32)).to(self.dev)
+        coeffs = self._i32(n)
+        ctx.interpolate_subgroup_dev(y.data_ptr(), n - 1, k, coeffs.data_ptr())
+        # Part 1b: LDE, cosets split over ranks, then the all-to-all that re-owns the evaluations by blocks
+        C_ = 8 // G
+        jb = 1 << (lb - 3)                       # j-values per block (a block holds all 8 cosets of jb points)
+        nbl = (N // G) >> lb                     # blocks per rank
+        work = self._i32(n)
+        send = []
+        for r in ranks:
+            E = self._i32(C_, n)
+            for c in range(C_):
+                ctx.shard_lde_coset(coeffs.data_ptr(), k, r + c * G, work.data_ptr(), E[c].data_ptr())
+            # E[c][j], j = ((bl*G + d) * jb + tt)  ->  send[d][c][bl][tt]
+            send.append(E.view(C_, nbl, G, jb).permute(2, 0, 1, 3).contiguous())
+        recv = self.comm.all_to_all(send)
+        self.comm_bytes += 4 * N * (G - 1) // G
+        f_local = []
+        for idx in range(nr):
+            # recv[g][c][bl][tt] -> f_local[bl][tt][r = c*G + g]
+            f_local.append(recv[idx].view(G, C_, nbl, jb).permute(2, 3, 1, 0).contiguous().view(-1))
+        del send, recv, work
+        f_trees = self._commit_tree(f_local, N, POST_F, 0, states, transcripts)
+
+        # Part 2: composition polynomial (needs f at i, i+8, i+16: 16-value halo per block)
+        heads = [f.view(nbl, 1 << lb)[:, :16].contiguous() for f in f_local]
+        heads_all = self.comm.all_gather(heads)  # [G, nbl, 16]
+        self.comm_bytes += 4 * 16 * (N >> lb)
+        cp_local = []
+        for idx, r in enumerate(ranks):
+            if r + 1 < G:
+                halo = heads_all[idx][r + 1].contiguous()
+            else:
+                halo = t.roll(heads_all[idx][0], shifts=-1, dims=0).contiguous()   # block b+1 wraps to rank 0, next bl
+            cp = self._i32(N // G)
+            ctx.shard_cp(f_local[idx].data_ptr(), halo.data_ptr(), N // G, k, G, r, lb, states[idx].data_ptr(), cp.data_ptr())
+            cp_local.append(cp)
+        layers = [self._commit_tree(cp_local, N, POST_CP, 0, states, transcripts)]
+
+        # Part 3: FRI.  Folds stay rank-local while a layer has >= 2 blocks per rank.
+        cur, length, i = cp_local, N, 0
+        while (length // G) >= (2 << lb):
+            nxt = []
+            for idx, r in enumerate(ranks):
+                o = self._i32(length // G // 2)
+                ctx.shard_fold(cur[idx].data_ptr(), length // G, i, log_N, G, r, lb, states[idx].data_ptr(), o.data_ptr())
+                nxt.append(o)
+            i += 1
+            length //= 2
+            layers.append(self._commit_tree(nxt, length, POST_FRI, i, states, transcripts))
+            cur = nxt
+        # replicated tail: gather layer i (one block per rank) and finish on every rank
+        first_tail = i
+        full = self.comm.all_gather([c.view(-1, 1 << lb) for c in cur])     # [G, nbl=1, blk]
+        self.comm_bytes += 4 * length
+        tails = []
+        for idx in range(nr):
+            arena_vals = self._i32(2 * length)
+            arena_heaps = self._u8(64 * 2 * length)
+            arena_vals[:length] = full[idx].permute(1, 0, 2).reshape(-1)
+            ctx.shard_fri_tail(k, first_tail, arena_vals.data_ptr(), arena_heaps.data_ptr(),
+                               states[idx].data_ptr(), transcripts[idx].data_ptr())
+            tails.append((arena_vals, arena_heaps))
+        ctx.synchronize()
+
+        # Part 4: decommit.  Owners read values + local sibling digests; everybody assembles the same bytes.
+        results = []
+        st_host = [s.cpu().numpy().view(np.uint32) for s in states]
+        q_raw = int(st_host[0][44])
+        x = q_raw % (N - 16)
+        wanted = [("f", x), ("f", x + 8), ("f", x + 16), ("l0", x)]
+        for li in range(0, first_tail + 1):
+            ln = N >> li
+            wanted += [(f"l{li}", x % ln), (f"l{li}", (x % ln + ln // 2) % ln)]
+        contrib = []
+        for idx, r in enumerate(ranks):
+            mine = {}
+            for name, gi in wanted:
+                tree = f_trees[idx] if name == "f" else layers[int(name[1:])][idx]
+                b = gi >> lb
+                if b % G != r:
+                    continue
+                loc = ((b // G) << lb) | (gi & ((1 << lb) - 1))
+                mine[(name, gi)] = (int(tree.vals[loc].item()) & 0xFFFFFFFF, self._local_path(tree, loc))
+            contrib.append(mine)
+        everyone = self.comm.all_gather_object(contrib)
+        for idx, r in enumerate(ranks):
+            merged = {}
+            for d in everyone[idx]:
+                merged.update(d)
+            tr = bytearray(transcripts[idx][:tl].cpu().numpy().tobytes())
+            off = 84 + 36 * k
+
+            def full_path(name, gi):
+                tree = f_trees[idx] if name == "f" else layers[int(name[1:])][idx]
+                val, low = merged[(name, gi)]
+                return val, low + self._upper_path(tree, gi >> lb)
+
+            def tail_entry(li, gi):
+                vals, heaps = tails[idx]
+                voff = sum((N >> j) for j in range(first_tail, li))
+                hoff = sum(64 * (N >> j) for j in range(first_tail, li))
+                ln = N >> li
+                val = int(vals[voff + gi].item()) & 0xFFFFFFFF
+                heap = heaps[hoff: hoff + 32 * (2 * ln - 1)].view(-1, 32)
+                path, node = [], gi + ln - 1
+                sib = []
+                while node != 0:
+                    sib.append(node - 1 if node % 2 == 0 else node + 1)
+                    node = (node - 1) >> 1
+                got = heap[self.torch.tensor(sib, device=self.dev, dtype=self.torch.long)].cpu().numpy()
+                return val, [bytes(g) for g in got]
+
+            for name, gi in wanted[:4]:
+                val, path = full_path(name, gi)
+                rec = struct.pack("<IQ", val, len(path)) + b"".join(path)
+                tr[off: off + len(rec)] = rec
+                off += len(rec)
+            for li in range(k):
+                ln = N >> li
+                xi, nx = x % ln, (x % ln + ln // 2) % ln
+                if li <= first_tail:
+                    (v0, p0), (v1, p1) = full_path(f"l{li}", xi), full_path(f"l{li}", nx)
+                else:
+                    (v0, p0), (v1, p1) = tail_entry(li, xi), tail_entry(li, nx)
+                rec = struct.pack("<IIQ", v0, v1, len(p0)) + b"".join(p0) + struct.pack("<Q", len(p1)) + b"".join(p1)
+                tr[off: off + len(rec)] = rec
+                off += len(rec)
+            assert off == tl, (off, tl)
+            # channel.rs:19-26 over the decommitment records (host; ~k + 4 sequential hashes)
+            state = b"".join(struct.pack(">I", int(w)) for w in st_host[idx][47:55])
+            o2 = 84 + 36 * k
+            for rr in range(4 + k):
+                ln_rec = 12 + 32 * log_N if rr < 4 else 24 + 64 * (log_N - (rr - 4))
+                state = hashlib.sha256(state + bytes(tr[o2: o2 + ln_rec])).digest()
+                o2 += ln_rec
+            results.append((bytes(tr), state))
+        self.first_tail_layer = first_tail
+        return results[0] if nr == 1 else results
+
+    def _local_path(self, tree, loc):
+        """Sibling digests of the bottom log_block levels, from the rank-local heap (merkle.rs:54-71 order)."""
+        local_len = tree.length // self.G
+        node = loc + local_len - 1
+        sib = []
+        for _ in range(self.lb):
+            sib.append(node - 1 if node % 2 == 0 else node + 1)
+            node = (node - 1) >> 1
+        heap = tree.heap.view(-1, 32)
+        got = heap[self.torch.tensor(sib, device=self.dev, dtype=self.torch.long)].cpu().numpy()
+        return [bytes(g) for g in got]
+
+    def _upper_path(self, tree, block):
+        nbt = tree.length >> self.lb
+        node = block + nbt - 1
+        sib = []
+        while node != 0:
+            sib.append(node - 1 if node % 2 == 0 else node + 1)
+            node = (node - 1) >> 1
+        if not sib:
+            return []
+        heap = tree.upper.view(-1, 32)
+        got = heap[self.torch.tensor(sib, device=self.dev, dtype=self.torch.long)].cpu().numpy()
+        return [bytes(g) for g in got]
+
+
+def ctx_transcript_len(k):
+    from ._binding import transcript_len
+    return transcript_len(k)
