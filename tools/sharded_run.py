@@ -46,7 +46,7 @@ with torch.cuda.stream(s):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ok = None
     if rank == 0:
-        if k <= 22:
+        if k <= 24:
             c1 = zk.Context(local)
             tr1, st1 = c1.prove_fibsq_from_trace(k, trace)
             ok = bool(tr1 == tr and st1 == st)
