@@ -344,6 +344,11 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
     CK(launch_decommit(s, log_n, f_eval, N, (const uint8_t*)ctx->f_heap.p, 64 * N, layers, 2 * N,
                        (const uint8_t*)ctx->layer_heaps.p, 128 * N, states, trd, trs, nb));
     nl++;
+    const bool device_tail = nb >= 8;  // the sequential channel tail: per-proof threads on the device, or the host
+    if (device_tail) {
+        CK(launch_chan_tail(s, states, trd, trs, log_n, nb));
+        nl++;
+    }
     tm.mark();
     uint8_t* pin_tr = (uint8_t*)ctx->pinned;
     ProofState* pin_st = (ProofState*)(pin_tr + trs * nb);
@@ -359,7 +364,16 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
         if (pin_st[b].pad[0] != 0)
             return fail(ctx, ZK_ERR_ASSERT, "last FRI layer is not constant (prover.rs:238)");
         memcpy(transcripts_out + trl * b, pin_tr + trs * b, trl);
-        finish_channel_host(log_n, pin_st[b], pin_tr + trs * b, states_out + 32 * (size_t)b);
+        if (device_tail) {
+            uint8_t* so = states_out + 32 * (size_t)b;
+            for (int i = 0; i < 8; i++) {
+                uint32_t wv = pin_st[b].chan[i];
+                so[4 * i] = (uint8_t)(wv >> 24); so[4 * i + 1] = (uint8_t)(wv >> 16);
+                so[4 * i + 2] = (uint8_t)(wv >> 8); so[4 * i + 3] = (uint8_t)wv;
+            }
+        } else {
+            finish_channel_host(log_n, pin_st[b], pin_tr + trs * b, states_out + 32 * (size_t)b);
+        }
     }
     return ZK_OK;
 }

@@ -145,6 +145,8 @@ cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uin
                         FoldArgs f, PowTab pow, uint32_t batch, uint64_t next_stride, const ProofState* st = nullptr);
 cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch,
                       uint64_t out_stride, const ProofState* st = nullptr);
+cudaError_t launch_chan_tail(cudaStream_t s, ProofState* states, const uint8_t* transcripts, uint64_t stride,
+                             uint32_t log_n, uint32_t batch);
 cudaError_t launch_state_set(cudaStream_t s, ProofState* st, uint32_t a_first, uint32_t a_last);
 
 // offsets inside the bincode transcript (channel.rs:19-26 appends in commit order)

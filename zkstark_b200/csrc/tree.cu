@@ -504,6 +504,58 @@ __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
     }
 }
 
+// channel.rs:19-26 over the decommitment records (prover.rs:274-288), one THREAD per proof: 4 + L sequential
+// commits, each state = SHA256(state || record).  Used for batches (the chains of all proofs advance in
+// parallel); for a single proof the host does the same ~340 compressions faster than one GPU thread.
+__device__ __forceinline__ uint32_t tail_word(const uint32_t st[8], const uint32_t* rec, uint32_t nw, uint32_t i,
+                                              uint32_t last, uint32_t bits)
+{
+    if (i < 8) return st[i];
+    if (i < nw) return sha::bswap32(rec[i - 8]);
+    if (i == nw) return 0x80000000u;
+    if (i == last) return bits;  // message < 2^29 bytes: the high length word is 0
+    return 0u;
+}
+__global__ void __launch_bounds__(32) chan_tail_kernel(ProofState* states, const uint8_t* transcripts, uint64_t stride,
+                                                       uint32_t log_n, uint32_t batch)
+{
+    const uint32_t b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= batch) return;
+    const uint32_t L = log_n, log_N = log_n + LOG_BLOWUP;
+    ProofState* ps = states + b;
+    const uint8_t* tr = transcripts + (size_t)b * stride;
+    uint32_t st[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = ps->chan_at_query[i];
+    size_t off = 84 + 36 * (size_t)L;
+    for (uint32_t r = 0; r < 4 + L; r++) {
+        const uint32_t len = r < 4 ? 12 + 32 * log_N : 24 + 64 * (log_N - (r - 4));
+        const uint32_t* rec = reinterpret_cast<const uint32_t*>(tr + off);
+        const uint32_t nw = 8 + len / 4;                 // message words (state || record)
+        const uint32_t n_blocks = (nw + 3 + 15) / 16;    // + 0x80 word + 64-bit length
+        const uint32_t last = 16 * n_blocks - 1, bits = 32 * nw;
+        uint32_t out[8];
+        sha::init_iv(out);
+        for (uint32_t blk = 0; blk < n_blocks; blk++) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) w[j] = tail_word(st, rec, nw, 16 * blk + j, last, bits);
+            sha::compress<0>(out, w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[i] = out[i];
+        off += len;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) ps->chan[i] = st[i];
+}
+cudaError_t launch_chan_tail(cudaStream_t s, ProofState* states, const uint8_t* transcripts, uint64_t stride,
+                             uint32_t log_n, uint32_t batch)
+{
+    chan_tail_kernel<<<(batch + 31) / 32, 32, 0, s>>>(states, transcripts, stride, log_n, batch);
+    return cudaGetLastError();
+}
+
 // channel.rs:12-17 + public inputs: zero state, a[0], a[n-2]
 __global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64_t trace_stride,
                                   uint32_t log_n, uint32_t batch)
