@@ -39,7 +39,8 @@ typedef enum zk_status {
     ZK_ERR_CUDA = -2,    /* CUDA runtime error, see zk_last_error */
     ZK_ERR_NOMEM = -3,   /* device or host allocation failed */
     ZK_ERR_BUFFER = -4,  /* caller buffer too small */
-    ZK_ERR_ASSERT = -5   /* an inline assert of the reference failed (e.g. prover.rs:42) */
+    ZK_ERR_ASSERT = -5,  /* an inline assert of the reference failed (e.g. prover.rs:42) */
+    ZK_ERR_VERIFY = -6   /* zk_verify_fibsq: the proof was rejected */
 } zk_status;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -104,6 +105,16 @@ int zk_prove_fibsq_from_trace(zk_ctx *ctx, uint32_t log_n, const uint32_t *trace
  * Internally processed in device-resident sub-batches sized to the ctx memory budget. */
 int zk_prove_fibsq_batch(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t *traces,
                          uint8_t *transcripts_out, uint8_t *states_out);
+/* same as zk_prove_fibsq_batch but from the secrets: the traces (prover.rs:32-39) are generated on the device,
+ * one thread per proof -- for batches the sequential host recurrence would otherwise dominate */
+int zk_prove_fibsq_batch_secrets(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t *secrets,
+                                 uint8_t *transcripts_out, uint8_t *states_out);
+/* Proof::verify (proof.rs:15-149) generalised to n = 2^log_n; host code, no GPU needed.  a_last = a[n-2] is the
+ * public input (2338775057 in the reference, proof.rs:70).  Returns ZK_OK or ZK_ERR_VERIFY with *failed_check set
+ * to the proof.rs line of the assert that would have fired.  rederive != 0 additionally replays the channel and
+ * checks alpha / beta / query (and `state`, when given) -- the reference trusts the values in the proof. */
+int zk_verify_fibsq(uint32_t log_n, uint32_t a_last, const uint8_t *transcript, size_t len, const uint8_t *state,
+                    int rederive, int *failed_check);
 /* prover.rs:32-39: a[0] = 1, a[1] = secret, a[i] = a[i-2]^2 + a[i-1]^2; 2^log_n - 1 values (host) */
 int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t *trace_out);
 /* cap on device bytes a ctx may hold for proving work space (default: 70% of free memory) */

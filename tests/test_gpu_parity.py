@@ -238,3 +238,23 @@ def test_launch_counter_counts_own_kernels(ctx):
     before = ctx.launch_count()
     ctx.prove_fibsq(8)
     assert ctx.launch_count() - before >= 12
+
+
+# ---------------------------------------------------------------- 8(f) rows: device trace generation, verifier
+def test_prove_batch_from_secrets(ctx, orc):
+    """zk_prove_fibsq_batch_secrets: traces generated on the device (one thread per proof, prover.rs:32-39)."""
+    log_n = 9
+    secrets = np.array([3141592, 0, 1, P - 1, P + 5, 0xFFFFFFFF] + list(range(100, 140)), dtype=np.uint32)
+    trs, sts = ctx.prove_fibsq_batch_secrets(log_n, secrets)
+    for j in (0, 1, 2, 3, 4, 5, 17, 45):
+        otr, ost, info = orc.prove_fibsq(log_n, int(secrets[j]))
+        assert trs[j].tobytes() == otr and sts[j].tobytes() == ost
+        assert zk.verify_fibsq(log_n, info.a_last, otr, ost) == (True, 0)
+
+
+def test_gpu_proof_passes_product_verifier(ctx, kats):
+    proof = zk.generate_proof(zk.Channel.new(), ctx=ctx)
+    proof.verify()  # proof.rs:15-149 with a[1022] = 2338775057 (proof.rs:70)
+    tampered = zk.Proof(proof.state, proof.data[:100] + bytes([proof.data[100] ^ 1]) + proof.data[101:])
+    with pytest.raises(zk.ZkError):
+        tampered.verify()

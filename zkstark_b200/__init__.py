@@ -18,6 +18,7 @@ from ._binding import (  # noqa: F401
     transcript_len,
     trace_fibsq,
     merkle_trace_host,
+    verify_fibsq,
 )
 from .api import (  # noqa: F401
     Channel,

@@ -66,6 +66,8 @@ def lib():
         "zk_prove_fibsq_from_trace": ([vp, u32, vp, vp, sz, C.POINTER(sz), vp], i32),
         "zk_prove_fibsq_batch": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_trace_fibsq": ([u32, u32, vp], i32),
+        "zk_prove_fibsq_batch_secrets": ([vp, u32, u32, vp, vp, vp], i32),
+        "zk_verify_fibsq": ([u32, u32, vp, sz, vp, i32, C.POINTER(i32)], i32),
         "zk_interpolate_subgroup_dev": ([vp, vp, u32, u32, vp], i32),
         "zk_lde_coset_dev": ([vp, vp, u32, u32, u32, vp], i32),
         "zk_fri_fold_dev": ([vp, vp, u64, u32, u32, vp], i32),
@@ -121,6 +123,15 @@ def trace_fibsq(log_n, secret=3141592):
     if rc:
         raise ZkError(rc, "zk_trace_fibsq")
     return out
+
+
+def verify_fibsq(log_n, a_last, transcript, state=None, rederive=True):
+    """proof.rs:15-149 (host).  Returns (ok, failed_check) where failed_check is the proof.rs line of the assert."""
+    fc = C.c_int(0)
+    rc = lib().zk_verify_fibsq(log_n, a_last, transcript, len(transcript), state, int(rederive), C.byref(fc))
+    if rc not in (0, -6):
+        raise ZkError(rc, "zk_verify_fibsq: invalid argument")
+    return rc == 0, fc.value
 
 
 def merkle_trace_host(heap, index):
@@ -226,6 +237,15 @@ class Context:
         tr = np.empty((nb, tl), dtype=np.uint8)
         st = np.empty((nb, 32), dtype=np.uint8)
         self._ck(lib().zk_prove_fibsq_batch(self._h, log_n, nb, _p(traces), _p(tr), _p(st)))
+        return tr, st
+
+    def prove_fibsq_batch_secrets(self, log_n, secrets):
+        secrets = _u32(secrets)
+        nb = len(secrets)
+        tl = transcript_len(log_n)
+        tr = np.empty((nb, tl), dtype=np.uint8)
+        st = np.empty((nb, 32), dtype=np.uint8)
+        self._ck(lib().zk_prove_fibsq_batch_secrets(self._h, log_n, nb, _p(secrets), _p(tr), _p(st)))
         return tr, st
 
     # ---- raw-pointer entry points (device memory owned by the caller, e.g. torch tensors)

@@ -86,6 +86,13 @@ class Proof:
         self.state = state
         self.data = data
 
+    def verify(self, log_n=10, a_last=2338775057):
+        """proof.rs:15-149: raises (the reference panics) if any check fails; also replays the channel."""
+        from ._binding import verify_fibsq
+        ok, line = verify_fibsq(log_n, a_last, self.data, self.state, rederive=True)
+        if not ok:
+            raise ZkError(-6, f"proof rejected: the assert at proof.rs:{line} fails")
+
     def size(self):  # proof.rs:151-154: size_of::<Proof>() == 48 (32-byte array + Box<[u8]> fat pointer)
         return 48 + len(self.data)
 

@@ -24,6 +24,8 @@ cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* t
 cudaError_t launch_lde_one_coset(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
                                  uint32_t log_n, uint32_t r, const uint32_t* coeffs, uint32_t* work, uint32_t* out,
                                  int* n_launches);
+cudaError_t launch_trace_batch(cudaStream_t s, const uint32_t* secrets_dev, uint32_t* traces, uint64_t stride,
+                               uint32_t log_n, uint32_t batch);
 cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
 double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
@@ -755,6 +757,27 @@ int zk_prove_fibsq_batch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const u
         for (uint32_t b = 0; b < nb; b++)
             CK(cudaMemcpyAsync((uint32_t*)ctx->traces.p + n * b, traces + (n - 1) * (size_t)(done + b), 4 * (n - 1),
                                cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done))) return rc;
+    }
+    return ZK_OK;
+}
+
+int zk_prove_fibsq_batch_secrets(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t* secrets,
+                                 uint8_t* transcripts_out, uint8_t* states_out)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!secrets || !transcripts_out || !states_out || n_proofs == 0) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << log_n, trl = transcript_len(log_n);
+    const uint32_t nbmax = pick_subbatch(ctx, log_n, n_proofs);
+    if ((rc = ensure_workspace(ctx, log_n, nbmax))) return rc;
+    CK(ctx->s0.ensure(4 * (size_t)nbmax));
+    for (uint32_t done = 0; done < n_proofs; done += nbmax) {
+        uint32_t nb = n_proofs - done < nbmax ? n_proofs - done : nbmax;
+        CK(cudaMemcpyAsync(ctx->s0.p, secrets + done, 4 * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+        CK(launch_trace_batch(ctx->stream, (const uint32_t*)ctx->s0.p, (uint32_t*)ctx->traces.p, n, log_n, nb));
+        ctx->launches += 1;
         if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done))) return rc;
     }
     return ZK_OK;

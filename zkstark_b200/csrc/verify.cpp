@@ -1,0 +1,197 @@
+// Proof::verify (proof.rs:15-149) as a product feature, generalised to n = 2^log_n.
+// Host code: one query point, ~24 authentication paths -- not data-parallel work.  Beyond the reference it can
+// (a) replay the Fiat-Shamir channel (channel.rs:19-32) and check that every alpha / beta / query in the transcript
+// is the value the channel would have drawn (the reference reads them from the proof, proof.rs:22-37) and
+// (b) check Proof.state, which the reference ignores (proof.rs:5-8).
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/zkstark_b200.h"
+#include "field.cuh"
+
+namespace zk {
+namespace sha {
+void host_sha256(const uint8_t* data, size_t len, uint8_t out[32]);
+}
+}  // namespace zk
+
+using namespace zk;
+
+namespace {
+
+struct Reader {  // bincode 1.3 fixint little-endian (channel.rs:20)
+    const uint8_t* p;
+    size_t len, off = 0;
+    bool ok = true;
+    uint32_t u32()
+    {
+        if (off + 4 > len) { ok = false; return 0; }
+        uint32_t v = p[off] | (p[off + 1] << 8) | (p[off + 2] << 16) | ((uint32_t)p[off + 3] << 24);
+        off += 4;
+        return v;
+    }
+    uint64_t u64()
+    {
+        uint64_t lo = u32(), hi = u32();
+        return lo | (hi << 32);
+    }
+    const uint8_t* bytes(size_t n)
+    {
+        if (off + n > len) { ok = false; return p; }
+        const uint8_t* r = p + off;
+        off += n;
+        return r;
+    }
+};
+
+struct Replay {  // channel.rs:11-32
+    uint8_t state[32];
+    bool on;
+    explicit Replay(bool enable) : on(enable) { memset(state, 0, 32); }
+    void commit(const uint8_t* v, size_t n)
+    {
+        if (!on) return;
+        uint8_t buf[32 + 24 + 64 * 40];
+        memcpy(buf, state, 32);
+        memcpy(buf + 32, v, n);
+        sha::host_sha256(buf, 32 + n, state);
+    }
+    uint32_t draw() const { return ((uint32_t)state[0] << 24) | (state[1] << 16) | (state[2] << 8) | state[3]; }
+};
+
+uint32_t f_add(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a + b) % P); }
+uint32_t f_sub(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a + P - b) % P); }
+uint32_t f_div(uint32_t a, uint32_t b) { return h_mul(a, h_inv(b)); }
+
+// merkle.rs:82-110 compute_root_from_path
+void root_from_path(uint32_t element, uint64_t index, const uint8_t* path, uint32_t plen, uint8_t out[32])
+{
+    uint8_t cur[32], buf[64];
+    index += ((uint64_t)1 << plen) - 1;
+    uint8_t be[4] = {(uint8_t)(element >> 24), (uint8_t)(element >> 16), (uint8_t)(element >> 8), (uint8_t)element};
+    sha::host_sha256(be, 4, cur);
+    for (uint32_t i = 0; i < plen; i++) {
+        const uint8_t* h = path + 32 * (size_t)i;
+        if (index % 2 == 0) { memcpy(buf, h, 32); memcpy(buf + 32, cur, 32); index -= 2; }
+        else { memcpy(buf, cur, 32); memcpy(buf + 32, h, 32); index -= 1; }
+        sha::host_sha256(buf, 64, cur);
+        index >>= 1;
+    }
+    memcpy(out, cur, 32);
+}
+
+}  // namespace
+
+extern "C" int zk_verify_fibsq(uint32_t log_n, uint32_t a_last, const uint8_t* transcript, size_t len,
+                               const uint8_t* state, int rederive, int* failed_check)
+{
+    int dummy = 0;
+    if (!failed_check) failed_check = &dummy;
+    *failed_check = 0;
+    if (!transcript || log_n < ZK_MIN_LOG_N || log_n > ZK_MAX_LOG_N) return ZK_ERR_INVALID;
+    if (len != zk_transcript_len(log_n)) { *failed_check = 20; return ZK_ERR_VERIFY; }  // deserialize .unwrap() (proof.rs:20-46)
+    const uint32_t k = log_n, L = k, log_N = k + ZK_LOG_BLOWUP;
+    const uint64_t n = (uint64_t)1 << k, N = n << ZK_LOG_BLOWUP, B = (uint64_t)1 << ZK_LOG_BLOWUP;
+    Reader rd{transcript, len};
+    Replay ch(rederive != 0);
+#define FAIL(line) do { *failed_check = (line); return ZK_ERR_VERIFY; } while (0)
+
+    // proof.rs:20-46 -- pull elements out of the proof (and replay the channel beside it)
+    const uint8_t* f_root = rd.bytes(32);
+    ch.commit(f_root, 32);
+    uint32_t alpha[3], beta[33] = {0};
+    for (int j = 0; j < 3; j++) {
+        size_t at = rd.off;
+        alpha[j] = rd.u32();
+        if (ch.on && ch.draw() != alpha[j]) FAIL(22 + j);
+        ch.commit(transcript + at, 4);
+    }
+    const uint8_t* roots[33];
+    roots[0] = rd.bytes(32);
+    ch.commit(roots[0], 32);
+    for (uint32_t i = 1; i <= L; i++) {
+        size_t at = rd.off;
+        beta[i] = rd.u32();
+        if (ch.on && ch.draw() != beta[i]) FAIL(30);
+        ch.commit(transcript + at, 4);
+        roots[i] = rd.bytes(32);
+        ch.commit(roots[i], 32);
+    }
+    size_t at = rd.off;
+    const uint32_t free_term = rd.u32();
+    ch.commit(transcript + at, 4);
+    at = rd.off;
+    const uint32_t q_raw = rd.u32();
+    if (ch.on && ch.draw() != q_raw) FAIL(37);
+    ch.commit(transcript + at, 4);
+    uint32_t fv[4];
+    const uint8_t* fp[4];
+    for (int j = 0; j < 4; j++) {
+        at = rd.off;
+        fv[j] = rd.u32();
+        if (rd.u64() != log_N) FAIL(38 + j);
+        fp[j] = rd.bytes(32 * (size_t)log_N);
+        if (!rd.ok) FAIL(38 + j);
+        ch.commit(transcript + at, rd.off - at);
+    }
+    uint32_t lx[33], lnx[33];
+    const uint8_t *px[33], *pnx[33];
+    for (uint32_t i = 0; i < L; i++) {
+        at = rd.off;
+        const uint32_t pl = log_N - i;
+        lx[i] = rd.u32();
+        lnx[i] = rd.u32();
+        if (rd.u64() != pl) FAIL(44);
+        px[i] = rd.bytes(32 * (size_t)pl);
+        if (rd.u64() != pl) FAIL(44);
+        pnx[i] = rd.bytes(32 * (size_t)pl);
+        if (!rd.ok) FAIL(44);
+        ch.commit(transcript + at, rd.off - at);
+    }
+    if (!rd.ok || rd.off != len) FAIL(46);
+    if (ch.on && state && memcmp(state, ch.state, 32) != 0) FAIL(6);  // Proof.state (proof.rs:6), unchecked upstream
+
+    // proof.rs:49-60 -- protocol constants and the test point
+    const uint32_t w = GEN, g = h_root(k), h = h_root(log_N);
+    const uint64_t tp = (uint64_t)q_raw % (N - 2 * B);
+    const uint32_t x = h_mul(w, h_pow(h, tp));
+
+    // proof.rs:63-77 -- the composition polynomial at the test point
+    {
+        const uint32_t f_x = fv[0] % P, f_gx = fv[1] % P, f_ggx = fv[2] % P;
+        const uint32_t g1 = h_pow(g, n - 1), g2 = h_pow(g, n - 2), g3 = h_pow(g, n - 3);
+        const uint32_t p0 = f_div(f_sub(f_x, 1), f_sub(x, 1));
+        const uint32_t p1 = f_div(f_sub(f_x, a_last % P), f_sub(x, g2));
+        const uint32_t num = f_sub(f_sub(f_ggx, h_mul(f_gx, f_gx)), h_mul(f_x, f_x));
+        const uint32_t den = f_div(f_sub(h_pow(x, n), 1), h_mul(h_mul(f_sub(x, g3), f_sub(x, g2)), f_sub(x, g1)));
+        const uint32_t p2 = f_div(num, den);
+        const uint32_t cp0 = f_add(f_add(h_mul(alpha[0] % P, p0), h_mul(alpha[1] % P, p1)), h_mul(alpha[2] % P, p2));
+        if (cp0 != fv[3]) FAIL(76);
+    }
+    // proof.rs:80-95 -- trace authentication paths
+    uint8_t r[32];
+    root_from_path(fv[0], tp, fp[0], log_N, r);          if (memcmp(r, f_root, 32)) FAIL(80);
+    root_from_path(fv[1], tp + B, fp[1], log_N, r);      if (memcmp(r, f_root, 32)) FAIL(84);
+    root_from_path(fv[2], tp + 2 * B, fp[2], log_N, r);  if (memcmp(r, f_root, 32)) FAIL(88);
+    root_from_path(fv[3], tp, fp[3], log_N, r);          if (memcmp(r, roots[0], 32)) FAIL(92);
+    // proof.rs:101-126 -- fold relations cp_{i+1}(x^2) = g(x^2) + beta h(x^2)
+    const uint32_t inv2 = h_inv(2);
+    for (uint32_t i = 0; i < L; i++) {
+        const uint32_t next = (i + 1 < L) ? lx[i + 1] : free_term;
+        const uint32_t xi = h_pow(x, (uint64_t)1 << i);
+        const uint32_t g_xx = h_mul(f_add(lx[i] % P, lnx[i] % P), inv2);
+        const uint32_t h_xx = f_div(f_sub(lx[i] % P, lnx[i] % P), h_mul(xi, 2));
+        if (f_add(g_xx, h_mul(beta[i + 1] % P, h_xx)) != next) FAIL(i + 1 < L ? 113 : 125);
+    }
+    // proof.rs:129-148 -- FRI authentication paths
+    for (uint32_t i = 0; i < L; i++) {
+        const uint64_t size = N >> i;
+        root_from_path(lx[i], tp % size, px[i], log_N - i, r);
+        if (memcmp(r, roots[i], 32)) FAIL(136);
+        root_from_path(lnx[i], (tp + size / 2) % size, pnx[i], log_N - i, r);
+        if (memcmp(r, roots[i], 32)) FAIL(140);
+    }
+#undef FAIL
+    return ZK_OK;
+}
