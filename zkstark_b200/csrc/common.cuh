@@ -17,6 +17,9 @@ constexpr uint32_t TOP_THREADS = 512;
 #define ZK_PASS_THREADS 128
 #endif
 constexpr uint32_t PASS_THREADS = ZK_PASS_THREADS;
+#ifndef ZK_PASS_MINBLOCKS
+#define ZK_PASS_MINBLOCKS 1
+#endif
 constexpr uint32_t MAX_PASS_K = 6;
 #ifndef ZK_SHA_UNI
 #define ZK_SHA_UNI 1  // leaf and node hashes share one copy of the data-block compression

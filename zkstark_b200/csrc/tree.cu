@@ -168,7 +168,7 @@ __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, ui
 // every node of the subtree above them (levels in_level-1 .. in_level-k); for value
 // sources also the leaf digests themselves.
 template <int SRC, int V = ZK_SHA_V, int UNI = ZK_SHA_UNI>
-__global__ void __launch_bounds__(PASS_THREADS) tree_pass_kernel(const TreeArgs a)
+__global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_kernel(const TreeArgs a)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t t = blockIdx.x * PASS_THREADS + threadIdx.x;
