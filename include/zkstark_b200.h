@@ -182,6 +182,8 @@ int zk_shard_fri_tail_dev(zk_ctx *ctx, uint32_t log_n, uint32_t first_layer, uin
  *     ms_out[2] = SM cycles per node hash                                                        */
 /* tuning knobs of zk_bench_kernel(0): SHA-256 pipe-balancing variant (-1 = production) and levels per thread */
 int zk_bench_set(zk_ctx *ctx, int sha_variant, uint32_t leaf_pass_k);
+/* trees of up to 2^log leaves (x batch) are built leaves -> root by the tile kernel in one launch (process-wide) */
+int zk_bench_set_tile_direct_log(zk_ctx *ctx, uint32_t log_leaves);
 int zk_bench_kernel(zk_ctx *ctx, int which, uint32_t log_size, uint32_t iters, int flush_l2, float ms_out[3]);
 
 #ifdef __cplusplus

@@ -8,7 +8,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libzkstark_b200.so")
+# ZK_LIB: an experiment build of the same library (tools/ only); the product path is the in-tree .so
+LIB_PATH = os.environ.get("ZK_LIB") or os.path.join(_PKG, "libzkstark_b200.so")
 HEADER = os.path.join(_ROOT, "include", "zkstark_b200.h")
 
 ZK_OK = 0
@@ -83,6 +84,7 @@ def lib():
         "zk_shard_fold_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fri_tail_dev": ([vp, u32, u32, vp, vp, vp, vp], i32),
         "zk_bench_set": ([vp, i32, u32], i32),
+        "zk_bench_set_tile_direct_log": ([vp, u32], i32),
     }
     for name, (argt, rest) in sig.items():
         fn = getattr(L, name)
@@ -320,6 +322,9 @@ class Context:
         arr = (C.c_float * 3)()
         self._ck(lib().zk_bench_kernel(self._h, which, log_size, iters, int(flush_l2), arr))
         return float(arr[0]), float(arr[1]), float(arr[2])
+
+    def bench_set_tile_direct_log(self, log_leaves):
+        self._ck(lib().zk_bench_set_tile_direct_log(self._h, log_leaves))
 
     def bench_set(self, sha_variant=-1, leaf_pass_k=0):
         self._ck(lib().zk_bench_set(self._h, sha_variant, leaf_pass_k))

@@ -80,6 +80,7 @@ struct zk_ctx {
     std::map<uint32_t, SizeTables> tabs;  // by log_N
     DevBuf s0, s1, s2;                    // scratch for the host-buffer stage calls
     DevBuf flushbuf;
+    DevBuf counters;                      // tile-arrival counters of the tree kernels (one per proof of a batch)
     int bench_variant = -1;
     uint32_t bench_k = 0;
     // prove work space
@@ -172,6 +173,8 @@ int init_tw(zk_ctx* ctx)
     CK(cudaMemcpy(ctx->tw_inv, inv.data(), 1023 * 4, cudaMemcpyHostToDevice));
     return ZK_OK;
 }
+
+constexpr uint32_t MAX_BATCH = 256;  // proofs per sub-batch (one tile counter each)
 
 bool is_pow2(uint64_t v) { return v && !(v & (v - 1)); }
 uint32_t ilog2(uint64_t v)
@@ -302,6 +305,7 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
                   f_eval, N, nb, &nl));
     tm.mark();
     TreeArgs a{};
+    a.counters = (uint32_t*)ctx->counters.p;
     a.state = states;
     a.transcript = trd;
     a.transcript_stride = trs;
@@ -395,7 +399,7 @@ uint32_t pick_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs)
     size_t per = per_proof_bytes(log_n);
     size_t nb = budget / per;
     if (nb < 1) nb = 1;
-    if (nb > 256) nb = 256;
+    if (nb > MAX_BATCH) nb = MAX_BATCH;
     if (nb > n_proofs) nb = n_proofs;
     return (uint32_t)nb;
 }
@@ -437,6 +441,8 @@ int zk_ctx_create_on_stream(int device, void* cuda_stream, zk_ctx** out)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
     int rc = init_tw(ctx);
     if (rc == ZK_OK && sha_init_constants() != cudaSuccess) rc = ZK_ERR_CUDA;
+    if (rc == ZK_OK && (ctx->counters.ensure(4 * MAX_BATCH) != cudaSuccess ||
+                        cudaMemset(ctx->counters.p, 0, 4 * MAX_BATCH) != cudaSuccess)) rc = ZK_ERR_CUDA;
     if (rc) { delete ctx; return rc; }
     *out = ctx;
     return ZK_OK;
@@ -450,7 +456,7 @@ void zk_ctx_destroy(zk_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->tabs) { free_powtab(kv.second.h); free_powtab(kv.second.w); }
-    DevBuf* bufs[] = {&ctx->flushbuf, &ctx->s0, &ctx->s1, &ctx->s2, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval,
+    DevBuf* bufs[] = {&ctx->counters, &ctx->flushbuf, &ctx->s0, &ctx->s1, &ctx->s2, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval,
                       &ctx->layers, &ctx->f_heap, &ctx->layer_heaps, &ctx->states, &ctx->transcripts};
     for (DevBuf* b : bufs) b->release();
     if (ctx->tw_fwd) cudaFree(ctx->tw_fwd);
@@ -584,6 +590,7 @@ int zk_merkle_build_dev(zk_ctx* ctx, const uint32_t* leaves, uint64_t size, uint
     if (!is_pow2(size) || size > ((uint64_t)1 << 30)) return fail(ctx, ZK_ERR_INVALID, "size must be a power of two (merkle.rs:17-21)");
     CK(cudaSetDevice(ctx->device));
     TreeArgs a{};
+    a.counters = (uint32_t*)ctx->counters.p;
     a.vals = const_cast<uint32_t*>(leaves);
     a.heap = heap_out;
     a.log_size = ilog2(size);
@@ -840,6 +847,7 @@ int zk_shard_merkle_blocks_dev(zk_ctx* ctx, const uint32_t* vals_local, uint64_t
     if (lg < log_block || log_block < 1) return fail(ctx, ZK_ERR_INVALID, "local_len smaller than a block");
     CK(cudaSetDevice(ctx->device));
     TreeArgs a{};
+    a.counters = (uint32_t*)ctx->counters.p;
     a.vals = const_cast<uint32_t*>(vals_local);
     a.heap = heap_local;
     a.log_size = lg;
@@ -858,6 +866,7 @@ int zk_shard_upper_tree_dev(zk_ctx* ctx, uint8_t* upper_heap, uint32_t log_count
     if (post_op == POST_FRI && fri_layer >= n_layers) return fail(ctx, ZK_ERR_INVALID, "the last layer belongs to the replicated tail");
     CK(cudaSetDevice(ctx->device));
     TreeArgs a{};
+    a.counters = (uint32_t*)ctx->counters.p;
     a.heap = upper_heap;
     a.log_size = log_count;
     a.in_level = log_count;
@@ -929,6 +938,7 @@ int zk_shard_fri_tail_dev(zk_ctx* ctx, uint32_t log_n, uint32_t first_layer, uin
     SizeTables* T;
     if ((rc = get_tables(ctx, log_N, &T))) return rc;
     TreeArgs a{};
+    a.counters = (uint32_t*)ctx->counters.p;
     a.state = (ProofState*)state_dev;
     a.transcript = transcript_dev;
     a.n_layers = L;
@@ -963,6 +973,13 @@ int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
     return ZK_OK;
 }
 
+int zk_bench_set_tile_direct_log(zk_ctx* ctx, uint32_t log_leaves)
+{
+    if (!ctx || (log_leaves & 0xffu) > 2 * TILE_LOG || (log_leaves >> 8) > TILE_LOG) return ZK_ERR_INVALID;
+    set_tile_direct_log(log_leaves);
+    return ZK_OK;
+}
+
 int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, int flush_l2, float ms_out[3])
 {
     if (!ctx || !ms_out || iters == 0 || iters > 1000) return ZK_ERR_INVALID;
@@ -992,6 +1009,7 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
     SizeTables* T = nullptr;
     size_t n_in = (size_t)1 << log_size, N8 = n_in << LOG_BLOWUP;
     TreeArgs ta{};
+    ta.counters = (uint32_t*)ctx->counters.p;
     FoldArgs fa{};
     CpArgs ca{};
     switch (which) {

@@ -11,8 +11,15 @@ namespace zk {
 
 constexpr uint32_t LOG_BLOWUP = 3;  // 8192/1024 (prover.rs:56-57); literal +8/+16 at prover.rs:268-271
 constexpr uint32_t MAX_LOG_N = 27;  // N = 2^30 is the largest power-of-two subgroup of F_p^*
-constexpr uint32_t TOP_LOG = 10;    // a single CTA finishes trees of <= 2^TOP_LOG inputs
-constexpr uint32_t TOP_THREADS = 512;
+constexpr uint32_t TILE_LOG = 10;   // the tile kernel reduces 2^TILE_LOG inputs per CTA, two per thread
+constexpr uint32_t TILE_PAIRS = 1u << (TILE_LOG - 1);
+constexpr uint32_t TILE_MIN_LOG = 7;
+#ifndef ZK_TILE_SHA_V
+#define ZK_TILE_SHA_V 3  // SHA-256 variant of the (latency-bound) tile kernel
+#endif
+#ifndef ZK_TILE_DIRECT_LOG
+#define ZK_TILE_DIRECT_LOG 17  // trees up to this many leaves (x batch) go leaves -> root in one tile-kernel launch
+#endif
 #ifndef ZK_PASS_THREADS
 #define ZK_PASS_THREADS 128
 #endif
@@ -113,7 +120,9 @@ struct TreeArgs {
     uint32_t log_size;      // tree has 2^log_size leaves
     uint32_t in_level;      // level the kernel consumes (== log_size for leaf passes)
     uint32_t k;             // levels produced by one thread of a pass kernel
+    uint32_t log_tile;      // tile kernel: inputs per CTA (set by the launcher)
     ProofState* state;      // per proof (may be null for POST_NONE)
+    uint32_t* counters;     // per proof tile-arrival counter (zero between launches); needed above 2^TILE_LOG inputs
     uint8_t* transcript;    // per proof
     uint64_t transcript_stride;
     int post;               // PostOp
@@ -133,6 +142,7 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src_kind, TreeArgs a, uint
 cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int* n_launches);
 // the leaf pass alone (bench support): a.in_level / a.k preset by the caller
 cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant);
+void set_tile_direct_log(uint32_t v);
 cudaError_t sha_init_constants();
 cudaError_t launch_node_latency(cudaStream_t s, uint32_t* out, uint32_t reps, uint32_t warps, int variant, long long* cycles);
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,

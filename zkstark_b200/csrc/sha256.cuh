@@ -277,6 +277,15 @@ __device__ __forceinline__ void load_digest(const uint8_t* src, uint32_t d[8])
     d[4] = bswap32(b.x); d[5] = bswap32(b.y); d[6] = bswap32(b.z); d[7] = bswap32(b.w);
 }
 
+// same, through L2 (ld.global.cg): for digests written by other CTAs of the running launch
+__device__ __forceinline__ void load_digest_cg(const uint8_t* src, uint32_t d[8])
+{
+    const uint4* p = reinterpret_cast<const uint4*>(src);
+    uint4 a = __ldcg(p), b = __ldcg(p + 1);
+    d[0] = bswap32(a.x); d[1] = bswap32(a.y); d[2] = bswap32(a.z); d[3] = bswap32(a.w);
+    d[4] = bswap32(b.x); d[5] = bswap32(b.y); d[6] = bswap32(b.z); d[7] = bswap32(b.w);
+}
+
 #endif  // __CUDACC__ && ZK_SHA_DEVICE
 
 // ---- host SHA-256 (generic length) for the host-side tail of the channel

@@ -236,32 +236,57 @@ __global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_ker
     }
 }
 
+// ---------------------------------------------------------------- one out-of-line SHA-256 for latency-bound code
+// The tile kernel and the channel hash a handful of messages one after the other; with every call site inlined
+// the kernel carried ~6 copies of the 17 KB compression body and each copy was fetched cold exactly once
+// (measured: ~2.7 us per copy on a 45 us kernel).  One out-of-line copy stays hot in the instruction cache.
+// Message = 16 words (one block, already padded) or 64 bytes + the constant padding block (`two_blocks`).
+struct Dig8 { uint32_t v[8]; };
+template <int V>
+__device__ __noinline__ Dig8 sha_msg(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                     uint32_t w6, uint32_t w7, uint32_t w8, uint32_t w9, uint32_t w10, uint32_t w11,
+                                     uint32_t w12, uint32_t w13, uint32_t w14, uint32_t w15, uint32_t two_blocks)
+{
+    uint32_t w[16] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11, w12, w13, w14, w15};
+    Dig8 d;
+    sha::init_iv(d.v);
+    sha::compress<V>(d.v, w);
+    if (two_blocks) sha::compress_pad64<V>(d.v);
+    return d;
+}
+template <int V>
+__device__ __forceinline__ void msg_node(const uint32_t l[8], const uint32_t r[8], uint32_t out[8])   // merkle.rs:40-46
+{
+    Dig8 d = sha_msg<V>(l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7], r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], 1u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = d.v[i];
+}
+template <int V>
+__device__ __forceinline__ void msg_leaf(uint32_t v, uint32_t out[8])                                 // merkle.rs:30-34
+{
+    Dig8 d = sha_msg<V>(v, 0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 32u, 0u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = d.v[i];
+}
+
 // ---------------------------------------------------------------- device channel
 // channel.rs:19-26 for a 32-byte value: state = SHA256(state || v) -- a 64-byte message,
 // i.e. exactly the node hash.
-__device__ __noinline__ void chan_commit_digest(uint32_t st[8], const uint32_t v[8])
+__device__ __forceinline__ void chan_commit_digest(uint32_t st[8], const uint32_t v[8])
 {
     uint32_t out[8];
-    sha::hash_node<ZK_SHA_V>(st, v, out);
+    msg_node<ZK_TILE_SHA_V>(st, v, out);
 #pragma unroll
     for (int i = 0; i < 8; i++) st[i] = out[i];
 }
 // channel.rs:19-26 for a u32: bincode writes it little-endian (4 bytes); the 36-byte message
 // state || le(v) is one padded block.
-__device__ __noinline__ void chan_commit_u32(uint32_t st[8], uint32_t v)
+__device__ __forceinline__ void chan_commit_u32(uint32_t st[8], uint32_t v)
 {
-    uint32_t w[16], out[8];
+    Dig8 d = sha_msg<ZK_TILE_SHA_V>(st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[7], sha::bswap32(v), 0x80000000u,
+                                    0u, 0u, 0u, 0u, 0u, 36u * 8u, 0u);
 #pragma unroll
-    for (int i = 0; i < 8; i++) w[i] = st[i];
-    w[8] = sha::bswap32(v);
-    w[9] = 0x80000000u;
-#pragma unroll
-    for (int i = 10; i < 15; i++) w[i] = 0u;
-    w[15] = 36u * 8u;
-    sha::init_iv(out);
-    sha::compress<0>(out, w);
-#pragma unroll
-    for (int i = 0; i < 8; i++) st[i] = out[i];
+    for (int i = 0; i < 8; i++) st[i] = d.v[i];
 }
 // channel.rs:28-32
 __device__ __forceinline__ uint32_t chan_get_u32(uint32_t st[8])
@@ -326,60 +351,111 @@ __device__ void post_root(const TreeArgs& a, uint32_t b, const uint32_t root[8])
     for (int i = 0; i < 8; i++) ps->chan[i] = st[i];
 }
 
-// ---------------------------------------------------------------- top kernel
-// One CTA per proof: consumes 2^in_level (<= 2^TOP_LOG) inputs, finishes the tree, then the
-// channel step.  One node per thread per level (TOP_THREADS >= 2^(TOP_LOG-1)).
-template <int SRC>
-__global__ void __launch_bounds__(TOP_THREADS) tree_top_kernel(const TreeArgs a)
+// ---------------------------------------------------------------- tile kernel (upper tree in ONE launch)
+// A tile is up to 2^TILE_LOG consecutive inputs of level `in_level` -- leaf values (hashed here, after the fused
+// fold / composition source produced them) or digests left by a pass kernel.  One CTA reduces its tile to a
+// single digest level by level (two inputs per thread, then word-major ping-pong buffers in shared memory:
+// conflict-free 64-bit reads, one barrier per level), writing every node into the heap.  The CTA that finishes
+// LAST (per-proof arrival counter, threadfence-reduction pattern: no co-residency requirement, no grid sync)
+// reduces the <= 2^TILE_LOG tile roots to the tree root and runs the Fiat-Shamir step (channel.rs:19-32), so
+// a whole upper tree + challenge draw is a single launch instead of four digest passes + a top kernel.
+template <int SRC, int V>
+__device__ __forceinline__ void tile_input(const TreeArgs& a, uint8_t* heap, const uint32_t* vals, uint32_t level,
+                                           uint32_t idx, uint32_t d[8], bool coherent)
 {
-    extern __shared__ uint32_t sm[];  // [2^in_level][8]
-    const uint32_t b = blockIdx.x, t = threadIdx.x;
-    const uint32_t n_in = 1u << a.in_level;
-    uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
-
-    if (SRC == SRC_FOLD || SRC == SRC_CP) {
-        // two consecutive points per thread (every layer has an even number of points >= 8)
-        if (n_in >= 2 * TOP_THREADS) { if (2 * t < n_in) produce_values<SRC>(a, b, 2 * t, 2); }
-        else if (t < n_in) produce_values<SRC>(a, b, t, 1);
-        __syncthreads();
+    const size_t node = (((size_t)1 << level) - 1) + idx;
+    if (SRC == SRC_DIGESTS) {
+        if (coherent) sha::load_digest_cg(heap + 32 * node, d);   // written by other CTAs of this launch
+        else sha::load_digest(heap + 32 * node, d);
+    } else {
+        msg_leaf<V>(vals[idx], d);                                 // merkle.rs:30-34
+        sha::store_digest(heap + 32 * node, d);
     }
-    const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
-    const size_t lvl0 = ((size_t)1 << a.in_level) - 1;
-    for (uint32_t i = t; i < n_in; i += TOP_THREADS) {
-        uint32_t d[8];
-        if (SRC == SRC_DIGESTS) {
-            sha::load_digest(heap + 32 * (lvl0 + i), d);
-        } else {
-            sha::hash_leaf<ZK_SHA_V>(vals[i], d);
-            sha::store_digest(heap + 32 * (lvl0 + i), d);
-        }
+}
+
+// Reduces inputs [first, first + 2^log_cnt) of heap level `level` to one digest (returned in sm0 column 0 ... see
+// below); every produced node is stored at its heap position.  Returns with the subtree root in `root` of thread 0.
+template <int SRC, int V>
+__device__ __forceinline__ void tile_reduce(const TreeArgs& a, uint8_t* heap, const uint32_t* vals, uint32_t level,
+                                            uint32_t first, uint32_t log_cnt, bool coherent,
+                                            uint32_t (*bufA)[TILE_PAIRS], uint32_t (*bufB)[TILE_PAIRS / 2], uint32_t root[8])
+{
+    const uint32_t t = threadIdx.x;
+    if (log_cnt == 0) {                                            // a single input: it is the subtree root
+        if (t == 0) tile_input<SRC, V>(a, heap, vals, level, first, root, coherent);
+        return;
+    }
+    uint32_t cnt = 1u << (log_cnt - 1);                            // nodes of the level being produced
+    uint32_t lvl = level - 1;
+    uint32_t d[8];
+    if (t < cnt) {
+        uint32_t l[8], r[8];
+        tile_input<SRC, V>(a, heap, vals, level, first + 2 * t, l, coherent);
+        tile_input<SRC, V>(a, heap, vals, level, first + 2 * t + 1, r, coherent);
+        msg_node<V>(l, r, d);                                      // merkle.rs:40-46
+        sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + (first >> 1) + t), d);
 #pragma unroll
-        for (int w = 0; w < 8; w++) sm[8 * i + w] = d[w];
+        for (int w = 0; w < 8; w++) bufA[w][t] = d[w];
     }
     __syncthreads();
-    for (int lvl = (int)a.in_level - 1; lvl >= 0; lvl--) {
-        const uint32_t cnt = 1u << lvl;
-        uint32_t d[8];
+    bool inA = true;
+    uint32_t base = first >> 1;
+    while (cnt > 1) {
+        cnt >>= 1; lvl--; base >>= 1;
         if (t < cnt) {
             uint32_t l[8], r[8];
 #pragma unroll
-            for (int w = 0; w < 8; w++) { l[w] = sm[16 * t + w]; r[w] = sm[16 * t + 8 + w]; }
-            sha::hash_node<ZK_SHA_V>(l, r, d);
-            sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + t), d);
+            for (int w = 0; w < 8; w++) {
+                uint2 p = inA ? *reinterpret_cast<const uint2*>(&bufA[w][2 * t]) : *reinterpret_cast<const uint2*>(&bufB[w][2 * t]);
+                l[w] = p.x; r[w] = p.y;
+            }
+            msg_node<V>(l, r, d);
+            sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + base + t), d);
+#pragma unroll
+            for (int w = 0; w < 8; w++) { if (inA) bufB[w][t] = d[w]; else bufA[w][t] = d[w]; }
         }
         __syncthreads();
-        if (t < cnt) {
+        inA = !inA;
+    }
+    if (t == 0) {
 #pragma unroll
-            for (int w = 0; w < 8; w++) sm[8 * t + w] = d[w];
+        for (int w = 0; w < 8; w++) root[w] = d[w];
+    }
+}
+
+template <int SRC, int V = ZK_TILE_SHA_V>
+__global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
+{
+    __shared__ __align__(16) uint32_t bufA[8][TILE_PAIRS];
+    __shared__ __align__(16) uint32_t bufB[8][TILE_PAIRS / 2];
+    __shared__ uint32_t s_last;
+    const uint32_t b = blockIdx.y, tile = blockIdx.x, n_tiles = gridDim.x, t = threadIdx.x;
+    const uint32_t log_tile = a.in_level < a.log_tile ? a.in_level : a.log_tile;   // n_tiles == 2^(in_level - log_tile)
+    uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
+    const uint32_t first = tile << log_tile;
+
+    if (SRC == SRC_FOLD || SRC == SRC_CP) {
+        // every layer has an even number (>= 8) of points: two consecutive points per thread
+        if (2 * t < (1u << log_tile)) produce_values<SRC>(a, b, first + 2 * t, 2);
+        __syncthreads();                                           // CP reads neighbours' f only; fold reads cur only
+    }
+    const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
+    uint32_t root[8];
+    tile_reduce<SRC, V>(a, heap, vals, a.in_level, first, log_tile, false, bufA, bufB, root);
+    if (n_tiles > 1) {
+        __threadfence();                                           // this tile's nodes are visible device-wide ...
+        __syncthreads();
+        if (t == 0) {
+            const uint32_t prev = atomicAdd(a.counters + b, 1u);   // ... before the arrival is counted
+            s_last = (prev == n_tiles - 1);
+            if (prev == n_tiles - 1) a.counters[b] = 0;            // re-arm for the next launch on this stream
         }
         __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        tile_reduce<SRC_DIGESTS, V>(a, heap, vals, a.in_level - log_tile, 0, a.in_level - log_tile, true, bufA, bufB, root);
     }
-    if (t == 0 && a.post != POST_NONE) {
-        uint32_t root[8];
-#pragma unroll
-        for (int w = 0; w < 8; w++) root[w] = sm[w];
-        post_root(a, b, root);
-    }
+    if (t == 0 && a.post != POST_NONE) post_root(a, b, root);
 }
 
 // ---------------------------------------------------------------- stand-alone stage kernels
@@ -572,6 +648,8 @@ __global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64
 }
 
 // ---------------------------------------------------------------- launchers
+extern uint32_t g_tile_direct_log;
+extern uint32_t g_tile_log_override;
 template <int SRC>
 static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch)
 {
@@ -580,12 +658,55 @@ static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch
     tree_pass_kernel<SRC><<<grid, PASS_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
+// a.in_level inputs per proof -> root (+ channel step); in_level <= 2 * TILE_LOG
 template <int SRC>
-static cudaError_t launch_top(cudaStream_t s, const TreeArgs& a, uint32_t batch)
+static cudaError_t launch_tile(cudaStream_t s, const TreeArgs& a, uint32_t batch)
 {
-    size_t smem = (size_t)32 << a.in_level;
-    tree_top_kernel<SRC><<<batch, TOP_THREADS, smem, s>>>(a);
+    if (a.in_level > 2 * TILE_LOG) return cudaErrorInvalidValue;
+    // Tile size: a lone warp hashes a node in ~2.7 us, but an SM saturates at ~8 warps (ALU pipe: one warp
+    // instruction per 2 cycles per sub-partition), so the latency-bound levels want FEW warps on MANY SMs:
+    // tiles of 128 inputs (2 warps) while the closing CTA still gets <= 256 tile roots, larger tiles above that.
+    TreeArgs b = a;
+    int lt = (int)a.in_level - 8;
+    if (lt < (int)TILE_MIN_LOG) lt = TILE_MIN_LOG;
+    if (lt > (int)TILE_LOG) lt = TILE_LOG;
+    if (g_tile_log_override) lt = g_tile_log_override;
+    if (lt > (int)a.in_level) lt = a.in_level;
+    if (a.in_level - lt > TILE_LOG) return cudaErrorInvalidValue;
+    b.log_tile = lt;
+    const uint32_t n_tiles = 1u << (a.in_level - lt);
+    if (n_tiles > 1 && !a.counters) return cudaErrorInvalidValue;
+    uint32_t threads = lt >= 1 ? 1u << (lt - 1) : 1u;                       // pairs of a tile ...
+    if (n_tiles > 2 * threads) threads = n_tiles / 2;                        // ... or of the tile roots, in the closing CTA
+    if (threads < 32) threads = 32;
+    tree_tile_kernel<SRC><<<dim3(n_tiles, batch), threads, 0, s>>>(b);
     return cudaGetLastError();
+}
+static cudaError_t launch_tile_src(cudaStream_t s, int src, const TreeArgs& a, uint32_t batch)
+{
+    switch (src) {
+        case SRC_VALUES: return launch_tile<SRC_VALUES>(s, a, batch);
+        case SRC_FOLD: return launch_tile<SRC_FOLD>(s, a, batch);
+        case SRC_CP: return launch_tile<SRC_CP>(s, a, batch);
+        case SRC_DIGESTS: return launch_tile<SRC_DIGESTS>(s, a, batch);
+        default: return cudaErrorInvalidValue;
+    }
+}
+// digest passes until the tile kernel can take over, then the tile kernel
+static cudaError_t finish_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int* launches)
+{
+    cudaError_t e = cudaSuccess;
+    while (a.in_level > 2 * TILE_LOG) {
+        uint32_t rem = a.in_level - 2 * TILE_LOG;
+        a.k = rem >= 4 ? 4 : rem;
+        e = launch_pass<SRC_DIGESTS>(s, a, batch);
+        (*launches)++;
+        if (e != cudaSuccess) return e;
+        a.in_level -= a.k;
+    }
+    e = launch_tile<SRC_DIGESTS>(s, a, batch);
+    (*launches)++;
+    return e;
 }
 
 static uint32_t ilog2(uint64_t v)
@@ -600,21 +721,17 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
     cudaError_t e = cudaSuccess;
     int launches = 0;
     a.in_level = a.log_size;
-    if (a.log_size <= TOP_LOG) {
-        switch (src) {
-            case SRC_VALUES: e = launch_top<SRC_VALUES>(s, a, batch); break;
-            case SRC_FOLD: e = launch_top<SRC_FOLD>(s, a, batch); break;
-            case SRC_CP: e = launch_top<SRC_CP>(s, a, batch); break;
-            default: return cudaErrorInvalidValue;
-        }
+    const uint32_t lb = ilog2(batch);
+    if (a.log_size + lb <= g_tile_direct_log || a.log_size <= TILE_LOG) {
+        // small and mid-size trees: leaves -> root in one launch
+        e = launch_tile_src(s, src, a, batch);
         launches++;
     } else {
         // leaf pass: enough threads to fill 148 SMs several times over, else fewer levels per thread
-        const uint32_t lb = ilog2(batch);
         int k = (int)a.log_size + (int)lb - 18;
         if (k < 1) k = 1;
         if (k > (int)MAX_PASS_K) k = MAX_PASS_K;
-        if (k > (int)(a.log_size - TOP_LOG)) k = a.log_size - TOP_LOG;
+        if (k > (int)(a.log_size - TILE_LOG)) k = a.log_size - TILE_LOG;
         a.k = k;
         switch (src) {
             case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
@@ -625,16 +742,7 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
         launches++;
         if (e != cudaSuccess) return e;
         a.in_level -= k;
-        while (a.in_level > TOP_LOG) {
-            uint32_t rem = a.in_level - TOP_LOG;
-            a.k = rem >= 2 ? 2 : 1;
-            e = launch_pass<SRC_DIGESTS>(s, a, batch);
-            launches++;
-            if (e != cudaSuccess) return e;
-            a.in_level -= a.k;
-        }
-        e = launch_top<SRC_DIGESTS>(s, a, batch);
-        launches++;
+        e = finish_upper(s, a, batch, &launches);
     }
     if (n_launches) *n_launches += launches;
     return e;
@@ -677,20 +785,19 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src, TreeArgs a, uint32_t 
 
 cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int* n_launches)
 {
-    cudaError_t e = cudaSuccess;
     int launches = 0;
-    while (a.in_level > TOP_LOG) {
-        uint32_t rem = a.in_level - TOP_LOG;
-        a.k = rem >= 2 ? 2 : 1;
-        e = launch_pass<SRC_DIGESTS>(s, a, batch);
-        launches++;
-        if (e != cudaSuccess) return e;
-        a.in_level -= a.k;
-    }
-    e = launch_top<SRC_DIGESTS>(s, a, batch);
-    launches++;
+    cudaError_t e = finish_upper(s, a, batch, &launches);
     if (n_launches) *n_launches += launches;
     return e;
+}
+
+// trees of up to 2^g_tile_direct_log leaves (summed over the batch) skip the per-thread-subtree leaf pass
+uint32_t g_tile_direct_log = ZK_TILE_DIRECT_LOG;
+uint32_t g_tile_log_override = 0;
+void set_tile_direct_log(uint32_t v)   // bench knob: low 8 bits = direct threshold, bits 8.. = forced tile size (0 = adaptive)
+{
+    g_tile_direct_log = v & 0xffu;
+    g_tile_log_override = (v >> 8) & 0xffu;
 }
 
 __global__ void state_set_kernel(ProofState* st, uint32_t a_first, uint32_t a_last)
