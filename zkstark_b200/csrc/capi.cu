@@ -207,7 +207,9 @@ CpArgs make_cp_args(uint32_t log_n)
     const uint32_t wn = h_pow(GEN, n), hn = h_pow(h, n);
     uint32_t xn = wn;
     for (int i = 0; i < 8; i++) {
-        c.zinv_m[i] = h_to_mont(h_inv((uint32_t)(((uint64_t)xn + P - 1) % P)));
+        uint32_t zi = h_inv((uint32_t)(((uint64_t)xn + P - 1) % P));
+        for (int e = 0; e < 6; e++) zi = h_to_mont(zi);   // times R^6
+        c.zinv_r6[i] = zi;
         xn = h_mul(xn, hn);
     }
     return c;

@@ -29,7 +29,7 @@ constexpr uint32_t PASS_THREADS = ZK_PASS_THREADS;
 #endif
 constexpr uint32_t MAX_PASS_K = 6;
 #ifndef ZK_SHA_UNI
-#define ZK_SHA_UNI 1  // leaf and node hashes share one copy of the data-block compression
+#define ZK_SHA_UNI 2  // 1: leaf and node hashes share one copy of the data-block compression; 2: + leaf-specialised prologue and schedule
 #endif
 #ifndef ZK_SHA_V
 #define ZK_SHA_V 3  // SHA-256 pipe-balancing variant used by the production kernels (sha256.cuh)
@@ -103,7 +103,7 @@ struct CpArgs {             // prover.rs:101-173 pointwise
     uint64_t f_stride;
     uint32_t log_n;
     uint32_t g1, g2, g3;    // g^(n-1), g^(n-2), g^(n-3) canonical
-    uint32_t zinv_m[8];     // 1/(x^n - 1) for i mod 8, Montgomery form
+    uint32_t zinv_r6[8];    // 1/(x^n - 1) for i mod 8, times R^6 (see cp_chunk: the product with alpha_2 lands at R^5)
     int alpha_from_state;
     uint32_t alpha_raw[3];
     uint32_t a_first, a_last;  // used when !alpha_from_state (stand-alone API)

@@ -27,18 +27,32 @@ constexpr uint32_t GEN = 5u;             // F::generator(), prover.rs:44-45
 #define ZK_HD inline
 #endif
 
-ZK_HD uint32_t fadd(uint32_t a, uint32_t b)  // field.rs:96-101
+// r = a - b and whether it borrowed.  On the device the subtraction is written with the carry flag
+// (sub.cc / subc): ptxas then folds the comparison into the IADD3's carry-out predicate, so
+// "subtract, add p back on borrow" is 2 instructions instead of ISETP + IADD + predicated add.
+ZK_HD uint32_t sub_borrow(uint32_t a, uint32_t b, uint32_t& borrow)
 {
-    // a + b == a - (p - b); borrow <=> a + b < p
-    uint32_t t = P - b;
-    uint32_t r = a - t;
-    return (a < t) ? r + P : r;
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{sub.cc.u32 %0, %2, %3; subc.u32 %1, 0, 0;}" : "=r"(r), "=r"(borrow) : "r"(a), "r"(b));
+    return r;
+#else
+    borrow = a < b;
+    return a - b;
+#endif
 }
 
 ZK_HD uint32_t fsub(uint32_t a, uint32_t b)  // field.rs:117-122
 {
-    uint32_t r = a - b;
-    return (a < b) ? r + P : r;
+    uint32_t bw;
+    uint32_t r = sub_borrow(a, b, bw);
+    return bw ? r + P : r;
+}
+
+ZK_HD uint32_t fadd(uint32_t a, uint32_t b)  // field.rs:96-101
+{
+    // a + b == a - (p - b); borrow <=> a + b < p
+    return fsub(a, P - b);
 }
 
 ZK_HD uint32_t fneg(uint32_t a) { return a ? P - a : 0u; }  // field.rs:159-164
@@ -53,8 +67,9 @@ ZK_HD uint32_t mont_mul(uint32_t a, uint32_t b)  // field.rs:138-143 (one operan
 #else
     uint32_t u = (uint32_t)(((uint64_t)m * P) >> 32);
 #endif
-    uint32_t r = hi - u;
-    return (hi < u) ? r + P : r;
+    uint32_t bw;
+    uint32_t r = sub_borrow(hi, u, bw);
+    return bw ? r + P : r;
 }
 
 ZK_HD uint32_t to_mont(uint32_t a) { return mont_mul(a, R2); }    // a must be < p

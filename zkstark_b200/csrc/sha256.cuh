@@ -69,7 +69,7 @@ constexpr Consts make_consts()
 //   shift     x >> k                ->  IMAD.HI   hi(x * c[2^(32-k)])
 //   rotate    rotr(x, k) = hi | lo  ->  IMAD.WIDE x * c[2^(32-k)]   (hi, lo disjoint: OR == XOR)
 // `V` is a bit mask choosing which groups of operations move (tuned on the GPU):
-//   1 round adds   2 schedule adds   4 Sigma1 rotations   8 Sigma0 rotations   16 sigma0/1 shifts
+//   1 round adds   2 schedule adds   4 Sigma1 rotations   8 Sigma0 rotations   16 sigma0/1 shifts   32 K+W adds
 enum ShaConst { SC_ONE = 0, SC_R6, SC_R11, SC_R2, SC_R13, SC_S3, SC_S10, SC_R18, SC_R19, SC_COUNT };
 __constant__ uint32_t c_sha[16];  // one translation unit (tree.cu) owns the hashing kernels
 
@@ -176,7 +176,7 @@ __device__ __forceinline__ void compress(uint32_t st[8], uint32_t w[16])
 {
     constexpr Consts C = make_consts();
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-#define ZK_KW_FIRST(j) (C.k[j] + w[j])
+#define ZK_KW_FIRST(j) (addv<V, 32>(w[j], C.k[j]))
     ZK_SHA_16ROUNDS(V, ZK_KW_FIRST)
 #undef ZK_KW_FIRST
 #pragma unroll 1
@@ -196,7 +196,7 @@ __device__ __forceinline__ void compress(uint32_t st[8], uint32_t w[16])
                 kk[4 * q] = t.x; kk[4 * q + 1] = t.y; kk[4 * q + 2] = t.z; kk[4 * q + 3] = t.w;
             }
         }
-#define ZK_KW_LOOP(j) (kk[j] + w[j])
+#define ZK_KW_LOOP(j) (addv<V, 32>(w[j], kk[j]))
         ZK_SHA_16ROUNDS(V, ZK_KW_LOOP)
 #undef ZK_KW_LOOP
     }
@@ -225,6 +225,90 @@ __device__ __forceinline__ void compress_pad64(uint32_t st[8])
 #undef ZK_KW_PAD
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// Leaf-or-node compression sharing ONE rolled round loop (the production leaf pass, UNI == 2):
+//   leaf (merkle.rs:30-34): W0 = v, W1 = 0x80000000, W2..14 = 0, W15 = 32.  Rounds 0-15 are straight-line with
+//     the chaining value = IV and 15 constant words folded at compile time (round 0 collapses to two adds), and
+//     the first schedule trip W16..W31 is specialised: 9 of the 32 sigma terms survive.  Then the shared loop
+//     runs rounds 16-63.
+//   node data block: all 64 rounds go through the shared loop (round constants from the constant bank).
+// Instruction footprint is the same as one generic compression + the leaf prologue (~17 KB with the padding
+// block), which keeps the kernel out of the instruction-fetch-bound regime of the fully unrolled form.
+template <int V>
+__device__ __forceinline__ void sched_leaf(uint32_t v, uint32_t w[16])
+{
+    // constants of the leaf block: c_i = the part of W_i that does not depend on v
+    constexpr uint32_t W1 = 0x80000000u, W15 = 32u;
+    constexpr uint32_t s0_W1 = c_rotr(W1, 7) ^ c_rotr(W1, 18) ^ (W1 >> 3);
+    constexpr uint32_t s1_W15 = c_rotr(W15, 17) ^ c_rotr(W15, 19) ^ (W15 >> 10);
+    constexpr uint32_t s0_W15 = c_rotr(W15, 7) ^ c_rotr(W15, 18) ^ (W15 >> 3);
+    constexpr uint32_t W17 = s1_W15 + W1;                                        // sigma1(W15) + W10 + sigma0(W2) + W1
+    constexpr uint32_t s1_W17 = c_rotr(W17, 17) ^ c_rotr(W17, 19) ^ (W17 >> 10);
+    constexpr uint32_t W19 = s1_W17;                                             // + W12 + sigma0(W4) + W3 = 0
+    constexpr uint32_t s1_W19 = c_rotr(W19, 17) ^ c_rotr(W19, 19) ^ (W19 >> 10);
+    constexpr uint32_t W21 = s1_W19;
+    constexpr uint32_t s1_W21 = c_rotr(W21, 17) ^ c_rotr(W21, 19) ^ (W21 >> 10);
+    const uint32_t w16 = addv<V, 2>(v, s0_W1);                                   // sigma1(W14) + W9 + sigma0(W1) + W0
+    const uint32_t w18 = ssig1<V>(w16);                                          // + W11 + sigma0(W3) + W2 = 0
+    const uint32_t w20 = ssig1<V>(w18);
+    const uint32_t w22 = addv<V, 2>(ssig1<V>(w20), W15);                         // + sigma0(W7) + W6 = 0
+    const uint32_t w23 = addv<V, 2>(w16, s1_W21);                                // sigma1(W21) + W16 + sigma0(W8) + W7
+    const uint32_t w24 = addv<V, 2>(ssig1<V>(w22), W17);                         // + sigma0(W9) + W8 = 0
+    const uint32_t w25 = addv<V, 2>(ssig1<V>(w23), w18);
+    const uint32_t w26 = addv<V, 2>(ssig1<V>(w24), W19);
+    const uint32_t w27 = addv<V, 2>(ssig1<V>(w25), w20);
+    const uint32_t w28 = addv<V, 2>(ssig1<V>(w26), W21);
+    const uint32_t w29 = addv<V, 2>(ssig1<V>(w27), w22);
+    const uint32_t w30 = addv<V, 2>(addv<V, 2>(ssig1<V>(w28), w23), s0_W15);     // + W14 = 0
+    const uint32_t w31 = addv<V, 2>(addv<V, 2>(addv<V, 2>(ssig1<V>(w29), w24), ssig0<V>(w16)), W15);
+    w[0] = w16; w[1] = W17; w[2] = w18; w[3] = W19; w[4] = w20; w[5] = W21; w[6] = w22; w[7] = w23;
+    w[8] = w24; w[9] = w25; w[10] = w26; w[11] = w27; w[12] = w28; w[13] = w29; w[14] = w30; w[15] = w31;
+}
+
+// st: out only (the chaining value is always the IV).  leaf: w[0] = value, rest ignored; node: w = 16 data words.
+template <int V>
+__device__ __forceinline__ void compress_leaf_or_node(uint32_t st[8], uint32_t w[16], bool leaf)
+{
+    constexpr Consts C = make_consts();
+    uint32_t a = ZK_SHA_IV0, b = ZK_SHA_IV1, c = ZK_SHA_IV2, d = ZK_SHA_IV3, e = ZK_SHA_IV4, f = ZK_SHA_IV5,
+             g = ZK_SHA_IV6, h = ZK_SHA_IV7;
+    int i = 0;
+    if (leaf) {
+        const uint32_t v = w[0];
+        w[1] = 0x80000000u;
+#pragma unroll
+        for (int j = 2; j < 15; j++) w[j] = 0u;
+        w[15] = 32u;
+#define ZK_KW_LEAF(j) (addv<V, 32>(w[j], C.k[j]))
+        ZK_SHA_16ROUNDS(V, ZK_KW_LEAF)
+#undef ZK_KW_LEAF
+        sched_leaf<V>(v, w);
+        i = 16;
+    }
+#pragma unroll 1
+    for (;;) {
+        uint32_t kk[16];
+        {
+            const uint4* kp = reinterpret_cast<const uint4*>(c_k + i);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 t = kp[q];
+                kk[4 * q] = t.x; kk[4 * q + 1] = t.y; kk[4 * q + 2] = t.z; kk[4 * q + 3] = t.w;
+            }
+        }
+#define ZK_KW_LOOP(j) (addv<V, 32>(w[j], kk[j]))
+        ZK_SHA_16ROUNDS(V, ZK_KW_LOOP)
+#undef ZK_KW_LOOP
+        i += 16;
+        if (i == 64) break;
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            w[j] = addv<V, 2>(addv<V, 2>(addv<V, 2>(w[j], ssig1<V>(w[(j + 14) & 15])), w[(j + 9) & 15]),
+                              ssig0<V>(w[(j + 1) & 15]));
+    }
+    st[0] = a + ZK_SHA_IV0; st[1] = b + ZK_SHA_IV1; st[2] = c + ZK_SHA_IV2; st[3] = d + ZK_SHA_IV3;
+    st[4] = e + ZK_SHA_IV4; st[5] = f + ZK_SHA_IV5; st[6] = g + ZK_SHA_IV6; st[7] = h + ZK_SHA_IV7;
 }
 
 __device__ __forceinline__ void init_iv(uint32_t st[8])

@@ -77,12 +77,54 @@ __device__ __forceinline__ void fold_chunk(const FoldArgs& f, const PowTab& pw, 
 //  cp = a0 (f(x)-a_first)/(x-1) + a1 (f(x)-a_last)/(x-g^(n-2))
 //     + a2 (f(g^2 x) - f(g x)^2 - f(x)^2) (x-g^(n-3))(x-g^(n-2))(x-g^(n-1)) / (x^n-1)
 // f(g x) = f_eval[i+8], f(g^2 x) = f_eval[i+16] (indices mod N: cp_poly is evaluated on the
-// whole coset, prover.rs:172-173).  x^n - 1 depends on i mod 8 only; the two linear
-// denominators are inverted with one batched inversion per C points.
+// whole coset, prover.rs:172-173).  x^n - 1 depends on i mod 8 only.  The two linear denominators are merged,
+//  a0 (f-a_first)/(x-1) + a1 (f-a_last)/(x-g2) = [a0 (f-a_first)(x-g2) + a1 (f-a_last)(x-1)] / D,  D = (x-1)(x-g2),
+// and D is inverted with one batched inversion per C points.
+//
+// Montgomery bookkeeping: mont_mul(u, v) = u v / R, so a value is carried as (true value) * R^e and every product
+// lowers e by one; nothing is converted, the exponents are arranged to cancel:
+//   x, f, a0, a1: e = 0;  D: e = -1;  prefix products: e = 1 - 2j;  1/D_j out of the backward pass: e = 3 for all j;
+//   [..]: e = -2, times 1/D: e = 0.   squares: e = -1, numerator: e = -1, cubic: e = -2, product: e = -4,
+//   times Z[r] = a2 / (x^n - 1) * R^5: e = 0.
+// 17 multiplications per point + 43 / C for the inversion (was 33 + 63 / C with per-value conversions).
+__device__ __forceinline__ uint32_t mont_inv_chain(uint32_t x)   // x^(p-2); p - 2 = 0b10 followed by thirty 1s
+{
+    const uint32_t x2 = mont_mul(x, x);
+    const uint32_t x3 = mont_mul(x2, x);
+    uint32_t t = mont_mul(x3, x3);
+    t = mont_mul(t, t);
+    const uint32_t x15 = mont_mul(t, x3);
+    const uint32_t x31 = mont_mul(mont_mul(x15, x15), x);
+    uint32_t r = x2;
+#pragma unroll 1
+    for (int g = 0; g < 6; g++) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) r = mont_mul(r, r);
+        r = mont_mul(r, x31);
+    }
+    return r;
+}
+
+struct CpCoef {
+    uint32_t a0, a1;       // alpha_0, alpha_1 reduced (field.rs:20-24), e = 0
+    uint32_t z[8];         // alpha_2 / (x^n - 1) for i mod 8, e = 5
+    uint32_t a_first, a_last;
+};
+__device__ __forceinline__ void cp_coef(const CpArgs& c, const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last,
+                                        CpCoef& k)
+{
+    k.a0 = reduce_u32(alpha_raw[0]);
+    k.a1 = reduce_u32(alpha_raw[1]);
+    const uint32_t a2 = reduce_u32(alpha_raw[2]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) k.z[r] = mont_mul(c.zinv_r6[r], a2);
+    k.a_first = a_first;
+    k.a_last = a_last;
+}
+
 template <int C>
 __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, const uint32_t* f,
-                                         uint32_t* out, uint32_t base, const uint32_t al_m[3],
-                                         uint32_t a_first, uint32_t a_last)
+                                         uint32_t* out, uint32_t base, const CpCoef& k)
 {
     const uint32_t B = 1u << LOG_BLOWUP;
     const uint32_t len_mask = (1u << c.log_len) - 1u;
@@ -90,29 +132,22 @@ __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, cons
     const uint32_t blk_mask = (1u << c.shard.log_block) - 1u;
     const uint32_t h_m = pow_h_m(pw, 1);
     uint32_t x = mont_mul(GEN, pow_h_m(pw, shard_global(c.shard, base)));  // canonical 5 h^i, i global
-    uint32_t xs[C], den[2 * C], pre[2 * C];
-    uint32_t acc = R1;  // Montgomery 1
+    uint32_t xs[C], D[C], pre[C];
+    uint32_t acc = R1;
 #pragma unroll
     for (int j = 0; j < C; j++) {
         xs[j] = x;
-        den[2 * j] = fsub(x, 1u);
-        den[2 * j + 1] = fsub(x, c.g2);
-        pre[2 * j] = acc;
-        acc = mont_mul(acc, to_mont(den[2 * j]));
-        pre[2 * j + 1] = acc;
-        acc = mont_mul(acc, to_mont(den[2 * j + 1]));
+        D[j] = mont_mul(fsub(x, 1u), fsub(x, c.g2));
+        pre[j] = acc;
+        acc = mont_mul(acc, D[j]);
         x = mont_mul(x, h_m);
     }
-    acc = mont_inv(acc);  // no denominator vanishes on the coset
-    uint32_t inv_m[2 * C];
+    acc = mont_inv_chain(acc);  // no denominator vanishes on the coset
 #pragma unroll
-    for (int j = 2 * C - 1; j >= 0; j--) {
-        inv_m[j] = mont_mul(acc, pre[j]);                // Montgomery form of 1/den[j]
-        acc = mont_mul(acc, to_mont(den[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < C; j++) {
-        uint32_t i = base + j;
+    for (int j = C - 1; j >= 0; j--) {
+        const uint32_t i = base + j;
+        const uint32_t inv_d = mont_mul(acc, pre[j]);        // 1 / D_j, e = 3
+        if (j) acc = mont_mul(acc, D[j]);
         uint32_t fx = f[i], fgx, fggx;
         if (!sharded) {
             fgx = f[(i + B) & len_mask];
@@ -123,14 +158,14 @@ __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, cons
             fgx = (t + B <= blk_mask) ? f[i + B] : c.halo[bl * 16 + (t + B - blk_mask - 1)];
             fggx = (t + 2 * B <= blk_mask) ? f[i + 2 * B] : c.halo[bl * 16 + (t + 2 * B - blk_mask - 1)];
         }
-        uint32_t p0 = mont_mul(fsub(fx, a_first), inv_m[2 * j]);
-        uint32_t p1 = mont_mul(fsub(fx, a_last), inv_m[2 * j + 1]);
-        uint32_t fx_m = to_mont(fx), fgx_m = to_mont(fgx);
-        uint32_t num = fsub(fsub(fggx, mont_mul(fgx, fgx_m)), mont_mul(fx, fx_m));
-        uint32_t cub_m = mont_mul(mont_mul(to_mont(fsub(xs[j], c.g3)), to_mont(fsub(xs[j], c.g2))),
-                                  to_mont(fsub(xs[j], c.g1)));
-        uint32_t p2 = mont_mul(mont_mul(num, cub_m), c.zinv_m[i & 7]);
-        out[i] = fadd(fadd(mont_mul(p0, al_m[0]), mont_mul(p1, al_m[1])), mont_mul(p2, al_m[2]));
+        const uint32_t d0 = fsub(xs[j], 1u), d1 = fsub(xs[j], c.g2);
+        const uint32_t s = fadd(mont_mul(mont_mul(fsub(fx, k.a_first), d1), k.a0),
+                                mont_mul(mont_mul(fsub(fx, k.a_last), d0), k.a1));
+        const uint32_t p01 = mont_mul(s, inv_d);
+        const uint32_t num = fsub(fsub(mont_mul(fggx, 1u), mont_mul(fgx, fgx)), mont_mul(fx, fx));
+        const uint32_t cub = mont_mul(mont_mul(fsub(xs[j], c.g3), d1), fsub(xs[j], c.g1));
+        const uint32_t p2 = mont_mul(mont_mul(num, cub), k.z[shard_global(c.shard, i) & 7]);
+        out[i] = fadd(p01, p2);
     }
 }
 
@@ -148,18 +183,13 @@ __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, ui
     } else if (SRC == SRC_CP) {
         const uint32_t* f = a.cp.f + (size_t)b * a.cp.f_stride;
         uint32_t* out = a.vals + (size_t)b * a.vals_stride;
-        uint32_t al_m[3], a_first, a_last;
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            uint32_t raw = a.cp.alpha_from_state ? a.state[b].alpha_raw[j] : a.cp.alpha_raw[j];
-            al_m[j] = to_mont(reduce_u32(raw));
-        }
-        a_first = a.cp.alpha_from_state ? a.state[b].a_first : a.cp.a_first;
-        a_last = a.cp.alpha_from_state ? a.state[b].a_last : a.cp.a_last;
-        if (count >= 8) { for (uint32_t o = 0; o < count; o += 8) cp_chunk<8>(a.cp, a.pow, f, out, base + o, al_m, a_first, a_last); }
-        else if (count == 4) cp_chunk<4>(a.cp, a.pow, f, out, base, al_m, a_first, a_last);
-        else if (count == 2) cp_chunk<2>(a.cp, a.pow, f, out, base, al_m, a_first, a_last);
-        else cp_chunk<1>(a.cp, a.pow, f, out, base, al_m, a_first, a_last);
+        CpCoef k;
+        if (a.cp.alpha_from_state) cp_coef(a.cp, a.state[b].alpha_raw, a.state[b].a_first, a.state[b].a_last, k);
+        else cp_coef(a.cp, a.cp.alpha_raw, a.cp.a_first, a.cp.a_last, k);
+        if (count >= 8) { for (uint32_t o = 0; o < count; o += 8) cp_chunk<8>(a.cp, a.pow, f, out, base + o, k); }
+        else if (count == 4) cp_chunk<4>(a.cp, a.pow, f, out, base, k);
+        else if (count == 2) cp_chunk<2>(a.cp, a.pow, f, out, base, k);
+        else cp_chunk<1>(a.cp, a.pow, f, out, base, k);
     }
 }
 
@@ -185,19 +215,26 @@ __global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_ker
     uint32_t d[8];
     const size_t lvl0 = ((size_t)1 << a.in_level) - 1;
     if (UNI && SRC != SRC_DIGESTS) {
-        // One shared copy of the data-block compression for leaves and nodes (smaller instruction footprint):
-        // the message is set up first, then the same code hashes it; nodes add the constant padding block.
+        // One shared copy of the round loop for leaves and nodes (small instruction footprint): the message is
+        // set up first, then the same code hashes it; nodes add the constant padding block.
         for (uint32_t i = 0; i < cnt; i++) {
             uint32_t w[16];
-            w[0] = vals[base + i]; w[1] = 0x80000000u;                      // merkle.rs:30-34
+            w[0] = vals[base + i];                                          // merkle.rs:30-34
+            if (UNI == 1) {
+                w[1] = 0x80000000u;
 #pragma unroll
-            for (int j = 2; j < 15; j++) w[j] = 0u;
-            w[15] = 32u;
+                for (int j = 2; j < 15; j++) w[j] = 0u;
+                w[15] = 32u;
+            }
             uint32_t m = i, lvl = 0, idx = base + i;
             bool node = false;
             for (;;) {
-                sha::init_iv(d);
-                sha::compress<V>(d, w);
+                if (UNI == 1) {
+                    sha::init_iv(d);
+                    sha::compress<V>(d, w);
+                } else {
+                    sha::compress_leaf_or_node<V>(d, w, !node);
+                }
                 if (node) sha::compress_pad64<V>(d);                        // merkle.rs:40-46
                 sha::store_digest(heap + 32 * ((((size_t)1 << (a.in_level - lvl)) - 1) + idx), d);
                 if (!(m & 1u)) break;
@@ -483,12 +520,11 @@ __global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab
     const uint32_t N = 1u << c.log_len;
     const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (base >= N) return;
-    uint32_t al_m[3];
     const bool from_state = c.alpha_from_state && st;
-#pragma unroll
-    for (int j = 0; j < 3; j++) al_m[j] = to_mont(reduce_u32(from_state ? st[b].alpha_raw[j] : c.alpha_raw[j]));
-    cp_chunk<4>(c, pw, c.f + (size_t)b * c.f_stride, out + (size_t)b * out_stride, base, al_m,
-                reduce_u32(from_state ? st[b].a_first : c.a_first), reduce_u32(from_state ? st[b].a_last : c.a_last));
+    CpCoef k;
+    if (from_state) cp_coef(c, st[b].alpha_raw, reduce_u32(st[b].a_first), reduce_u32(st[b].a_last), k);
+    else cp_coef(c, c.alpha_raw, reduce_u32(c.a_first), reduce_u32(c.a_last), k);
+    cp_chunk<4>(c, pw, c.f + (size_t)b * c.f_stride, out + (size_t)b * out_stride, base, k);
 }
 
 // ---------------------------------------------------------------- decommit gather (prover.rs:263-289)
@@ -821,8 +857,9 @@ cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, in
 #ifdef ZK_SHA_EXPERIMENTS
 #define ZK_VCASE(v) \
         case v: tree_pass_kernel<SRC_VALUES, v, 0><<<grid, PASS_THREADS, 0, s>>>(a); break; \
-        case 100 + v: tree_pass_kernel<SRC_VALUES, v, 1><<<grid, PASS_THREADS, 0, s>>>(a); break;
-        ZK_VCASE(0) ZK_VCASE(1) ZK_VCASE(17) ZK_VCASE(3) ZK_VCASE(19) ZK_VCASE(21)
+        case 100 + v: tree_pass_kernel<SRC_VALUES, v, 1><<<grid, PASS_THREADS, 0, s>>>(a); break; \
+        case 200 + v: tree_pass_kernel<SRC_VALUES, v, 2><<<grid, PASS_THREADS, 0, s>>>(a); break;
+        ZK_VCASE(0) ZK_VCASE(1) ZK_VCASE(2) ZK_VCASE(3) ZK_VCASE(35) ZK_VCASE(33) ZK_VCASE(19)
 #endif
         default: tree_pass_kernel<SRC_VALUES><<<grid, PASS_THREADS, 0, s>>>(a); break;
     }
