@@ -63,7 +63,7 @@ def test_merkle_full_size_properties(ctx, orc):
 
 
 # ---------------------------------------------------------------- K2 interpolation + LDE
-@pytest.mark.parametrize("log_n", [3, 4, 5, 8, 10, 11, 12, 13, 16, 20])
+@pytest.mark.parametrize("log_n", [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22])
 def test_interpolate_phantom_vs_oracle(ctx, orc, log_n):
     y = edge_values((1 << log_n) - 1, 200 + log_n)
     got = ctx.interpolate_subgroup(y, log_n)
@@ -78,7 +78,7 @@ def test_interpolate_full_vs_oracle(ctx, orc, log_n):
     assert np.array_equal(ctx.interpolate_subgroup(y, log_n), orc.interpolate_subgroup(y, log_n))
 
 
-@pytest.mark.parametrize("log_n", [3, 4, 7, 10, 11, 12, 13, 16, 20])
+@pytest.mark.parametrize("log_n", [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21])
 def test_lde_vs_oracle(ctx, orc, log_n):
     c = edge_values(1 << log_n, 400 + log_n)
     got = ctx.lde_coset(c, log_n)

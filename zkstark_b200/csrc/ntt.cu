@@ -22,11 +22,8 @@ struct NttPassArgs {
     const uint32_t* src; uint64_t src_stride;   // per proof (elements)
     uint32_t* dst; uint64_t dst_stride;
     uint32_t log_M;      // transform length
-    uint32_t log_R;      // radix of this pass
     uint32_t log_S;      // stride of this pass (strided kernel)
     uint32_t log_Msub;   // log_R + log_S
-    uint32_t n_cosets;   // 1 (iNTT) or 8 (LDE): coset r lives at + r*M in the work buffer
-    int coset_scale;     // load c_k (5 h^r)^k from the single coefficient array `src`
     int inverse;
     int use_scale;
     uint32_t scale_m;    // Montgomery constant multiplied into the final outputs (n^-1)
@@ -38,129 +35,162 @@ struct NttPassArgs {
     uint32_t coset_base; // index of the first coset of this launch (sharded LDE: one coset per launch)
 };
 
-constexpr int NTT_MAX_THREADS = 1024;  // block size is chosen per radix: 32 * clamp(R/16, 2, 32)
-constexpr int NTT_UNR = 4;             // independent global loads in flight per thread
 constexpr int TP = 33;  // padded tile pitch
+
+// Everything that shapes the inner loops is a compile-time constant of the radix: the block size, the rows a
+// warp moves in the load/store phases, the register-blocked rounds of the CTA-local transform and all their
+// shared-memory offsets (immediates in the LDS/STS).  The first version of these kernels took the radix at run
+// time and spent ~60 % of its 457 instructions per point (ncu, profiles/r1c) on index arithmetic and on
+// recomputing twiddles from the power tables; this one issues ~190.
+template <int LOG_R>
+struct NttCfg {
+    static constexpr int R = 1 << LOG_R;
+    static constexpr int NW = (R / 16) < 2 ? 2 : ((R / 16) > 32 ? 32 : (R / 16));  // warps per CTA
+    static constexpr int THREADS = 32 * NW;
+    static constexpr int RW = R / NW;  // rows per warp in the load / store phases (4 .. 32)
+};
 
 __device__ __forceinline__ uint32_t pw(const PowTab& t, uint32_t e)
 {
     return mont_mul(__ldg(t.lo + (e & ((1u << t.lo_bits) - 1u))), __ldg(t.hi + (e >> t.lo_bits)));
 }
 
-__device__ __forceinline__ uint32_t brev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
-
-// One register-blocked round of the in-place DIF: stages s .. s+LR-1 of the size-R transform along
+// One register-blocked round of the in-place DIF: stages S0 .. S0+LR-1 of the size-R transform along
 // the row index of sm[R][TP].  A thread owns one column (its lane) of one radix-2^LR group: it pulls
 // the 2^LR rows into registers, runs LR butterfly stages there, and writes them back -- one shared
 // memory round trip per LR stages.  Twiddles are warp-uniform (they depend on the row group only):
-// stage s' butterfly with in-group position j uses w_R^((j*stride + lo) << s'), a broadcast LDS.
-template <int LR>
-__device__ __forceinline__ void dif_round(uint32_t* sm, const uint32_t* tws, uint32_t log_R, uint32_t s)
+// stage S0+t, in-group position j uses w_R^((j*stride + lo) << (S0+t)), a broadcast LDS at an immediate
+// offset from one per-stage base.  In the last round (stride 1) the j = 0 twiddles are 1 and are skipped.
+template <int LOG_R, int S0, int LR>
+__device__ __forceinline__ void dif_round(uint32_t* sm, const uint32_t* tws, uint32_t warp, uint32_t lane)
 {
-    constexpr int RAD = 1 << LR;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const uint32_t log_stride = log_R - s - LR;
-    const uint32_t n_mini = 1u << (log_R - LR);
-    for (uint32_t q = warp; q < n_mini; q += nw) {
-        const uint32_t lo = q & ((1u << log_stride) - 1u), hi = q >> log_stride;
-        const uint32_t base = (hi << (log_R - s)) + lo;
-        uint32_t x[RAD];
+    constexpr int RAD = 1 << LR, LOG_STRIDE = LOG_R - S0 - LR, N_MINI = 1 << (LOG_R - LR);
+    constexpr int NW = NttCfg<LOG_R>::NW, TRIPS = (N_MINI + NW - 1) / NW;
 #pragma unroll
-        for (int d = 0; d < RAD; d++) x[d] = sm[(base + ((uint32_t)d << log_stride)) * TP + lane];
+    for (int i = 0; i < TRIPS; i++) {
+        const uint32_t q = warp + i * NW;
+        if ((N_MINI % NW) == 0 || q < (uint32_t)N_MINI) {
+            const uint32_t lo = q & ((1u << LOG_STRIDE) - 1u), hi = q >> LOG_STRIDE;
+            uint32_t* p = sm + ((hi << (LOG_R - S0)) + lo) * TP + lane;
+            uint32_t x[RAD];
 #pragma unroll
-        for (int t = 0; t < LR; t++) {
-            const int half = RAD >> (t + 1);
+            for (int d = 0; d < RAD; d++) x[d] = p[(d << LOG_STRIDE) * TP];
 #pragma unroll
-            for (int j = 0; j < half; j++) {
-                const uint32_t tw = tws[(((uint32_t)j << log_stride) + lo) << (s + t)];
+            for (int t = 0; t < LR; t++) {
+                const int half = RAD >> (t + 1);
+                const uint32_t* tp = tws + (lo << (S0 + t));
 #pragma unroll
-                for (int blk = 0; blk < RAD / (2 * half); blk++) {
-                    const int i0 = blk * 2 * half + j, i1 = i0 + half;
-                    const uint32_t u = x[i0], v = x[i1];
-                    x[i0] = fadd(u, v);
-                    x[i1] = mont_mul(fsub(u, v), tw);
+                for (int j = 0; j < half; j++) {
+                    const bool trivial = (LOG_STRIDE == 0 && j == 0);
+                    const uint32_t tw = trivial ? 0u : tp[j << (LOG_STRIDE + S0 + t)];
+#pragma unroll
+                    for (int blk = 0; blk < RAD / (2 * half); blk++) {
+                        const int i0 = blk * 2 * half + j, i1 = i0 + half;
+                        const uint32_t u = x[i0], v = x[i1];
+                        x[i0] = fadd(u, v);
+                        x[i1] = trivial ? fsub(u, v) : mont_mul(fsub(u, v), tw);
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int d = 0; d < RAD; d++) sm[(base + ((uint32_t)d << log_stride)) * TP + lane] = x[d];
+            for (int d = 0; d < RAD; d++) p[(d << LOG_STRIDE) * TP] = x[d];
+        }
     }
     __syncthreads();
 }
 
 // In-place DIF over the row index of sm[R][TP], all 32 columns; leaves X[c] at row brev(c).
-__device__ __forceinline__ void cta_dif(uint32_t* sm, const uint32_t* tws, uint32_t log_R)
+template <int LOG_R, int S0 = 0>
+__device__ __forceinline__ void cta_dif(uint32_t* sm, const uint32_t* tws, uint32_t warp, uint32_t lane)
 {
-    uint32_t s = 0;
-    while (s < log_R) {
-        const uint32_t rem = log_R - s;
-        const uint32_t r = rem > 4 ? (rem == 5 ? 3u : 4u) : rem;
-        switch (r) {
-            case 4: dif_round<4>(sm, tws, log_R, s); break;
-            case 3: dif_round<3>(sm, tws, log_R, s); break;
-            case 2: dif_round<2>(sm, tws, log_R, s); break;
-            default: dif_round<1>(sm, tws, log_R, s); break;
-        }
-        s += r;
+    if constexpr (S0 < LOG_R) {
+        constexpr int rem = LOG_R - S0;
+        constexpr int LR = rem > 4 ? (rem == 5 ? 3 : 4) : rem;
+        dif_round<LOG_R, S0, LR>(sm, tws, warp, lane);
+        cta_dif<LOG_R, S0 + LR>(sm, tws, warp, lane);
     }
 }
 
-// c_k * 5^k * h^(r k): coefficient scaling that moves the evaluation onto coset r (prover.rs:69)
-__device__ __forceinline__ uint32_t coset_scale(const NttPassArgs& a, uint32_t c, uint32_t k, uint32_t r)
+template <int BITS>
+__device__ __forceinline__ uint32_t brev_c(uint32_t x) { return BITS ? (__brev(x) >> (32 - BITS)) : 0u; }
+
+// Montgomery form of sigma^e, sigma = 5 h^rr: the coset shift of coset rr (prover.rs:69)
+__device__ __forceinline__ uint32_t sigma_pow_m(const NttPassArgs& a, uint32_t rr, uint32_t e)
 {
-    uint32_t v = mont_mul(c, pw(a.wpow, k));
-    r += a.coset_base;
-    if (r) v = mont_mul(v, pw(a.hpow, (uint32_t)(((uint64_t)r * k) & ((1u << a.hpow.log_N) - 1u))));
+    uint32_t v = pw(a.wpow, e);
+    if (rr) v = mont_mul(v, pw(a.hpow, (uint32_t)(((uint64_t)rr * e) & ((1u << a.hpow.log_N) - 1u))));
     return v;
 }
 
-__global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_strided_kernel(const NttPassArgs a)
+// Strided pass: M_sub = R*S.  The CTA owns 32 consecutive columns b and all R rows a of x[a S + b]:
+// load (with the coset scaling c_k sigma^k fused into the first LDE pass), CTA-local DIF, multiply by
+// w_Msub^(b c), store (c, b) in place.  Each warp moves a contiguous block of RW rows; the per-row
+// factors sigma^(k0 + u S) and w^(b (c0 + u)) advance along four independent multiplicative chains, so a
+// point costs two multiplications instead of two table look-ups (4 loads + 3 multiplications).
+template <int LOG_R, bool COSET>
+__global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_strided_kernel(const NttPassArgs a)
 {
+    using C = NttCfg<LOG_R>;
+    constexpr int R = C::R, RW = C::RW;
     extern __shared__ uint32_t smem[];
-    const uint32_t R = 1u << a.log_R, S = 1u << a.log_S;
     uint32_t* sm = smem;
     uint32_t* tws = smem + R * TP;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const uint32_t tiles_per_blk = S >> 5, n_blk = 1u << (a.log_M - a.log_Msub);
+    uint32_t* su = tws + R / 2;  // sigma^(m S), m = 1..4 (COSET)
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t log_tpb = a.log_S - 5;                        // tiles of 32 columns per block of M_sub
+    const uint32_t log_per_array = a.log_M - LOG_R - 5;
     uint32_t tile = blockIdx.x;
-    const uint32_t per_array = tiles_per_blk * n_blk;
-    const uint32_t r = tile / per_array;  // coset
-    tile -= r * per_array;
-    const uint32_t blk = tile / tiles_per_blk, b = ((tile % tiles_per_blk) << 5) + lane;
+    const uint32_t r = tile >> log_per_array;                    // coset
+    tile &= (1u << log_per_array) - 1u;
+    const uint32_t blk = tile >> log_tpb, b = ((tile & ((1u << log_tpb) - 1u)) << 5) + lane;
     const size_t M = (size_t)1 << a.log_M;
-    const uint32_t* src = a.src + (size_t)blockIdx.y * a.src_stride + (a.coset_scale ? 0 : r * M);
+    const uint32_t* src = a.src + (size_t)blockIdx.y * a.src_stride + (COSET ? 0 : r * M);
     uint32_t* dst = a.dst + (size_t)blockIdx.y * a.dst_stride + r * M;
     const size_t base = ((size_t)blk << a.log_Msub) + b;
+    const uint32_t rr = r + a.coset_base;
 
-    for (uint32_t i = threadIdx.x; i < R / 2; i += blockDim.x) tws[i] = a.tw[i];
-    // load (rows of 32 consecutive words = 128 B), NTT_UNR independent loads in flight per thread
-    for (uint32_t row0 = warp * NTT_UNR; row0 < R; row0 += nw * NTT_UNR) {
-        uint32_t v[NTT_UNR];
+    for (uint32_t i = threadIdx.x; i < R / 2; i += C::THREADS) tws[i] = a.tw[i];
+    if (COSET && threadIdx.x < 4) su[threadIdx.x] = sigma_pow_m(a, rr, (threadIdx.x + 1u) << a.log_S);
+    const uint32_t row0 = warp * RW;
+    uint32_t v[RW];
+    {
+        const uint32_t* p = src + base + ((size_t)row0 << a.log_S);
 #pragma unroll
-        for (int u = 0; u < NTT_UNR; u++) v[u] = src[base + ((size_t)(row0 + u) << a.log_S)];
+        for (int u = 0; u < RW; u++) v[u] = p[(size_t)u << a.log_S];
+    }
+    if (COSET) {
+        __syncthreads();
+        uint32_t t[4];
+        t[0] = sigma_pow_m(a, rr, (uint32_t)(base + ((size_t)row0 << a.log_S)));
 #pragma unroll
-        for (int u = 0; u < NTT_UNR; u++) {
-            if (a.coset_scale) v[u] = coset_scale(a, v[u], (uint32_t)(base + ((size_t)(row0 + u) << a.log_S)), r);
-            sm[(row0 + u) * TP + lane] = v[u];
+        for (int u = 1; u < 4; u++) t[u] = mont_mul(t[0], su[u - 1]);
+        const uint32_t step = su[3];
+#pragma unroll
+        for (int u = 0; u < RW; u++) {
+            v[u] = mont_mul(v[u], t[u & 3]);
+            if (u + 4 < RW) t[u & 3] = mont_mul(t[u & 3], step);
         }
     }
+#pragma unroll
+    for (int u = 0; u < RW; u++) sm[(row0 + u) * TP + lane] = v[u];
     __syncthreads();
-    cta_dif(sm, tws, a.log_R);
-    // twiddle w_Msub^(b c) and store (c,b)
-    const uint32_t N1 = (1u << a.hpow.log_N) - 1u, sh = a.hpow.log_N - a.log_Msub;
-    for (uint32_t c0 = warp * NTT_UNR; c0 < R; c0 += nw * NTT_UNR) {
-        uint32_t v[NTT_UNR], t[NTT_UNR];
+    cta_dif<LOG_R>(sm, tws, warp, lane);
+    // twiddle w_Msub^(b c) and store (c, b)
+    {
+        const uint32_t N1 = (1u << a.hpow.log_N) - 1u, sh = a.hpow.log_N - a.log_Msub;
+        uint32_t e1 = b << sh, e0 = (b * row0) << sh;
+        if (a.inverse) { e1 = ((N1 + 1u) - e1) & N1; e0 = ((N1 + 1u) - e0) & N1; }
+        const uint32_t w1 = pw(a.hpow, e1), w2 = mont_mul(w1, w1), w3 = mont_mul(w2, w1), w4 = mont_mul(w2, w2);
+        uint32_t t[4];
+        t[0] = pw(a.hpow, e0);
+        t[1] = mont_mul(t[0], w1); t[2] = mont_mul(t[0], w2); t[3] = mont_mul(t[0], w3);
+        uint32_t* q = dst + ((size_t)blk << a.log_Msub) + ((size_t)row0 << a.log_S) + b;
 #pragma unroll
-        for (int u = 0; u < NTT_UNR; u++) {
-            const uint32_t c = c0 + u;
-            uint32_t e = (b * c) << sh;
-            if (a.inverse) e = ((N1 + 1u) - e) & N1;
-            t[u] = pw(a.hpow, e);
-            v[u] = sm[brev(c, a.log_R) * TP + lane];
+        for (int u = 0; u < RW; u++) {
+            const uint32_t x = sm[brev_c<LOG_R>(row0 + u) * TP + lane];
+            q[(size_t)u << a.log_S] = mont_mul(x, t[u & 3]);
+            if (u + 4 < RW) t[u & 3] = mont_mul(t[u & 3], w4);
         }
-#pragma unroll
-        for (int u = 0; u < NTT_UNR; u++)
-            dst[((size_t)blk << a.log_Msub) + ((size_t)(c0 + u) << a.log_S) + b] = mont_mul(v[u], t[u]);
     }
 }
 
@@ -168,62 +198,63 @@ __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_strided_kernel(const NttP
 // that for every output digit c the 32 lanes write 32 consecutive words:
 //   lane = u * CS + r   (r = coset, u = index along the first-pass digit c1)
 //   out[(rho_nat + (M/R) c) * CS + r],  rho_nat = c1 + R1 c2
-__global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_final_kernel(const NttPassArgs a)
+template <int LOG_R, int LOG_CS, bool COSET>
+__global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_final_kernel(const NttPassArgs a)
 {
+    using C = NttCfg<LOG_R>;
+    constexpr int R = C::R, RW = C::RW, CS = 1 << LOG_CS;
     extern __shared__ uint32_t smem[];
-    const uint32_t R = 1u << a.log_R;
     uint32_t* sm = smem;
     uint32_t* tws = smem + R * TP;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const uint32_t CS = a.n_cosets, R1 = 1u << a.log_R1, Q2 = 1u << a.log_Q2;
-    uint32_t U = 32 / CS;           // lanes along c1
-    if (U > R1) U = R1;
-    const uint32_t tiles_c1 = R1 / U;
-    const uint32_t c2 = blockIdx.x / tiles_c1, c1_0 = (blockIdx.x % tiles_c1) * U;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t log_U = (5 - LOG_CS) < a.log_R1 ? (5 - LOG_CS) : a.log_R1;   // lanes along c1
+    const uint32_t log_tiles_c1 = a.log_R1 - log_U;
+    const uint32_t c2 = blockIdx.x >> log_tiles_c1, c1_0 = (blockIdx.x & ((1u << log_tiles_c1) - 1u)) << log_U;
     const size_t M = (size_t)1 << a.log_M;
     const uint32_t* srcb = a.src + (size_t)blockIdx.y * a.src_stride;
     uint32_t* dstb = a.dst + (size_t)blockIdx.y * a.dst_stride;
 
-    for (uint32_t i = threadIdx.x; i < R / 2; i += blockDim.x) tws[i] = a.tw[i];
+    for (uint32_t i = threadIdx.x; i < R / 2; i += C::THREADS) tws[i] = a.tw[i];
     // load: the tile is n_rows contiguous rows of R words; flat index f = l * R + a0, a warp reads 32
-    // consecutive words of one row per access (R >= 32), NTT_UNR accesses in flight
-    const uint32_t n_rows = U * CS, total = n_rows << a.log_R;
-    for (uint32_t f0 = threadIdx.x; f0 < total; f0 += blockDim.x * NTT_UNR) {
-        uint32_t v[NTT_UNR];
+    // consecutive words of one row per access (R >= 32), all RW accesses of a thread in flight
+    const uint32_t n_rows = CS << log_U, total = n_rows << LOG_R;
+    uint32_t v[RW];
 #pragma unroll
-        for (int u = 0; u < NTT_UNR; u++) {
-            const uint32_t f = f0 + u * blockDim.x;
-            if (f < total) {
-                const uint32_t l = f >> a.log_R, a0 = f & (R - 1);
-                const uint32_t rr = l % CS, uu = l / CS;
-                const size_t q = (size_t)(c1_0 + uu) * Q2 + c2;
-                v[u] = srcb[(a.coset_scale ? 0 : rr * M) + (q << a.log_R) + a0];
-            }
+    for (int u = 0; u < RW; u++) {
+        const uint32_t f = threadIdx.x + u * C::THREADS;
+        if (f < total) {
+            const uint32_t l = f >> LOG_R, a0 = f & (R - 1);
+            const uint32_t rr = l & (CS - 1), uu = l >> LOG_CS;
+            const size_t q = ((size_t)(c1_0 + uu) << a.log_Q2) + c2;
+            v[u] = srcb[(COSET ? 0 : rr * M) + (q << LOG_R) + a0];
         }
+    }
 #pragma unroll
-        for (int u = 0; u < NTT_UNR; u++) {
-            const uint32_t f = f0 + u * blockDim.x;
-            if (f < total) {
-                const uint32_t l = f >> a.log_R, a0 = f & (R - 1);
-                if (a.coset_scale) {
-                    const uint32_t rr = l % CS, uu = l / CS;
-                    const size_t q = (size_t)(c1_0 + uu) * Q2 + c2;
-                    v[u] = coset_scale(a, v[u], (uint32_t)((q << a.log_R) + a0), rr);
-                }
-                sm[a0 * TP + l] = v[u];
+    for (int u = 0; u < RW; u++) {
+        const uint32_t f = threadIdx.x + u * C::THREADS;
+        if (f < total) {
+            const uint32_t l = f >> LOG_R, a0 = f & (R - 1);
+            if (COSET) {  // single-pass transforms only (M = R <= 1024): the plain table form is fine here
+                const uint32_t rr = (l & (CS - 1)) + a.coset_base, uu = l >> LOG_CS;
+                const size_t q = ((size_t)(c1_0 + uu) << a.log_Q2) + c2;
+                v[u] = mont_mul(v[u], sigma_pow_m(a, rr, (uint32_t)((q << LOG_R) + a0)));
             }
+            sm[a0 * TP + l] = v[u];
         }
     }
     __syncthreads();
-    cta_dif(sm, tws, a.log_R);
+    cta_dif<LOG_R>(sm, tws, warp, lane);
     if (lane < n_rows) {
-        const uint32_t r = lane % CS, u = lane / CS;
-        const size_t rho = (size_t)(c1_0 + u) + (size_t)R1 * c2;
-        const uint32_t log_rows = a.log_M - a.log_R;
-        for (uint32_t c = warp; c < R; c += nw) {
-            uint32_t v = sm[brev(c, a.log_R) * TP + lane];
-            if (a.use_scale) v = mont_mul(v, a.scale_m);
-            dstb[(rho + ((size_t)c << log_rows)) * CS + r] = v;
+        const uint32_t r = lane & (CS - 1), u = lane >> LOG_CS;
+        const size_t rho = (size_t)(c1_0 + u) + ((size_t)c2 << a.log_R1);
+        const uint32_t log_rows = a.log_M - LOG_R;
+        uint32_t* q = dstb + (rho << LOG_CS) + r;
+#pragma unroll
+        for (int i = 0; i < RW; i++) {
+            const uint32_t c = warp + i * C::NW;
+            uint32_t x = sm[brev_c<LOG_R>(c) * TP + lane];
+            if (a.use_scale) x = mont_mul(x, a.scale_m);
+            q[((size_t)c << log_rows) << LOG_CS] = x;
         }
     }
 }
@@ -274,14 +305,6 @@ static NttPlan make_plan(uint32_t mu, uint32_t log_arrays)
     for (uint32_t i = 0; i < np; i++) p.log_r[i] = (mu + np - 1 - i) / np;  // as even as possible, larger first
     return p;
 }
-static inline uint32_t ntt_threads(uint32_t log_R)
-{
-    uint32_t nw = (1u << log_R) >> 4;
-    if (nw < 2) nw = 2;
-    if (nw > 32) nw = 32;
-    return nw * 32;
-}
-
 // tw tables: for radix 2^m the R/2 entries start at offset 2^(m-1) - 1 (m >= 1)
 static inline size_t tw_off(uint32_t m) { return m ? ((size_t)1 << (m - 1)) - 1 : 0; }
 
@@ -291,13 +314,38 @@ struct NttTables {
     PowTab hpow, wpow;
 };
 
-static cudaError_t set_smem(const void* fn, size_t bytes)
+template <typename K>
+static cudaError_t launch_k(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, const NttPassArgs& a)
 {
-    if (bytes > 48 * 1024) return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    return cudaSuccess;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<grid, threads, smem, s>>>(a);
+    return cudaGetLastError();
 }
 
-// Transform `n_cosets` arrays of length 2^mu.  Passes before the last run in place on `work`
+template <int LOG_R>
+static cudaError_t launch_strided(bool coset, dim3 grid, cudaStream_t s, const NttPassArgs& a)
+{
+    const size_t smem = ((size_t)NttCfg<LOG_R>::R * TP + NttCfg<LOG_R>::R / 2 + 4) * 4;
+    if (coset) return launch_k(ntt_strided_kernel<LOG_R, true>, grid, NttCfg<LOG_R>::THREADS, smem, s, a);
+    return launch_k(ntt_strided_kernel<LOG_R, false>, grid, NttCfg<LOG_R>::THREADS, smem, s, a);
+}
+template <int LOG_R>
+static cudaError_t launch_final(bool coset, uint32_t n_cosets, dim3 grid, cudaStream_t s, const NttPassArgs& a)
+{
+    const size_t smem = ((size_t)NttCfg<LOG_R>::R * TP + NttCfg<LOG_R>::R / 2 + 1) * 4;
+    const int th = NttCfg<LOG_R>::THREADS;
+    if (n_cosets == 8) {
+        if (coset) return launch_k(ntt_final_kernel<LOG_R, 3, true>, grid, th, smem, s, a);
+        return launch_k(ntt_final_kernel<LOG_R, 3, false>, grid, th, smem, s, a);
+    }
+    if (coset) return launch_k(ntt_final_kernel<LOG_R, 0, true>, grid, th, smem, s, a);
+    return launch_k(ntt_final_kernel<LOG_R, 0, false>, grid, th, smem, s, a);
+}
+
+// Transform `n_cosets` (1 or 8) arrays of length 2^mu.  Passes before the last run in place on `work`
 // (n_cosets * M words per proof); the last writes natural order (interleaved over cosets) to dst.
 // With coset_scale the first pass reads the single coefficient array `coeffs` instead of `work`.
 static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint32_t n_cosets, bool coset_scale,
@@ -305,12 +353,12 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
                            uint64_t work_stride, uint32_t* dst, uint64_t dst_stride, bool use_scale,
                            uint32_t scale_m, uint32_t batch, int* n_launches, uint32_t coset_base = 0)
 {
+    if (n_cosets != 1 && n_cosets != 8) return cudaErrorInvalidValue;
     uint32_t log_arrays = 0;
     while ((1u << log_arrays) < n_cosets * batch) log_arrays++;
     NttPlan p = make_plan(mu, log_arrays);
     NttPassArgs a{};
     a.log_M = mu;
-    a.n_cosets = n_cosets;
     a.inverse = inverse;
     a.hpow = T.hpow;
     a.wpow = T.wpow;
@@ -319,29 +367,35 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     uint32_t log_S = mu;
     cudaError_t e;
     for (uint32_t i = 0; i + 1 < p.n_pass; i++) {
-        a.log_R = p.log_r[i];
+        const uint32_t log_R = p.log_r[i];
         a.log_Msub = log_S;
-        log_S -= a.log_R;
+        log_S -= log_R;
         a.log_S = log_S;
-        a.tw = twb + tw_off(a.log_R);
-        a.coset_scale = (i == 0 && coset_scale);
+        a.tw = twb + tw_off(log_R);
+        const bool cs = (i == 0 && coset_scale);
         a.src = (i == 0) ? coeffs : work;
         a.src_stride = (i == 0) ? coeffs_stride : work_stride;
         a.dst = work;
         a.dst_stride = work_stride;
-        size_t smem = ((size_t)(1u << a.log_R) * TP + (1u << a.log_R) / 2) * 4;
-        if ((e = set_smem((const void*)ntt_strided_kernel, smem)) != cudaSuccess) return e;
-        uint32_t tiles = (1u << (mu - 5)) >> a.log_R;  // (M / (R*S)) * (S/32)
+        uint32_t tiles = (1u << (mu - 5)) >> log_R;  // (M / (R*S)) * (S/32)
         dim3 grid(tiles * n_cosets, batch);
-        ntt_strided_kernel<<<grid, ntt_threads(a.log_R), smem, s>>>(a);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        switch (log_R) {
+            case 5: e = launch_strided<5>(cs, grid, s, a); break;
+            case 6: e = launch_strided<6>(cs, grid, s, a); break;
+            case 7: e = launch_strided<7>(cs, grid, s, a); break;
+            case 8: e = launch_strided<8>(cs, grid, s, a); break;
+            case 9: e = launch_strided<9>(cs, grid, s, a); break;
+            case 10: e = launch_strided<10>(cs, grid, s, a); break;
+            default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
     }
-    a.log_R = p.log_r[p.n_pass - 1];
-    a.log_Msub = a.log_R;
+    const uint32_t log_R = p.log_r[p.n_pass - 1];
+    a.log_Msub = log_R;
     a.log_S = 0;
-    a.tw = twb + tw_off(a.log_R);
-    a.coset_scale = (p.n_pass == 1 && coset_scale);
+    a.tw = twb + tw_off(log_R);
+    const bool cs = (p.n_pass == 1 && coset_scale);
     a.src = (p.n_pass == 1) ? coeffs : work;
     a.src_stride = (p.n_pass == 1) ? coeffs_stride : work_stride;
     a.dst = dst;
@@ -351,14 +405,22 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     a.log_R1 = p.n_pass >= 2 ? p.log_r[0] : 0;
     a.log_Q2 = p.n_pass == 3 ? p.log_r[1] : 0;
     {
-        size_t smem = ((size_t)(1u << a.log_R) * TP + (1u << a.log_R) / 2 + 1) * 4;
-        if ((e = set_smem((const void*)ntt_final_kernel, smem)) != cudaSuccess) return e;
-        uint32_t R1 = 1u << a.log_R1, U = 32 / n_cosets;
-        if (U > R1) U = R1;
-        uint32_t tiles = (R1 / U) << a.log_Q2;
+        uint32_t log_U = n_cosets == 8 ? 2 : 5;
+        if (log_U > a.log_R1) log_U = a.log_R1;
+        uint32_t tiles = 1u << (a.log_R1 - log_U + a.log_Q2);
         dim3 grid(tiles, batch);
-        ntt_final_kernel<<<grid, ntt_threads(a.log_R), smem, s>>>(a);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        switch (log_R) {
+            case 3: e = launch_final<3>(cs, n_cosets, grid, s, a); break;
+            case 4: e = launch_final<4>(cs, n_cosets, grid, s, a); break;
+            case 5: e = launch_final<5>(cs, n_cosets, grid, s, a); break;
+            case 6: e = launch_final<6>(cs, n_cosets, grid, s, a); break;
+            case 7: e = launch_final<7>(cs, n_cosets, grid, s, a); break;
+            case 8: e = launch_final<8>(cs, n_cosets, grid, s, a); break;
+            case 9: e = launch_final<9>(cs, n_cosets, grid, s, a); break;
+            case 10: e = launch_final<10>(cs, n_cosets, grid, s, a); break;
+            default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
     }
     return cudaSuccess;
