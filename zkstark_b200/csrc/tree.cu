@@ -532,6 +532,14 @@ __global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab
 //   4 x (u32 value | u64 len | len digests)          f[x], f[x+8], f[x+16], cp[x]
 //   L x (u32 cp_i[x_i] | u32 cp_i[nx_i] | u64 len | path(x_i) | u64 len | path(nx_i))
 // merkle.rs:54-71 `trace`: sibling of heap index i is i-1 (i even) or i+1 (i odd), leaf -> root.
+__device__ __forceinline__ size_t layer_vals_off_dev(uint32_t log_N, uint32_t i)   // sum_{j<i} 2^(log_N-j)
+{
+    return ((size_t)2 << log_N) - ((size_t)2 << (log_N - i));
+}
+__device__ __forceinline__ size_t layer_heap_off_dev(uint32_t log_N, uint32_t i)   // common.cuh layer_heap_off: sum_{j<i} 64*2^(log_N-j)
+{
+    return 64 * (((size_t)2 << log_N) - ((size_t)2 << (log_N - i)));
+}
 struct DecommitArgs {
     uint32_t log_n;
     const uint32_t* f_eval; uint64_t f_stride;
@@ -542,19 +550,16 @@ struct DecommitArgs {
     uint8_t* transcript; uint64_t transcript_stride;
 };
 
-__device__ __forceinline__ void copy_sibling(uint8_t* dst, const uint8_t* heap, uint32_t log_size,
-                                             uint32_t leaf, uint32_t step)
+// `step` levels above leaf `leaf` of a 2^log_size-leaf heap, the sibling (merkle.rs:58-66)
+__device__ __forceinline__ size_t sibling_node(uint32_t log_size, uint32_t leaf, uint32_t step)
 {
-    // heap index of the ancestor `step` levels above the leaf, then its sibling
-    size_t i = ((((size_t)1 << log_size) - 1) + leaf);
-    for (uint32_t s = 0; s < step; s++) i = (i - 1) >> 1;
-    size_t sib = (i & 1) ? i + 1 : i - 1;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(heap + 32 * sib);
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);  // transcript offsets are 4-byte aligned
-#pragma unroll
-    for (int w = 0; w < 8; w++) d[w] = src[w];
+    const size_t i = (((size_t)1 << (log_size - step)) - 1) + (leaf >> step);  // ancestor, heap index
+    return (i & 1) ? i + 1 : i - 1;
 }
 
+// Every sibling digest of every record is an independent 32-byte gather, so the work is a flat list of
+// (record, path, step) items spread over the CTA: all loads are in flight at once (the first version walked
+// the 4 + L records one after the other, ~24 dependent DRAM round trips = 60 us at k = 20).
 __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
 {
     const uint32_t b = blockIdx.x;
@@ -566,41 +571,28 @@ __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
     const uint32_t* lay = a.layers + (size_t)b * a.layers_stride;
     const uint8_t* lh = a.layer_heaps + (size_t)b * a.layer_heaps_stride;
     const uint32_t x = (uint32_t)((size_t)ps->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
-    size_t off = 84 + 36 * (size_t)L;
+    const size_t off0 = 84 + 36 * (size_t)L;
+    const size_t rec0 = 12 + 32 * (size_t)log_N;
     if (threadIdx.x == 0) {
         // prover.rs:238: the last FRI polynomial has degree 0, i.e. its 8 evaluations are equal
-        size_t voff = 0;
-        for (uint32_t j = 0; j < L; j++) voff += (size_t)1 << (log_N - j);
+        const size_t voff = layer_vals_off_dev(log_N, L);
         uint32_t bad = 0;
         for (uint32_t j = 1; j < (N >> L); j++) bad |= (lay[voff + j] != lay[voff]);
         ps->pad[0] = bad;
     }
-    // records 0..3
-    const size_t rec0 = 12 + 32 * (size_t)log_N;
-    for (uint32_t r = 0; r < 4; r++) {
-        const uint32_t idx = (r < 3) ? x + r * B : x;
-        const uint32_t* vals = (r < 3) ? f : lay;
-        const uint8_t* heap = (r < 3) ? fh : lh;
-        uint8_t* rec = tr + off + r * rec0;
-        if (threadIdx.x == 0) {
-            *reinterpret_cast<uint32_t*>(rec) = vals[idx];
-            *reinterpret_cast<uint32_t*>(rec + 4) = log_N;   // u64 LE length
+    // values and length prefixes: one thread per record
+    for (uint32_t r = threadIdx.x; r < 4 + L; r += blockDim.x) {
+        if (r < 4) {                                             // prover.rs:266-277
+            uint8_t* rec = tr + off0 + r * rec0;
+            *reinterpret_cast<uint32_t*>(rec) = (r < 3) ? f[x + r * B] : lay[x];
+            *reinterpret_cast<uint32_t*>(rec + 4) = log_N;       // u64 LE length
             *reinterpret_cast<uint32_t*>(rec + 8) = 0;
-        }
-        for (uint32_t s = threadIdx.x; s < log_N; s += blockDim.x)
-            copy_sibling(rec + 12 + 32 * (size_t)s, heap, log_N, idx, s);
-    }
-    off += 4 * rec0;
-    // FRI layer records (prover.rs:280-289)
-    for (uint32_t i = 0; i < L; i++) {
-        const uint32_t lg = log_N - i, len = 1u << lg;
-        const uint32_t xi = x & (len - 1), nx = (xi + len / 2) & (len - 1);
-        size_t voff = 0, hoff = 0;
-        for (uint32_t j = 0; j < i; j++) { voff += (size_t)1 << (log_N - j); hoff += (size_t)64 << (log_N - j); }
-        const uint32_t* vals = lay + voff;
-        const uint8_t* heap = lh + hoff;
-        uint8_t* rec = tr + off;
-        if (threadIdx.x == 0) {
+        } else {                                                 // prover.rs:280-289
+            const uint32_t i = r - 4, lg = log_N - i, len = 1u << lg;
+            const uint32_t xi = x & (len - 1), nx = (xi + len / 2) & (len - 1);
+            const uint32_t* vals = lay + layer_vals_off_dev(log_N, i);
+            // records before this one: sum_{j<i} (24 + 64 (log_N - j))
+            uint8_t* rec = tr + off0 + 4 * rec0 + 24 * (size_t)i + 64 * ((size_t)i * log_N - (size_t)i * (i - 1) / 2);
             *reinterpret_cast<uint32_t*>(rec) = vals[xi];
             *reinterpret_cast<uint32_t*>(rec + 4) = vals[nx];
             *reinterpret_cast<uint32_t*>(rec + 8) = lg;
@@ -608,11 +600,36 @@ __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
             *reinterpret_cast<uint32_t*>(rec + 16 + 32 * (size_t)lg) = lg;
             *reinterpret_cast<uint32_t*>(rec + 20 + 32 * (size_t)lg) = 0;
         }
-        for (uint32_t s = threadIdx.x; s < 2 * lg; s += blockDim.x) {
-            if (s < lg) copy_sibling(rec + 16 + 32 * (size_t)s, heap, lg, xi, s);
-            else copy_sibling(rec + 24 + 32 * (size_t)lg + 32 * (size_t)(s - lg), heap, lg, nx, s - lg);
+    }
+    // sibling digests: item = (record r, path p, step s); 8 lanes move one digest (4 bytes each)
+    const uint32_t per_rec_f = log_N;
+    const uint32_t n_items = 4 * per_rec_f + 2 * (L * log_N - L * (L - 1) / 2);
+    const uint32_t sub = threadIdx.x & 7;
+    for (uint32_t it = threadIdx.x >> 3; it < n_items; it += blockDim.x >> 3) {
+        const uint8_t* heap;
+        uint8_t* dst;
+        uint32_t lg, leaf, s;
+        if (it < 4 * per_rec_f) {
+            const uint32_t r = it / per_rec_f;
+            s = it - r * per_rec_f;
+            lg = log_N;
+            leaf = (r < 3) ? x + r * B : x;
+            heap = (r < 3) ? fh : lh;
+            dst = tr + off0 + r * rec0 + 12 + 32 * (size_t)s;
+        } else {
+            uint32_t rem = it - 4 * per_rec_f, i = 0;
+            while (rem >= 2 * (log_N - i)) { rem -= 2 * (log_N - i); i++; }   // <= L iterations, no memory traffic
+            lg = log_N - i;
+            const uint32_t len = 1u << lg, xi = x & (len - 1), nx = (xi + len / 2) & (len - 1);
+            const uint32_t path = rem >= lg;
+            s = path ? rem - lg : rem;
+            leaf = path ? nx : xi;
+            heap = lh + layer_heap_off_dev(log_N, i);
+            uint8_t* rec = tr + off0 + 4 * rec0 + 24 * (size_t)i + 64 * ((size_t)i * log_N - (size_t)i * (i - 1) / 2);
+            dst = rec + (path ? 24 + 32 * (size_t)lg : 16) + 32 * (size_t)s;
         }
-        off += 24 + 64 * (size_t)lg;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(heap + 32 * sibling_node(lg, leaf, s));
+        reinterpret_cast<uint32_t*>(dst)[sub] = src[sub];        // transcript offsets are 4-byte aligned
     }
 }
 
