@@ -971,13 +971,14 @@ int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
 {
     if (!ctx) return ZK_ERR_INVALID;
     ctx->bench_variant = sha_variant;
-    ctx->bench_k = leaf_pass_k;
+    ctx->bench_k = leaf_pass_k & 0xffu;
+    if (leaf_pass_k >> 8) set_coop_cnt((leaf_pass_k >> 8) - 1);   // bits 8..: 1 + widest cooperative tile level (0: keep)
     return ZK_OK;
 }
 
 int zk_bench_set_tile_direct_log(zk_ctx* ctx, uint32_t log_leaves)
 {
-    if (!ctx || (log_leaves & 0xffu) > 2 * TILE_LOG || (log_leaves >> 8) > TILE_LOG) return ZK_ERR_INVALID;
+    if (!ctx || (log_leaves & 0xffu) > 2 * TILE_LOG || ((log_leaves >> 8) & 0xffu) > TILE_LOG) return ZK_ERR_INVALID;
     set_tile_direct_log(log_leaves);
     return ZK_OK;
 }

@@ -11,7 +11,7 @@ namespace zk {
 
 constexpr uint32_t LOG_BLOWUP = 3;  // 8192/1024 (prover.rs:56-57); literal +8/+16 at prover.rs:268-271
 constexpr uint32_t MAX_LOG_N = 27;  // N = 2^30 is the largest power-of-two subgroup of F_p^*
-constexpr uint32_t TILE_LOG = 10;   // the tile kernel reduces 2^TILE_LOG inputs per CTA, two per thread
+constexpr uint32_t TILE_LOG = 11;   // the tile kernel reduces up to 2^TILE_LOG inputs per CTA, two per thread
 constexpr uint32_t TILE_PAIRS = 1u << (TILE_LOG - 1);
 constexpr uint32_t TILE_MIN_LOG = 7;
 #ifndef ZK_TILE_SHA_V
@@ -19,6 +19,15 @@ constexpr uint32_t TILE_MIN_LOG = 7;
 #endif
 #ifndef ZK_TILE_DIRECT_LOG
 #define ZK_TILE_DIRECT_LOG 17  // trees up to this many leaves (x batch) go leaves -> root in one tile-kernel launch
+#endif
+#ifndef ZK_TILE_SHIFT
+#define ZK_TILE_SHIFT 7         // the tile kernel splits a tree into 2^7 = 128 tiles: one CTA per SM (148 SMs)
+#endif
+#ifndef ZK_PASS_LOG_THREADS
+#define ZK_PASS_LOG_THREADS 18  // the leaf pass runs about this many threads (log2), each hashing a 2^k-leaf subtree
+#endif
+#ifndef ZK_COOP_CNT
+#define ZK_COOP_CNT 128         // tile kernel: levels with <= this many nodes hash each node with a warp pair (0: off)
 #endif
 #ifndef ZK_PASS_THREADS
 #define ZK_PASS_THREADS 128
@@ -121,6 +130,7 @@ struct TreeArgs {
     uint32_t in_level;      // level the kernel consumes (== log_size for leaf passes)
     uint32_t k;             // levels produced by one thread of a pass kernel
     uint32_t log_tile;      // tile kernel: inputs per CTA (set by the launcher)
+    uint32_t coop_cnt;      // tile kernel: levels of at most this many nodes use two warps per node (set by the launcher)
     ProofState* state;      // per proof (may be null for POST_NONE)
     uint32_t* counters;     // per proof tile-arrival counter (zero between launches); needed above 2^TILE_LOG inputs
     uint8_t* transcript;    // per proof
@@ -143,6 +153,7 @@ cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int*
 // the leaf pass alone (bench support): a.in_level / a.k preset by the caller
 cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant);
 void set_tile_direct_log(uint32_t v);
+void set_coop_cnt(uint32_t v);
 cudaError_t sha_init_constants();
 cudaError_t launch_node_latency(cudaStream_t s, uint32_t* out, uint32_t reps, uint32_t warps, int variant, long long* cycles);
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,

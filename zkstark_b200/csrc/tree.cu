@@ -394,8 +394,95 @@ __device__ void post_root(const TreeArgs& a, uint32_t b, const uint32_t root[8])
 // single digest level by level (two inputs per thread, then word-major ping-pong buffers in shared memory:
 // conflict-free 64-bit reads, one barrier per level), writing every node into the heap.  The CTA that finishes
 // LAST (per-proof arrival counter, threadfence-reduction pattern: no co-residency requirement, no grid sync)
-// reduces the <= 2^TILE_LOG tile roots to the tree root and runs the Fiat-Shamir step (channel.rs:19-32), so
-// a whole upper tree + challenge draw is a single launch instead of four digest passes + a top kernel.
+// reduces the tile roots to the tree root and runs the Fiat-Shamir step (channel.rs:19-32), so a whole upper
+// tree + challenge draw is a single launch instead of four digest passes + a top kernel.
+//
+// Narrow levels are LATENCY bound: a lone warp needs ~3.0 us per node (measured in-kernel, profiles/README r1e) because
+// its 18 ALU-pipe instructions per round issue at one per 2 cycles, while the dependency chain of a round is only
+// ~20 cycles.  Levels with <= 32*COOP_PAIRS nodes therefore hash every node with TWO warps on two different SM
+// sub-partitions: the helper warp computes the message schedule K[t] + W[t], t = 16..63, into shared memory, 16 words
+// at a time, and the main warp runs the 64 rounds consuming them (named barriers 1..12, helper arrives / main
+// syncs), then the constant padding block.  For leaf sources the pair also hashes the left / right leaf in parallel.
+constexpr uint32_t COOP_PAIRS = 4;              // named barriers 1 + 3*pair + {0,1,2} <= 12
+constexpr uint32_t COOP_WORDS = 64 * 32;        // per pair: 48 schedule words + 16 exchange words, one column per lane
+extern __shared__ __align__(16) uint32_t tile_smem[];
+
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t n)
+{
+    asm volatile("barrier.sync.aligned %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t n)
+{
+    asm volatile("barrier.arrive.aligned %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// main warp of a pair: node hash (merkle.rs:40-46) with the schedule of rounds 16..63 read from tile_smem[kw + ..]
+template <int V>
+__device__ __noinline__ Dig8 coop_main(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                       uint32_t w6, uint32_t w7, uint32_t w8, uint32_t w9, uint32_t w10, uint32_t w11,
+                                       uint32_t w12, uint32_t w13, uint32_t w14, uint32_t w15, uint32_t kw, uint32_t bar)
+{
+    constexpr sha::Consts C = sha::make_consts();
+    using sha::addv; using sha::bsig0; using sha::bsig1; using sha::ch; using sha::maj;
+    const uint32_t w[16] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11, w12, w13, w14, w15};
+    uint32_t a = ZK_SHA_IV0, b = ZK_SHA_IV1, c = ZK_SHA_IV2, d = ZK_SHA_IV3, e = ZK_SHA_IV4, f = ZK_SHA_IV5,
+             g = ZK_SHA_IV6, h = ZK_SHA_IV7;
+#define ZK_KW_FIRST(j) (addv<V, 32>(w[j], C.k[j]))
+    ZK_SHA_16ROUNDS(V, ZK_KW_FIRST)
+#undef ZK_KW_FIRST
+#pragma unroll 1
+    for (uint32_t ck = 0; ck < 3; ck++) {
+        bar_sync(bar + ck, 64);                                    // the helper has published words 16*ck .. 16*ck+15
+        uint32_t kk[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) kk[j] = tile_smem[kw + (16 * ck + j) * 32];
+#define ZK_KW_COOP(j) (kk[j])
+        ZK_SHA_16ROUNDS(V, ZK_KW_COOP)
+#undef ZK_KW_COOP
+    }
+    Dig8 o;
+    o.v[0] = a + ZK_SHA_IV0; o.v[1] = b + ZK_SHA_IV1; o.v[2] = c + ZK_SHA_IV2; o.v[3] = d + ZK_SHA_IV3;
+    o.v[4] = e + ZK_SHA_IV4; o.v[5] = f + ZK_SHA_IV5; o.v[6] = g + ZK_SHA_IV6; o.v[7] = h + ZK_SHA_IV7;
+    sha::compress_pad64<V>(o.v);
+    return o;
+}
+// helper warp of a pair: K[t] + W[t] for t = 16..63 of the same 16-word message
+template <int V>
+__device__ __noinline__ void coop_helper(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                         uint32_t w6, uint32_t w7, uint32_t w8, uint32_t w9, uint32_t w10, uint32_t w11,
+                                         uint32_t w12, uint32_t w13, uint32_t w14, uint32_t w15, uint32_t kw, uint32_t bar)
+{
+    using sha::addv; using sha::ssig0; using sha::ssig1;
+    uint32_t w[16] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11, w12, w13, w14, w15};
+#pragma unroll 1
+    for (uint32_t ck = 0; ck < 3; ck++) {
+        uint32_t kk[16];
+        {
+            const uint4* kp = reinterpret_cast<const uint4*>(sha::c_k + 16 + 16 * ck);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 t = kp[q];
+                kk[4 * q] = t.x; kk[4 * q + 1] = t.y; kk[4 * q + 2] = t.z; kk[4 * q + 3] = t.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            w[j] = addv<V, 2>(addv<V, 2>(addv<V, 2>(w[j], ssig1<V>(w[(j + 14) & 15])), w[(j + 9) & 15]),
+                              ssig0<V>(w[(j + 1) & 15]));
+            tile_smem[kw + (16 * ck + j) * 32] = addv<V, 2>(w[j], kk[j]);
+        }
+        bar_arrive(bar + ck, 64);
+    }
+}
+
+struct TileBufs {
+    uint32_t* A;       // [8][P]
+    uint32_t* B;       // [8][P/2]
+    uint32_t P;        // == blockDim.x
+    uint32_t coop;     // word offset of the cooperative area inside tile_smem
+    uint32_t coop_cnt; // levels with at most this many nodes are hashed cooperatively (0: never)
+};
+
 template <int SRC, int V>
 __device__ __forceinline__ void tile_input(const TreeArgs& a, uint8_t* heap, const uint32_t* vals, uint32_t level,
                                            uint32_t idx, uint32_t d[8], bool coherent)
@@ -410,12 +497,63 @@ __device__ __forceinline__ void tile_input(const TreeArgs& a, uint8_t* heap, con
     }
 }
 
-// Reduces inputs [first, first + 2^log_cnt) of heap level `level` to one digest (returned in sm0 column 0 ... see
-// below); every produced node is stored at its heap position.  Returns with the subtree root in `root` of thread 0.
+// One level hashed by warp pairs.  `cnt` nodes (<= 32 * COOP_PAIRS, 2 * ceil(cnt/32) warps exist); node j of the
+// level is column j.  FIRST: the children are tile inputs (heap digests / leaf values), else they are columns 2j, 2j+1
+// of `in` (pitch in_p).  Results go to `out` (pitch out_p) and to the heap at `heap_lvl + j`.
+template <int SRC, int V, bool FIRST>
+__device__ __forceinline__ void coop_level(const TreeArgs& a, uint8_t* heap, const uint32_t* vals, uint32_t level,
+                                           uint32_t first, bool coherent, uint32_t cnt, const uint32_t* in, uint32_t in_p,
+                                           uint32_t* out, uint32_t out_p, size_t heap_lvl, uint32_t coop, uint32_t d[8])
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nm = (cnt + 31) >> 5;
+    if (warp >= 2 * nm) return;
+    const bool is_main = warp < nm;
+    const uint32_t pair = is_main ? warp : warp - nm;
+    const uint32_t j = pair * 32 + lane, jc = j < cnt ? j : 0;      // lanes past the level hash a duplicate, store nothing
+    const uint32_t area = coop + pair * COOP_WORDS + lane, bar = 1 + 3 * pair;
+    uint32_t m[16];
+    if (FIRST && SRC != SRC_DIGESTS) {
+        // the pair hashes the two leaves side by side and swaps digests through shared memory (barrier bar+2 is free
+        // until the last schedule chunk)
+        uint32_t x[8];
+        tile_input<SRC, V>(a, heap, vals, level, first + 2 * jc + (is_main ? 0 : 1), x, coherent);
+#pragma unroll
+        for (int w = 0; w < 8; w++) tile_smem[area + (48 + (is_main ? 0 : 8) + w) * 32] = x[w];
+        bar_sync(bar + 2, 64);
+#pragma unroll
+        for (int w = 0; w < 16; w++) m[w] = tile_smem[area + (48 + w) * 32];
+    } else if (FIRST) {
+        tile_input<SRC, V>(a, heap, vals, level, first + 2 * jc, m, coherent);
+        tile_input<SRC, V>(a, heap, vals, level, first + 2 * jc + 1, m + 8, coherent);
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            uint2 p = *reinterpret_cast<const uint2*>(in + w * in_p + 2 * jc);
+            m[w] = p.x; m[8 + w] = p.y;
+        }
+    }
+    if (is_main) {
+        Dig8 r = coop_main<V>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13],
+                              m[14], m[15], area, bar);
+#pragma unroll
+        for (int w = 0; w < 8; w++) d[w] = r.v[w];
+        if (j < cnt) {
+            sha::store_digest(heap + 32 * (heap_lvl + j), d);
+#pragma unroll
+            for (int w = 0; w < 8; w++) out[w * out_p + j] = d[w];
+        }
+    } else {
+        coop_helper<V>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13], m[14],
+                       m[15], area, bar);
+    }
+}
+
+// Reduces inputs [first, first + 2^log_cnt) of heap level `level` to one digest; every produced node is stored at
+// its heap position.  Returns with the subtree root in `root` of thread 0.
 template <int SRC, int V>
 __device__ __forceinline__ void tile_reduce(const TreeArgs& a, uint8_t* heap, const uint32_t* vals, uint32_t level,
-                                            uint32_t first, uint32_t log_cnt, bool coherent,
-                                            uint32_t (*bufA)[TILE_PAIRS], uint32_t (*bufB)[TILE_PAIRS / 2], uint32_t root[8])
+                                            uint32_t first, uint32_t log_cnt, bool coherent, const TileBufs& tb,
+                                            uint32_t root[8])
 {
     const uint32_t t = threadIdx.x;
     if (log_cnt == 0) {                                            // a single input: it is the subtree root
@@ -425,31 +563,40 @@ __device__ __forceinline__ void tile_reduce(const TreeArgs& a, uint8_t* heap, co
     uint32_t cnt = 1u << (log_cnt - 1);                            // nodes of the level being produced
     uint32_t lvl = level - 1;
     uint32_t d[8];
-    if (t < cnt) {
+    uint32_t base = first >> 1;
+    if (cnt <= tb.coop_cnt && 64 * ((cnt + 31) >> 5) <= tb.P) {
+        coop_level<SRC, V, true>(a, heap, vals, level, first, coherent, cnt, nullptr, 0, tb.A, tb.P,
+                                 (((size_t)1 << lvl) - 1) + base, tb.coop, d);
+    } else if (t < cnt) {
         uint32_t l[8], r[8];
         tile_input<SRC, V>(a, heap, vals, level, first + 2 * t, l, coherent);
         tile_input<SRC, V>(a, heap, vals, level, first + 2 * t + 1, r, coherent);
         msg_node<V>(l, r, d);                                      // merkle.rs:40-46
-        sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + (first >> 1) + t), d);
+        sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + base + t), d);
 #pragma unroll
-        for (int w = 0; w < 8; w++) bufA[w][t] = d[w];
+        for (int w = 0; w < 8; w++) tb.A[w * tb.P + t] = d[w];
     }
     __syncthreads();
     bool inA = true;
-    uint32_t base = first >> 1;
     while (cnt > 1) {
         cnt >>= 1; lvl--; base >>= 1;
-        if (t < cnt) {
+        const uint32_t* in = inA ? tb.A : tb.B;
+        uint32_t* out = inA ? tb.B : tb.A;
+        const uint32_t in_p = inA ? tb.P : tb.P / 2, out_p = inA ? tb.P / 2 : tb.P;
+        if (cnt <= tb.coop_cnt && 64 * ((cnt + 31) >> 5) <= tb.P) {
+            coop_level<SRC, V, false>(a, heap, vals, level, first, coherent, cnt, in, in_p, out, out_p,
+                                      (((size_t)1 << lvl) - 1) + base, tb.coop, d);
+        } else if (t < cnt) {
             uint32_t l[8], r[8];
 #pragma unroll
             for (int w = 0; w < 8; w++) {
-                uint2 p = inA ? *reinterpret_cast<const uint2*>(&bufA[w][2 * t]) : *reinterpret_cast<const uint2*>(&bufB[w][2 * t]);
+                uint2 p = *reinterpret_cast<const uint2*>(in + w * in_p + 2 * t);
                 l[w] = p.x; r[w] = p.y;
             }
             msg_node<V>(l, r, d);
             sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + base + t), d);
 #pragma unroll
-            for (int w = 0; w < 8; w++) { if (inA) bufB[w][t] = d[w]; else bufA[w][t] = d[w]; }
+            for (int w = 0; w < 8; w++) out[w * out_p + t] = d[w];
         }
         __syncthreads();
         inA = !inA;
@@ -463,9 +610,12 @@ __device__ __forceinline__ void tile_reduce(const TreeArgs& a, uint8_t* heap, co
 template <int SRC, int V = ZK_TILE_SHA_V>
 __global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
 {
-    __shared__ __align__(16) uint32_t bufA[8][TILE_PAIRS];
-    __shared__ __align__(16) uint32_t bufB[8][TILE_PAIRS / 2];
-    __shared__ uint32_t s_last;
+    TileBufs tb;
+    tb.P = blockDim.x;
+    tb.A = tile_smem;
+    tb.B = tile_smem + 8 * tb.P;
+    tb.coop = 12 * tb.P;
+    tb.coop_cnt = a.coop_cnt;
     const uint32_t b = blockIdx.y, tile = blockIdx.x, n_tiles = gridDim.x, t = threadIdx.x;
     const uint32_t log_tile = a.in_level < a.log_tile ? a.in_level : a.log_tile;   // n_tiles == 2^(in_level - log_tile)
     uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
@@ -478,19 +628,19 @@ __global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
     }
     const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
     uint32_t root[8];
-    tile_reduce<SRC, V>(a, heap, vals, a.in_level, first, log_tile, false, bufA, bufB, root);
+    tile_reduce<SRC, V>(a, heap, vals, a.in_level, first, log_tile, false, tb, root);
     if (n_tiles > 1) {
         __threadfence();                                           // this tile's nodes are visible device-wide ...
         __syncthreads();
+        int last = 0;
         if (t == 0) {
             const uint32_t prev = atomicAdd(a.counters + b, 1u);   // ... before the arrival is counted
-            s_last = (prev == n_tiles - 1);
-            if (prev == n_tiles - 1) a.counters[b] = 0;            // re-arm for the next launch on this stream
+            last = (prev == n_tiles - 1);
+            if (last) a.counters[b] = 0;                           // re-arm for the next launch on this stream
         }
-        __syncthreads();
-        if (!s_last) return;
+        if (!__syncthreads_or(last)) return;
         __threadfence();
-        tile_reduce<SRC_DIGESTS, V>(a, heap, vals, a.in_level - log_tile, 0, a.in_level - log_tile, true, bufA, bufB, root);
+        tile_reduce<SRC_DIGESTS, V>(a, heap, vals, a.in_level - log_tile, 0, a.in_level - log_tile, true, tb, root);
     }
     if (t == 0 && a.post != POST_NONE) post_root(a, b, root);
 }
@@ -703,6 +853,9 @@ __global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64
 // ---------------------------------------------------------------- launchers
 extern uint32_t g_tile_direct_log;
 extern uint32_t g_tile_log_override;
+extern uint32_t g_tile_shift;
+extern uint32_t g_pass_log_threads;
+extern uint32_t g_coop_cnt;
 template <int SRC>
 static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch)
 {
@@ -716,11 +869,12 @@ template <int SRC>
 static cudaError_t launch_tile(cudaStream_t s, const TreeArgs& a, uint32_t batch)
 {
     if (a.in_level > 2 * TILE_LOG) return cudaErrorInvalidValue;
-    // Tile size: a lone warp hashes a node in ~2.7 us, but an SM saturates at ~8 warps (ALU pipe: one warp
-    // instruction per 2 cycles per sub-partition), so the latency-bound levels want FEW warps on MANY SMs:
-    // tiles of 128 inputs (2 warps) while the closing CTA still gets <= 256 tile roots, larger tiles above that.
+    // Tile size: a lone warp hashes a node in ~2.7 us and already keeps its sub-partition's ALU pipe ~75 % busy
+    // (one warp instruction per 2 cycles), so the latency-bound levels want FEW warps on MANY SMs and no two CTAs
+    // on one SM (their surviving warps would share sub-partition 0): 2^g_tile_shift = 128 tiles <= 148 SMs,
+    // tiles of 128 inputs (2 warps) for small trees, up to 2^TILE_LOG inputs above that.
     TreeArgs b = a;
-    int lt = (int)a.in_level - 8;
+    int lt = (int)a.in_level - (int)g_tile_shift;
     if (lt < (int)TILE_MIN_LOG) lt = TILE_MIN_LOG;
     if (lt > (int)TILE_LOG) lt = TILE_LOG;
     if (g_tile_log_override) lt = g_tile_log_override;
@@ -732,7 +886,28 @@ static cudaError_t launch_tile(cudaStream_t s, const TreeArgs& a, uint32_t batch
     uint32_t threads = lt >= 1 ? 1u << (lt - 1) : 1u;                       // pairs of a tile ...
     if (n_tiles > 2 * threads) threads = n_tiles / 2;                        // ... or of the tile roots, in the closing CTA
     if (threads < 32) threads = 32;
-    tree_tile_kernel<SRC><<<dim3(n_tiles, batch), threads, 0, s>>>(b);
+    // cooperative levels need two warps per 32 nodes
+    uint32_t coop = g_coop_cnt > 32 * COOP_PAIRS ? 32 * COOP_PAIRS : g_coop_cnt;
+    if (coop) {
+        uint32_t need = 2 * (threads < coop ? threads : coop);
+        need = (need + 63) & ~63u;
+        if (need > threads) threads = need;
+    }
+    b.coop_cnt = coop;
+    const uint32_t npair = coop ? (threads / 64 < COOP_PAIRS ? threads / 64 : COOP_PAIRS) : 0;
+    const size_t smem = 4 * ((size_t)12 * threads + (size_t)COOP_WORDS * npair);
+    {
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(tree_tile_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(4 * (12 * TILE_PAIRS + COOP_WORDS * COOP_PAIRS)));
+            if (e != cudaSuccess) return e;
+            attr_done[dev] = true;
+        }
+    }
+    tree_tile_kernel<SRC><<<dim3(n_tiles, batch), threads, smem, s>>>(b);
     return cudaGetLastError();
 }
 static cudaError_t launch_tile_src(cudaStream_t s, int src, const TreeArgs& a, uint32_t batch)
@@ -781,7 +956,7 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
         launches++;
     } else {
         // leaf pass: enough threads to fill 148 SMs several times over, else fewer levels per thread
-        int k = (int)a.log_size + (int)lb - 18;
+        int k = (int)a.log_size + (int)lb - (int)g_pass_log_threads;
         if (k < 1) k = 1;
         if (k > (int)MAX_PASS_K) k = MAX_PASS_K;
         if (k > (int)(a.log_size - TILE_LOG)) k = a.log_size - TILE_LOG;
@@ -847,10 +1022,18 @@ cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int*
 // trees of up to 2^g_tile_direct_log leaves (summed over the batch) skip the per-thread-subtree leaf pass
 uint32_t g_tile_direct_log = ZK_TILE_DIRECT_LOG;
 uint32_t g_tile_log_override = 0;
-void set_tile_direct_log(uint32_t v)   // bench knob: low 8 bits = direct threshold, bits 8.. = forced tile size (0 = adaptive)
+uint32_t g_tile_shift = ZK_TILE_SHIFT;              // the tile kernel runs 2^g_tile_shift tiles per tree
+uint32_t g_pass_log_threads = ZK_PASS_LOG_THREADS;  // the leaf pass runs ~2^g_pass_log_threads threads (summed over the batch)
+uint32_t g_coop_cnt = ZK_COOP_CNT;                  // tile kernel: widest level hashed by warp pairs
+void set_coop_cnt(uint32_t v) { g_coop_cnt = v; }
+// bench knob: bits 0-7 direct threshold, 8-15 forced tile size (0 = adaptive), 16-23 tile shift, 24-31 leaf-pass
+// log-threads (0 = keep the default)
+void set_tile_direct_log(uint32_t v)
 {
     g_tile_direct_log = v & 0xffu;
     g_tile_log_override = (v >> 8) & 0xffu;
+    g_tile_shift = ((v >> 16) & 0xffu) ? ((v >> 16) & 0xffu) : ZK_TILE_SHIFT;
+    g_pass_log_threads = (v >> 24) ? (v >> 24) : ZK_PASS_LOG_THREADS;
 }
 
 __global__ void state_set_kernel(ProofState* st, uint32_t a_first, uint32_t a_last)
