@@ -168,6 +168,15 @@ int zk_shard_fold_dev(zk_ctx *ctx, const uint32_t *cur_local, uint64_t local_len
 int zk_shard_fri_tail_dev(zk_ctx *ctx, uint32_t log_n, uint32_t first_layer, uint32_t *layers_arena,
                           uint8_t *heaps_arena, void *state_dev, uint8_t *transcript_dev);
 
+/* prover.rs:263-289 (query decommitment) for the sharded proof.  tree_ptrs: HOST array of 3 * (first_tail + 2)
+ * device pointers {rank-local values, rank-local heap, replicated upper heap} of the f tree and of FRI layers
+ * 0..first_tail; tail_*: the arenas of zk_shard_fri_tail_dev.  Each rank writes only the values / sibling digests
+ * it owns into transcript_dev (rank 0 also the length prefixes and the replicated tail layers); the decommitment
+ * region must be zero on entry, and the byte-wise maximum over ranks (one all-reduce) completes the transcript. */
+int zk_shard_decommit_dev(zk_ctx *ctx, uint32_t log_n, uint32_t n_ranks, uint32_t rank, uint32_t log_block,
+                          uint32_t first_tail, const void *const *tree_ptrs, const uint32_t *tail_vals,
+                          const uint8_t *tail_heaps, const void *state_dev, uint8_t *transcript_dev);
+
 /* ---- measurement support (bench.py): runs ONE hot-path kernel (or kernel group) `iters` times on
  * the ctx stream, each launch bracketed by CUDA events (optionally after an L2 flush that is not
  * timed), on synthetic canonical residues it generates on the device.  ms_out[0] = mean ms per

@@ -83,6 +83,7 @@ def lib():
         "zk_shard_cp_dev": ([vp, vp, vp, u64, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fold_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fri_tail_dev": ([vp, u32, u32, vp, vp, vp, vp], i32),
+        "zk_shard_decommit_dev": ([vp, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp], i32),
         "zk_bench_set": ([vp, i32, u32], i32),
         "zk_bench_set_tile_direct_log": ([vp, u32], i32),
     }
@@ -297,6 +298,14 @@ class Context:
     def shard_fold(self, cur_ptr, local_len, layer_k, log_N0, n_ranks, rank, log_block, state_ptr, next_ptr):
         self._ck(lib().zk_shard_fold_dev(self._h, C.c_void_p(cur_ptr), local_len, layer_k, log_N0, n_ranks, rank, log_block,
                                          C.c_void_p(state_ptr), C.c_void_p(next_ptr)))
+
+    def shard_decommit(self, log_n, n_ranks, rank, log_block, first_tail, tree_ptrs, tail_vals_ptr, tail_heaps_ptr,
+                       state_ptr, transcript_ptr):
+        """tree_ptrs: flat list of 3 * (first_tail + 2) device addresses (values, local heap, upper heap per tree)"""
+        arr = (C.c_void_p * len(tree_ptrs))(*tree_ptrs)
+        self._ck(lib().zk_shard_decommit_dev(self._h, log_n, n_ranks, rank, log_block, first_tail, arr,
+                                             C.c_void_p(tail_vals_ptr), C.c_void_p(tail_heaps_ptr),
+                                             C.c_void_p(state_ptr), C.c_void_p(transcript_ptr)))
 
     def shard_fri_tail(self, log_n, first_layer, layers_ptr, heaps_ptr, state_ptr, transcript_ptr):
         self._ck(lib().zk_shard_fri_tail_dev(self._h, log_n, first_layer, C.c_void_p(layers_ptr), C.c_void_p(heaps_ptr),

@@ -966,6 +966,33 @@ int zk_shard_fri_tail_dev(zk_ctx* ctx, uint32_t log_n, uint32_t first_layer, uin
     return ZK_OK;
 }
 
+// prover.rs:263-289 for the sharded proof: see shard_decommit_kernel (tree.cu).
+int zk_shard_decommit_dev(zk_ctx* ctx, uint32_t log_n, uint32_t n_ranks, uint32_t rank, uint32_t log_block, uint32_t first_tail,
+                          const void* const* tree_ptrs, const uint32_t* tail_vals, const uint8_t* tail_heaps,
+                          const void* state_dev, uint8_t* transcript_dev)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!tree_ptrs || !state_dev || !transcript_dev || n_ranks == 0 || (n_ranks & (n_ranks - 1)) || rank >= n_ranks ||
+        first_tail >= log_n || first_tail + 2 > SHARD_MAX_TREES || log_block < 1)
+        return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    if (first_tail + 1 < log_n && (!tail_vals || !tail_heaps)) return fail(ctx, ZK_ERR_INVALID, "tail arenas missing");
+    CK(cudaSetDevice(ctx->device));
+    ShardDecommitArgs a{};
+    a.log_n = log_n; a.n_ranks = n_ranks; a.rank = rank; a.log_block = log_block; a.first_tail = first_tail;
+    for (uint32_t t = 0; t < first_tail + 2; t++) {
+        a.vals[t] = (const uint32_t*)tree_ptrs[3 * t];
+        a.heap[t] = (const uint8_t*)tree_ptrs[3 * t + 1];
+        a.upper[t] = (const uint8_t*)tree_ptrs[3 * t + 2];
+        if (!a.vals[t] || !a.heap[t] || !a.upper[t]) return fail(ctx, ZK_ERR_INVALID, "null tree pointer");
+    }
+    a.tail_vals = tail_vals; a.tail_heaps = tail_heaps;
+    a.state = (const ProofState*)state_dev; a.out = transcript_dev;
+    CK(launch_shard_decommit(ctx->stream, a));
+    ctx->launches += 1;
+    return ZK_OK;
+}
+
 // ------------------------------------------------------------------ measurement support
 int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
 {

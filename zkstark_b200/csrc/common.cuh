@@ -162,6 +162,20 @@ cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_ev
                             const uint8_t* layer_heaps, uint64_t layer_heaps_stride,
                             ProofState* state, uint8_t* transcript, uint64_t transcript_stride,
                             uint32_t batch);
+// Decommitment of a proof sharded blocked-cyclically (zkstark_b200/sharded.py): tree 0 is f, tree 1 + i is FRI layer i
+// (i <= first_tail, committed distributed); layers above first_tail live replicated in the tail arenas.
+constexpr uint32_t SHARD_MAX_TREES = 30;
+struct ShardDecommitArgs {
+    uint32_t log_n, n_ranks, rank, log_block, first_tail;
+    const uint32_t* vals[SHARD_MAX_TREES];   // rank-local values
+    const uint8_t* heap[SHARD_MAX_TREES];    // rank-local heap (levels up to the block roots)
+    const uint8_t* upper[SHARD_MAX_TREES];   // replicated heap over the block roots
+    const uint32_t* tail_vals;
+    const uint8_t* tail_heaps;
+    const ProofState* state;
+    uint8_t* out;                            // transcript buffer; only the records this rank owns are written
+};
+cudaError_t launch_shard_decommit(cudaStream_t s, const ShardDecommitArgs& a);
 cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
                               uint32_t log_n, uint32_t batch);
 // stand-alone element-wise stages (stages in isolation, for the per-function C-ABI)

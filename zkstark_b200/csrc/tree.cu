@@ -783,6 +783,100 @@ __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
     }
 }
 
+// The same records for a proof whose arrays are owned blocked-cyclically by several ranks (common.cuh ShardMap):
+// every rank runs this kernel over its own arrays and writes only what it owns -- a value, the log_block rank-local
+// siblings below its block root and the siblings above it from the replicated upper heap; rank 0 adds the length
+// prefixes and the layers of the replicated FRI tail.  Everything else stays zero, so the byte-wise maximum over the
+// ranks is the decommitment part of the transcript (one small all-reduce instead of per-record host round trips).
+struct ShardSrc { const uint32_t* val; const uint8_t* heap; uint32_t log_size; uint32_t leaf; const uint8_t* upper; uint32_t block; };
+__device__ __forceinline__ bool shard_locate(const ShardDecommitArgs& a, uint32_t tree /*0 = f, 1 + i = layer i*/, uint32_t layer,
+                                             uint32_t lg, uint32_t leaf, ShardSrc& o)
+{
+    const uint32_t log_N = a.log_n + LOG_BLOWUP;
+    if (tree == 0 || layer <= a.first_tail) {
+        const uint32_t G = a.n_ranks, lgG = 31 - __clz(G), lb = a.log_block;
+        const uint32_t b = leaf >> lb;
+        if ((b & (G - 1)) != a.rank) return false;
+        const uint32_t loc = ((b >> lgG) << lb) | (leaf & ((1u << lb) - 1u));
+        o.val = a.vals[tree] + loc;
+        o.heap = a.heap[tree]; o.log_size = lg - lgG; o.leaf = loc;
+        o.upper = a.upper[tree]; o.block = b;
+        return true;
+    }
+    if (a.rank != 0) return false;
+    const size_t voff = layer_vals_off_dev(log_N, layer) - layer_vals_off_dev(log_N, a.first_tail);
+    o.val = a.tail_vals + voff + leaf;
+    o.heap = a.tail_heaps + 64 * voff; o.log_size = lg; o.leaf = leaf;
+    o.upper = nullptr; o.block = 0;
+    return true;
+}
+__global__ void __launch_bounds__(256) shard_decommit_kernel(const ShardDecommitArgs a)
+{
+    const uint32_t k = a.log_n, L = k, log_N = k + LOG_BLOWUP, N = 1u << log_N, B = 1u << LOG_BLOWUP;
+    uint8_t* tr = a.out;
+    const uint32_t x = (uint32_t)((size_t)a.state->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
+    const size_t off0 = 84 + 36 * (size_t)L;
+    const size_t rec0 = 12 + 32 * (size_t)log_N;
+    for (uint32_t r = threadIdx.x; r < 4 + L; r += blockDim.x) {
+        ShardSrc sp;
+        if (r < 4) {                                             // prover.rs:266-277
+            uint8_t* rec = tr + off0 + r * rec0;
+            const uint32_t leaf = (r < 3) ? x + r * B : x;
+            if (shard_locate(a, r < 3 ? 0 : 1, 0, log_N, leaf, sp)) *reinterpret_cast<uint32_t*>(rec) = *sp.val;
+            if (a.rank == 0) *reinterpret_cast<uint32_t*>(rec + 4) = log_N;   // u64 LE length (high word stays 0)
+        } else {                                                 // prover.rs:280-289
+            const uint32_t i = r - 4, lg = log_N - i, len = 1u << lg;
+            const uint32_t xi = x & (len - 1), nx = (xi + len / 2) & (len - 1);
+            uint8_t* rec = tr + off0 + 4 * rec0 + 24 * (size_t)i + 64 * ((size_t)i * log_N - (size_t)i * (i - 1) / 2);
+            if (shard_locate(a, 1 + i, i, lg, xi, sp)) *reinterpret_cast<uint32_t*>(rec) = *sp.val;
+            if (shard_locate(a, 1 + i, i, lg, nx, sp)) *reinterpret_cast<uint32_t*>(rec + 4) = *sp.val;
+            if (a.rank == 0) {
+                *reinterpret_cast<uint32_t*>(rec + 8) = lg;
+                *reinterpret_cast<uint32_t*>(rec + 16 + 32 * (size_t)lg) = lg;
+            }
+        }
+    }
+    const uint32_t per_rec_f = log_N;
+    const uint32_t n_items = 4 * per_rec_f + 2 * (L * log_N - L * (L - 1) / 2);
+    const uint32_t sub = threadIdx.x & 7;
+    for (uint32_t it = threadIdx.x >> 3; it < n_items; it += blockDim.x >> 3) {
+        uint8_t* dst;
+        uint32_t lg, leaf, s, tree, layer;
+        if (it < 4 * per_rec_f) {
+            const uint32_t r = it / per_rec_f;
+            s = it - r * per_rec_f;
+            lg = log_N;
+            leaf = (r < 3) ? x + r * B : x;
+            tree = (r < 3) ? 0 : 1;
+            layer = 0;
+            dst = tr + off0 + r * rec0 + 12 + 32 * (size_t)s;
+        } else {
+            uint32_t rem = it - 4 * per_rec_f, i = 0;
+            while (rem >= 2 * (log_N - i)) { rem -= 2 * (log_N - i); i++; }
+            lg = log_N - i;
+            const uint32_t len = 1u << lg, xi = x & (len - 1), nx = (xi + len / 2) & (len - 1);
+            const uint32_t path = rem >= lg;
+            s = path ? rem - lg : rem;
+            leaf = path ? nx : xi;
+            tree = 1 + i;
+            layer = i;
+            uint8_t* rec = tr + off0 + 4 * rec0 + 24 * (size_t)i + 64 * ((size_t)i * log_N - (size_t)i * (i - 1) / 2);
+            dst = rec + (path ? 24 + 32 * (size_t)lg : 16) + 32 * (size_t)s;
+        }
+        ShardSrc sp;
+        if (!shard_locate(a, tree, layer, lg, leaf, sp)) continue;
+        const uint8_t* node;
+        if (sp.upper == nullptr || s < a.log_block) node = sp.heap + 32 * sibling_node(sp.log_size, sp.leaf, s);
+        else node = sp.upper + 32 * sibling_node(lg - a.log_block, sp.block, s - a.log_block);
+        reinterpret_cast<uint32_t*>(dst)[sub] = reinterpret_cast<const uint32_t*>(node)[sub];
+    }
+}
+cudaError_t launch_shard_decommit(cudaStream_t s, const ShardDecommitArgs& a)
+{
+    shard_decommit_kernel<<<1, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 // channel.rs:19-26 over the decommitment records (prover.rs:274-288), one THREAD per proof: 4 + L sequential
 // commits, each state = SHA256(state || record).  Used for batches (the chains of all proofs advance in
 // parallel); for a single proof the host does the same ~340 compressions faster than one GPU thread.

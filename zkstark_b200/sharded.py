@@ -43,8 +43,10 @@ class LocalComm:
         full = torch.stack(list(xs), dim=0)
         return [full for _ in xs]
 
-    def all_gather_object(self, objs):
-        return [list(objs) for _ in objs]
+    def all_reduce_max(self, xs):
+        import torch
+        m = torch.stack(list(xs), dim=0).amax(dim=0)
+        return [m for _ in xs]
 
 
 class TorchComm:
@@ -70,10 +72,9 @@ class TorchComm:
         self.dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=self.group)
         return [out]
 
-    def all_gather_object(self, objs):
-        out = [None] * self.world_size
-        self.dist.all_gather_object(out, objs[0], group=self.group)
-        return [out]
+    def all_reduce_max(self, xs):
+        self.dist.all_reduce(xs[0], op=self.dist.ReduceOp.MAX, group=self.group)
+        return [xs[0]]
 
 
 class _Tree:
@@ -96,6 +97,18 @@ class ShardedProver:
         if log_block < 5 or (self.N // self.G) < (1 << (log_block + 1)):
             raise ValueError("proof too small to shard: need at least two blocks per rank")
         self.comm_bytes = 0
+        self.profile = None      # set to {} to collect per-phase wall times (synchronising: for diagnosis only)
+        self._t_last = None
+
+    def _mark(self, name):
+        if self.profile is None:
+            return
+        import time
+        self.torch.cuda.synchronize()
+        now = time.perf_counter()
+        if self._t_last is not None:
+            self.profile[name] = self.profile.get(name, 0.0) + (now - self._t_last)
+        self._t_last = now
 
     # ------------------------------------------------------------------ helpers
     def _i32(self, *shape):
@@ -136,21 +149,40 @@ class ShardedProver:
         ranks = self.comm.my_ranks
         nr = len(ranks)
         tl = ctx_transcript_len(k)
-        trace = np.ascontiguousarray(trace, dtype=np.uint32)
-        assert len(trace) == n - 1
+        if isinstance(trace, t.Tensor):                 # host tensor of n-1 int32 words, ideally pinned (async H2D)
+            host = trace.view(t.int32)
+        else:
+            host = t.from_numpy(np.ascontiguousarray(trace, dtype=np.uint32).view(np.int32))
+        assert host.numel() == n - 1
+        a_first, a_last = int(host[0].item()) & 0xFFFFFFFF, int(host[n - 2].item()) & 0xFFFFFFFF
         self.comm_bytes = 0
+        self._t_last = None
+        self._mark("start")
 
         states = [t.zeros(64, dtype=t.int32, device=self.dev) for _ in ranks]
         transcripts = [t.zeros(tl + 64, dtype=t.uint8, device=self.dev) for _ in ranks]
         for i in range(nr):
-            ctx.shard_state_init(states[i].data_ptr(), int(trace[0]), int(trace[n - 2]))
+            ctx.shard_state_init(states[i].data_ptr(), a_first, a_last)
 
-        # Part 1a: interpolation, replicated (1/8 of the transform work)
-        y = self._i32(n)
-        y.zero_()
-        y[: n - 1] = t.from_numpy(trace.view(np.int32)).to(self.dev)
+        # Part 1a: interpolation, replicated (1/8 of the transform work).  Each real rank uploads only its
+        # 1/G slice of the trace over PCIe; the slices are all-gathered over NVLink.
+        if nr == 1 and G > 1:
+            chunk = n // G
+            lo = ranks[0] * chunk
+            hi = min(lo + chunk, n - 1)
+            part = self._i32(chunk)
+            if hi - lo < chunk:
+                part[hi - lo:].zero_()
+            part[: hi - lo].copy_(host[lo:hi], non_blocking=True)
+            y = self.comm.all_gather([part])[0].view(-1)
+            self.comm_bytes += 4 * n * (G - 1) // G
+        else:
+            y = self._i32(n)
+            y[n - 1:].zero_()
+            y[: n - 1].copy_(host, non_blocking=True)
         coeffs = self._i32(n)
         ctx.interpolate_subgroup_dev(y.data_ptr(), n - 1, k, coeffs.data_ptr())
+        self._mark("h2d+interpolate")
         # Part 1b: LDE, cosets split over ranks, then the all-to-all that re-owns the evaluations by blocks
         C_ = 8 // G
         jb = 1 << (lb - 3)                       # j-values per block (a block holds all 8 cosets of jb points)
@@ -163,14 +195,18 @@ class ShardedProver:
                 ctx.shard_lde_coset(coeffs.data_ptr(), k, r + c * G, work.data_ptr(), E[c].data_ptr())
             # E[c][j], j = ((bl*G + d) * jb + tt)  ->  send[d][c][bl][tt]
             send.append(E.view(C_, nbl, G, jb).permute(2, 0, 1, 3).contiguous())
+        self._mark("lde_cosets+pack")
         recv = self.comm.all_to_all(send)
+        self._mark("all_to_all")
         self.comm_bytes += 4 * N * (G - 1) // G
         f_local = []
         for idx in range(nr):
             # recv[g][c][bl][tt] -> f_local[bl][tt][r = c*G + g]
             f_local.append(recv[idx].view(G, C_, nbl, jb).permute(2, 3, 1, 0).contiguous().view(-1))
         del send, recv, work
+        self._mark("unpack")
         f_trees = self._commit_tree(f_local, N, POST_F, 0, states, transcripts)
+        self._mark("f_tree")
 
         # Part 2: composition polynomial (needs f at i, i+8, i+16: 16-value halo per block)
         heads = [f.view(nbl, 1 << lb)[:, :16].contiguous() for f in f_local]
@@ -185,7 +221,9 @@ class ShardedProver:
             cp = self._i32(N // G)
             ctx.shard_cp(f_local[idx].data_ptr(), halo.data_ptr(), N // G, k, G, r, lb, states[idx].data_ptr(), cp.data_ptr())
             cp_local.append(cp)
+        self._mark("cp_eval+halo")
         layers = [self._commit_tree(cp_local, N, POST_CP, 0, states, transcripts)]
+        self._mark("cp_tree")
 
         # Part 3: FRI.  Folds stay rank-local while a layer has >= 2 blocks per rank.
         cur, length, i = cp_local, N, 0
@@ -199,6 +237,7 @@ class ShardedProver:
             length //= 2
             layers.append(self._commit_tree(nxt, length, POST_FRI, i, states, transcripts))
             cur = nxt
+        self._mark("fri_sharded_layers")
         # replicated tail: gather layer i (one block per rank) and finish on every rank
         first_tail = i
         full = self.comm.all_gather([c.view(-1, 1 << lb) for c in cur])     # [G, nbl=1, blk]
@@ -212,106 +251,34 @@ class ShardedProver:
                                states[idx].data_ptr(), transcripts[idx].data_ptr())
             tails.append((arena_vals, arena_heaps))
         ctx.synchronize()
+        self._mark("fri_tail")
 
-        # Part 4: decommit.  Owners read values + local sibling digests; everybody assembles the same bytes.
+        # Part 4: decommit (prover.rs:263-289).  Every rank gathers the values and sibling digests it owns straight
+        # into its (otherwise identical) transcript buffer; a byte-wise MAX all-reduce completes it everywhere.
+        for idx, r in enumerate(ranks):
+            ptrs = []
+            for tree in [f_trees[idx]] + [layers[li][idx] for li in range(first_tail + 1)]:
+                ptrs += [tree.vals.data_ptr(), tree.heap.data_ptr(), tree.upper.data_ptr()]
+            ctx.shard_decommit(k, G, r, lb, first_tail, ptrs, tails[idx][0].data_ptr(), tails[idx][1].data_ptr(),
+                               states[idx].data_ptr(), transcripts[idx].data_ptr())
+        full = self.comm.all_reduce_max(transcripts)
+        self.comm_bytes += tl
         results = []
-        st_host = [s.cpu().numpy().view(np.uint32) for s in states]
-        q_raw = int(st_host[0][44])
-        x = q_raw % (N - 16)
-        wanted = [("f", x), ("f", x + 8), ("f", x + 16), ("l0", x)]
-        for li in range(0, first_tail + 1):
-            ln = N >> li
-            wanted += [(f"l{li}", x % ln), (f"l{li}", (x % ln + ln // 2) % ln)]
-        contrib = []
-        for idx, r in enumerate(ranks):
-            mine = {}
-            for name, gi in wanted:
-                tree = f_trees[idx] if name == "f" else layers[int(name[1:])][idx]
-                b = gi >> lb
-                if b % G != r:
-                    continue
-                loc = ((b // G) << lb) | (gi & ((1 << lb) - 1))
-                mine[(name, gi)] = (int(tree.vals[loc].item()) & 0xFFFFFFFF, self._local_path(tree, loc))
-            contrib.append(mine)
-        everyone = self.comm.all_gather_object(contrib)
-        for idx, r in enumerate(ranks):
-            merged = {}
-            for d in everyone[idx]:
-                merged.update(d)
-            tr = bytearray(transcripts[idx][:tl].cpu().numpy().tobytes())
-            off = 84 + 36 * k
-
-            def full_path(name, gi):
-                tree = f_trees[idx] if name == "f" else layers[int(name[1:])][idx]
-                val, low = merged[(name, gi)]
-                return val, low + self._upper_path(tree, gi >> lb)
-
-            def tail_entry(li, gi):
-                vals, heaps = tails[idx]
-                voff = sum((N >> j) for j in range(first_tail, li))
-                hoff = sum(64 * (N >> j) for j in range(first_tail, li))
-                ln = N >> li
-                val = int(vals[voff + gi].item()) & 0xFFFFFFFF
-                heap = heaps[hoff: hoff + 32 * (2 * ln - 1)].view(-1, 32)
-                path, node = [], gi + ln - 1
-                sib = []
-                while node != 0:
-                    sib.append(node - 1 if node % 2 == 0 else node + 1)
-                    node = (node - 1) >> 1
-                got = heap[self.torch.tensor(sib, device=self.dev, dtype=self.torch.long)].cpu().numpy()
-                return val, [bytes(g) for g in got]
-
-            for name, gi in wanted[:4]:
-                val, path = full_path(name, gi)
-                rec = struct.pack("<IQ", val, len(path)) + b"".join(path)
-                tr[off: off + len(rec)] = rec
-                off += len(rec)
-            for li in range(k):
-                ln = N >> li
-                xi, nx = x % ln, (x % ln + ln // 2) % ln
-                if li <= first_tail:
-                    (v0, p0), (v1, p1) = full_path(f"l{li}", xi), full_path(f"l{li}", nx)
-                else:
-                    (v0, p0), (v1, p1) = tail_entry(li, xi), tail_entry(li, nx)
-                rec = struct.pack("<IIQ", v0, v1, len(p0)) + b"".join(p0) + struct.pack("<Q", len(p1)) + b"".join(p1)
-                tr[off: off + len(rec)] = rec
-                off += len(rec)
-            assert off == tl, (off, tl)
-            # channel.rs:19-26 over the decommitment records (host; ~k + 4 sequential hashes)
-            state = b"".join(struct.pack(">I", int(w)) for w in st_host[idx][47:55])
+        for idx in range(nr):
+            tr = full[idx][:tl].cpu().numpy().tobytes()
+            st_host = states[idx].cpu().numpy().view(np.uint32)
+            # channel.rs:19-26 over the decommitment records (host; k + 4 sequential hashes)
+            state = b"".join(struct.pack(">I", int(w)) for w in st_host[47:55])
             o2 = 84 + 36 * k
             for rr in range(4 + k):
                 ln_rec = 12 + 32 * log_N if rr < 4 else 24 + 64 * (log_N - (rr - 4))
-                state = hashlib.sha256(state + bytes(tr[o2: o2 + ln_rec])).digest()
+                state = hashlib.sha256(state + tr[o2: o2 + ln_rec]).digest()
                 o2 += ln_rec
-            results.append((bytes(tr), state))
+            assert o2 == tl, (o2, tl)
+            results.append((tr, state))
+        self._mark("decommit+host_tail")
         self.first_tail_layer = first_tail
         return results[0] if nr == 1 else results
-
-    def _local_path(self, tree, loc):
-        """Sibling digests of the bottom log_block levels, from the rank-local heap (merkle.rs:54-71 order)."""
-        local_len = tree.length // self.G
-        node = loc + local_len - 1
-        sib = []
-        for _ in range(self.lb):
-            sib.append(node - 1 if node % 2 == 0 else node + 1)
-            node = (node - 1) >> 1
-        heap = tree.heap.view(-1, 32)
-        got = heap[self.torch.tensor(sib, device=self.dev, dtype=self.torch.long)].cpu().numpy()
-        return [bytes(g) for g in got]
-
-    def _upper_path(self, tree, block):
-        nbt = tree.length >> self.lb
-        node = block + nbt - 1
-        sib = []
-        while node != 0:
-            sib.append(node - 1 if node % 2 == 0 else node + 1)
-            node = (node - 1) >> 1
-        if not sib:
-            return []
-        heap = tree.upper.view(-1, 32)
-        got = heap[self.torch.tensor(sib, device=self.dev, dtype=self.torch.long)].cpu().numpy()
-        return [bytes(g) for g in got]
 
 
 def ctx_transcript_len(k):
