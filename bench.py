@@ -365,7 +365,8 @@ def extras(args, ctx, zk, line, clocks, world):
         "ms_per_launch": ms_leaf, "compressions_per_s": 3 * leaves / (ms_leaf * 1e-3),
         "hbm": {"achieved": alg_bytes / (ms_leaf * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (ms_leaf * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed `ncu --set full` capture
+        "traffic": counts.get("dram_bytes_per_launch") if log_leaves == 23 else None,
         "share_of_step": None,
         "note": "SHA-256 Merkle hashing is integer-pipe bound (north_star: INT roofline for hashing, HBM roofline for NTT/fold)",
     }

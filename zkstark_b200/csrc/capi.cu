@@ -65,6 +65,7 @@ struct PowTabOwned {
 struct SizeTables {
     PowTabOwned h;  // powers of h = 5^((p-1)/N)
     PowTabOwned w;  // powers of 5
+    DevBuf cp_tab;  // CpArgs::tab of the size log_N - 3 (built on first use by the prove pipeline)
 };
 
 }  // namespace
@@ -83,6 +84,7 @@ struct zk_ctx {
     DevBuf counters;                      // tile-arrival counters of the tree kernels (one per proof of a batch)
     int bench_variant = -1;
     uint32_t bench_k = 0;
+    bool use_cp_tab = true;               // composition polynomial from per-size constant tables (bench knob)
     // prove work space
     uint32_t w_log_n = 0, w_batch = 0;
     DevBuf traces, coeffs, work, f_eval, layers, f_heap, layer_heaps, states, transcripts;
@@ -331,6 +333,17 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
     a.cp.f = f_eval;
     a.cp.f_stride = N;
     a.cp.alpha_from_state = 1;
+    if (ctx->use_cp_tab) {
+        if (!T->cp_tab.p) {   // once per context and size: input-independent domain constants (12 N bytes)
+            if (T->cp_tab.ensure(12 * N) == cudaSuccess) {
+                CK(launch_cp_tables(s, (uint32_t*)T->cp_tab.p, a.cp, T->h.tab));
+                nl++;
+            } else {
+                cudaGetLastError();   // not enough memory for the tables: fall back to computing them per point
+            }
+        }
+        a.cp.tab = (const uint32_t*)T->cp_tab.p;
+    }
     CK(launch_merkle_tree(s, SRC_CP, a, nb, &nl));
     tm.mark();
     // Part 3 (prover.rs:192-254)
@@ -457,7 +470,7 @@ void zk_ctx_destroy(zk_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->tabs) { free_powtab(kv.second.h); free_powtab(kv.second.w); }
+    for (auto& kv : ctx->tabs) { free_powtab(kv.second.h); free_powtab(kv.second.w); kv.second.cp_tab.release(); }
     DevBuf* bufs[] = {&ctx->counters, &ctx->flushbuf, &ctx->s0, &ctx->s1, &ctx->s2, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval,
                       &ctx->layers, &ctx->f_heap, &ctx->layer_heaps, &ctx->states, &ctx->transcripts};
     for (DevBuf* b : bufs) b->release();
@@ -997,6 +1010,10 @@ int zk_shard_decommit_dev(zk_ctx* ctx, uint32_t log_n, uint32_t n_ranks, uint32_
 int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
 {
     if (!ctx) return ZK_ERR_INVALID;
+    if (sha_variant == -100 || sha_variant == -101) {   // composition polynomial: -100 per-point form, -101 constant tables
+        ctx->use_cp_tab = (sha_variant == -101);
+        return ZK_OK;
+    }
     ctx->bench_variant = sha_variant;
     ctx->bench_k = leaf_pass_k & 0xffu;
     if (leaf_pass_k >> 8) set_coop_cnt((leaf_pass_k >> 8) - 1);   // bits 8..: 1 + widest cooperative tile level (0: keep)

@@ -26,6 +26,12 @@ constexpr uint32_t TILE_MIN_LOG = 7;
 #ifndef ZK_PASS_LOG_THREADS
 #define ZK_PASS_LOG_THREADS 18  // the leaf pass runs about this many threads (log2), each hashing a 2^k-leaf subtree
 #endif
+#ifndef ZK_COOP_V
+#define ZK_COOP_V 96                    // SHA-256 variant of the main warp of a cooperative pair: latency form of the round, K+W on the FMA pipe
+#endif
+#ifndef ZK_COOP_HELPER_V
+#define ZK_COOP_HELPER_V ZK_TILE_SHA_V  // ... and of its helper warp
+#endif
 #ifndef ZK_COOP_CNT
 #define ZK_COOP_CNT 128         // tile kernel: levels with <= this many nodes hash each node with a warp pair (0: off)
 #endif
@@ -77,7 +83,7 @@ enum PostOp : int {
     POST_FRI = 3,  // prover.rs:224 commit layer root; next beta, or (:254,:263) free term + query
 };
 
-enum SrcKind : int { SRC_VALUES = 0, SRC_DIGESTS = 1, SRC_FOLD = 2, SRC_CP = 3 };
+enum SrcKind : int { SRC_VALUES = 0, SRC_DIGESTS = 1, SRC_FOLD = 2, SRC_CP = 3, SRC_CP_TAB = 4 /* SRC_CP with CpArgs::tab */ };
 
 // Blocked-cyclic ownership of an evaluation array across ranks (single proof sharded over GPUs):
 // global index i lives on rank (i >> log_block) % n_ranks at local index
@@ -119,6 +125,10 @@ struct CpArgs {             // prover.rs:101-173 pointwise
     ShardMap shard;            // sharded: f is the rank-local array, x comes from the global index
     const uint32_t* halo;      // sharded: first 16 values of the block that follows each local block
     uint32_t log_len;          // log2 of the number of local points (== log_N when not sharded)
+    // Optional per-size constant tables (built once per context and size by launch_cp_tables; they depend on the
+    // domain only, like twiddles): tab[i] = 1/(x_i - 1) R, tab[N + i] = 1/(x_i - g^(n-2)) R,
+    // tab[2N + i] = (x_i - g^(n-3))(x_i - g^(n-2))(x_i - g^(n-1)) / (x_i^n - 1) R^2, x_i = 5 h^i.  Null: computed on the fly.
+    const uint32_t* tab;
 };
 
 struct TreeArgs {
@@ -183,6 +193,7 @@ cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uin
                         FoldArgs f, PowTab pow, uint32_t batch, uint64_t next_stride, const ProofState* st = nullptr);
 cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch,
                       uint64_t out_stride, const ProofState* st = nullptr);
+cudaError_t launch_cp_tables(cudaStream_t s, uint32_t* tab, CpArgs c, PowTab pow);
 cudaError_t launch_chan_tail(cudaStream_t s, ProofState* states, const uint8_t* transcripts, uint64_t stride,
                              uint32_t log_n, uint32_t batch);
 cudaError_t launch_state_set(cudaStream_t s, ProofState* st, uint32_t a_first, uint32_t a_last);

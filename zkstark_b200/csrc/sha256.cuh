@@ -70,6 +70,7 @@ constexpr Consts make_consts()
 //   rotate    rotr(x, k) = hi | lo  ->  IMAD.WIDE x * c[2^(32-k)]   (hi, lo disjoint: OR == XOR)
 // `V` is a bit mask choosing which groups of operations move (tuned on the GPU):
 //   1 round adds   2 schedule adds   4 Sigma1 rotations   8 Sigma0 rotations   16 sigma0/1 shifts   32 K+W adds
+//   64 latency form of the round (see ZK_SHA_ROUND): for code that runs one warp per sub-partition
 enum ShaConst { SC_ONE = 0, SC_R6, SC_R11, SC_R2, SC_R13, SC_S3, SC_S10, SC_R18, SC_R19, SC_COUNT };
 __constant__ uint32_t c_sha[16];  // one translation unit (tree.cu) owns the hashing kernels
 
@@ -127,7 +128,16 @@ __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { re
 // e to the next e is SHF -> LOP3 -> add -> add, everything else (h + K + W, d + h + K + W, Sigma0 + Maj)
 // is off the critical path.  Matters for the latency-bound upper levels of a tree (one warp per SM).
 #define ZK_SHA_ROUND(V, a, b, c, d, e, f, g, h, kw)                      \
-    {                                                                    \
+    if ((V) & 64) {                                                      \
+        /* latency form (one warp per sub-partition): h + K + W and d + h + K + W on the FMA pipe, off the  \
+           chain; the three sums that consume the fresh e / a are single 3-input adds (IADD3) */            \
+        uint32_t hk = addv<1, 1>(h, (kw));                               \
+        uint32_t dhk = addv<1, 1>(d, hk);                                \
+        uint32_t s1 = bsig1<0>(e), cc = ch(e, f, g);                     \
+        uint32_t t2 = hk + bsig0<0>(a) + maj(a, b, c);                   \
+        d = dhk + s1 + cc;                                               \
+        h = t2 + s1 + cc;                                                \
+    } else {                                                             \
         uint32_t hk = addv<V, 1>(h, (kw));                               \
         uint32_t dhk = addv<V, 1>(d, hk);                                \
         uint32_t y = addv<V, 1>(ch(e, f, g), bsig1<V>(e));               \

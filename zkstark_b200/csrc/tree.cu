@@ -169,6 +169,91 @@ __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, cons
     }
 }
 
+// The same polynomial from the per-size constant tables (CpArgs::tab): everything that depends on the point only
+// is read back instead of recomputed -- 9 multiplications per point, no inversion, half the registers.
+//   cp = a0 (f(x)-a_first) A_i + a1 (f(x)-a_last) B_i + a2 (f(g^2 x) - f(g x)^2 - f(x)^2) C_i
+struct CpCoefTab { uint32_t a0m, a1m, a2m, a_first, a_last; };
+__device__ __forceinline__ void cp_coef_tab(const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last, CpCoefTab& k)
+{
+    k.a0m = to_mont(reduce_u32(alpha_raw[0]));                          // field.rs:20-24
+    k.a1m = to_mont(reduce_u32(alpha_raw[1]));
+    k.a2m = to_mont(reduce_u32(alpha_raw[2]));
+    k.a_first = a_first;
+    k.a_last = a_last;
+}
+template <int C>
+__device__ __forceinline__ void cp_chunk_tab(const CpArgs& c, const uint32_t* f, uint32_t* out, uint32_t base,
+                                             const CpCoefTab& k)
+{
+    const uint32_t B = 1u << LOG_BLOWUP;
+    const uint32_t N = 1u << c.log_len, len_mask = N - 1u;
+    uint32_t fx[C], fg[C], fgg[C], ta[C], tb[C], tc[C];
+    if (C >= 4) {
+#pragma unroll
+        for (int j = 0; j < C; j += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(f + base + j);
+            const uint4 a = *reinterpret_cast<const uint4*>(c.tab + base + j);
+            const uint4 b = *reinterpret_cast<const uint4*>(c.tab + N + base + j);
+            const uint4 q = *reinterpret_cast<const uint4*>(c.tab + 2 * (size_t)N + base + j);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(f + ((base + j + B) & len_mask));
+            const uint4 v2 = *reinterpret_cast<const uint4*>(f + ((base + j + 2 * B) & len_mask));
+            fx[j] = v.x; fx[j + 1] = v.y; fx[j + 2] = v.z; fx[j + 3] = v.w;
+            ta[j] = a.x; ta[j + 1] = a.y; ta[j + 2] = a.z; ta[j + 3] = a.w;
+            tb[j] = b.x; tb[j + 1] = b.y; tb[j + 2] = b.z; tb[j + 3] = b.w;
+            tc[j] = q.x; tc[j + 1] = q.y; tc[j + 2] = q.z; tc[j + 3] = q.w;
+            fg[j] = v1.x; fg[j + 1] = v1.y; fg[j + 2] = v1.z; fg[j + 3] = v1.w;
+            fgg[j] = v2.x; fgg[j + 1] = v2.y; fgg[j + 2] = v2.z; fgg[j + 3] = v2.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const uint32_t i = base + j;
+            fx[j] = f[i]; fg[j] = f[(i + B) & len_mask]; fgg[j] = f[(i + 2 * B) & len_mask];
+            ta[j] = c.tab[i]; tb[j] = c.tab[N + i]; tc[j] = c.tab[2 * (size_t)N + i];
+        }
+    }
+    uint32_t o[C];
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        const uint32_t p0 = mont_mul(mont_mul(fsub(fx[j], k.a_first), ta[j]), k.a0m);
+        const uint32_t p1 = mont_mul(mont_mul(fsub(fx[j], k.a_last), tb[j]), k.a1m);
+        const uint32_t num = fsub(fsub(mont_mul(fgg[j], 1u), mont_mul(fg[j], fg[j])), mont_mul(fx[j], fx[j]));   // / R
+        const uint32_t p2 = mont_mul(mont_mul(num, tc[j]), k.a2m);
+        o[j] = fadd(fadd(p0, p1), p2);
+    }
+    if (C >= 4) {
+#pragma unroll
+        for (int j = 0; j < C; j += 4)
+            *reinterpret_cast<uint4*>(out + base + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < C; j++) out[base + j] = o[j];
+    }
+}
+
+// Builds CpArgs::tab for one size (one thread per point, run once per context and size).
+__global__ void __launch_bounds__(256) cp_table_kernel(uint32_t* tab, CpArgs c, PowTab pw)
+{
+    const uint32_t N = 1u << pw.log_N;
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t x = mont_mul(GEN, pow_h_m(pw, i));                    // canonical 5 h^i
+    const uint32_t xm = to_mont(x);
+    const uint32_t d0m = to_mont(fsub(x, 1u)), d1m = to_mont(fsub(x, c.g2));
+    const uint32_t xn_m = mont_pow(xm, (uint64_t)1 << c.log_n);          // x^n, one of 8 values
+    const uint32_t zinv_m = mont_inv(fsub(xn_m, R1));                    // 1 / (x^n - 1), never singular on the coset
+    const uint32_t cub_m = mont_mul(mont_mul(to_mont(fsub(x, c.g3)), d1m), to_mont(fsub(x, c.g1)));
+    tab[i] = mont_inv(d0m);                                              // A_i R
+    tab[N + i] = mont_inv(d1m);                                          // B_i R
+    tab[2 * (size_t)N + i] = to_mont(mont_mul(cub_m, zinv_m));           // C_i R^2
+}
+cudaError_t launch_cp_tables(cudaStream_t s, uint32_t* tab, CpArgs c, PowTab pow)
+{
+    const uint32_t N = 1u << pow.log_N;
+    cp_table_kernel<<<(N + 255) / 256, 256, 0, s>>>(tab, c, pow);
+    return cudaGetLastError();
+}
+
 template <int SRC>
 __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, uint32_t base, uint32_t count)
 {
@@ -180,6 +265,18 @@ __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, ui
         else if (count == 4) fold_chunk<4>(a.fold, a.pow, cur, next, base, beta);
         else if (count == 2) fold_chunk<2>(a.fold, a.pow, cur, next, base, beta);
         else fold_chunk<1>(a.fold, a.pow, cur, next, base, beta);
+    } else if (SRC == SRC_CP_TAB) {
+        const uint32_t* f = a.cp.f + (size_t)b * a.cp.f_stride;
+        uint32_t* out = a.vals + (size_t)b * a.vals_stride;
+        CpCoefTab kt;
+        if (a.cp.alpha_from_state) cp_coef_tab(a.state[b].alpha_raw, a.state[b].a_first, a.state[b].a_last, kt);
+        else cp_coef_tab(a.cp.alpha_raw, a.cp.a_first, a.cp.a_last, kt);
+        if (count >= 4) {
+#pragma unroll 1
+            for (uint32_t o = 0; o < count; o += 4) cp_chunk_tab<4>(a.cp, f, out, base + o, kt);   // 4 per trip: 24 loads in flight, low register count
+        }
+        else if (count == 2) cp_chunk_tab<2>(a.cp, f, out, base, kt);
+        else cp_chunk_tab<1>(a.cp, f, out, base, kt);
     } else if (SRC == SRC_CP) {
         const uint32_t* f = a.cp.f + (size_t)b * a.cp.f_stride;
         uint32_t* out = a.vals + (size_t)b * a.vals_stride;
@@ -208,7 +305,7 @@ __global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_ker
     const uint32_t base = t << a.k;
     uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
 
-    if (SRC == SRC_FOLD || SRC == SRC_CP) produce_values<SRC>(a, b, base, cnt);
+    if (SRC == SRC_FOLD || SRC == SRC_CP || SRC == SRC_CP_TAB) produce_values<SRC>(a, b, base, cnt);
     const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
 
     uint32_t stack[MAX_PASS_K][8];
@@ -533,7 +630,7 @@ __device__ __forceinline__ void coop_level(const TreeArgs& a, uint8_t* heap, con
         }
     }
     if (is_main) {
-        Dig8 r = coop_main<V>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13],
+        Dig8 r = coop_main<ZK_COOP_V>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13],
                               m[14], m[15], area, bar);
 #pragma unroll
         for (int w = 0; w < 8; w++) d[w] = r.v[w];
@@ -543,7 +640,7 @@ __device__ __forceinline__ void coop_level(const TreeArgs& a, uint8_t* heap, con
             for (int w = 0; w < 8; w++) out[w * out_p + j] = d[w];
         }
     } else {
-        coop_helper<V>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13], m[14],
+        coop_helper<ZK_COOP_HELPER_V>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], m[12], m[13], m[14],
                        m[15], area, bar);
     }
 }
@@ -621,7 +718,7 @@ __global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
     uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
     const uint32_t first = tile << log_tile;
 
-    if (SRC == SRC_FOLD || SRC == SRC_CP) {
+    if (SRC == SRC_FOLD || SRC == SRC_CP || SRC == SRC_CP_TAB) {
         // every layer has an even number (>= 8) of points: two consecutive points per thread
         if (2 * t < (1u << log_tile)) produce_values<SRC>(a, b, first + 2 * t, 2);
         __syncthreads();                                           // CP reads neighbours' f only; fold reads cur only
@@ -1009,7 +1106,7 @@ static cudaError_t launch_tile_src(cudaStream_t s, int src, const TreeArgs& a, u
     switch (src) {
         case SRC_VALUES: return launch_tile<SRC_VALUES>(s, a, batch);
         case SRC_FOLD: return launch_tile<SRC_FOLD>(s, a, batch);
-        case SRC_CP: return launch_tile<SRC_CP>(s, a, batch);
+        case SRC_CP: return a.cp.tab ? launch_tile<SRC_CP_TAB>(s, a, batch) : launch_tile<SRC_CP>(s, a, batch);
         case SRC_DIGESTS: return launch_tile<SRC_DIGESTS>(s, a, batch);
         default: return cudaErrorInvalidValue;
     }
@@ -1058,7 +1155,7 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
         switch (src) {
             case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
             case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
-            case SRC_CP: e = launch_pass<SRC_CP>(s, a, batch); break;
+            case SRC_CP: e = a.cp.tab ? launch_pass<SRC_CP_TAB>(s, a, batch) : launch_pass<SRC_CP>(s, a, batch); break;
             default: return cudaErrorInvalidValue;
         }
         launches++;
@@ -1086,7 +1183,7 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src, TreeArgs a, uint32_t 
     switch (src) {
         case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
         case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
-        case SRC_CP: e = launch_pass<SRC_CP>(s, a, batch); break;
+        case SRC_CP: e = a.cp.tab ? launch_pass<SRC_CP_TAB>(s, a, batch) : launch_pass<SRC_CP>(s, a, batch); break;
         default: return cudaErrorInvalidValue;
     }
     launches++;
