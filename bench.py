@@ -380,8 +380,12 @@ def extras(args, ctx, zk, line, clocks, world):
         ("fri_fold layer0", 4, k + 3, 4 * N + 2 * N),
         ("cp_eval", 5, k, 8 * N),
         ("merkle tree (all passes)", 1, k + 3, 4 * N + 32 * (2 * N - 1)),
+        # the same stream kernels at the size of BASELINE configs[4] (2^24 trace): the 2^20 working set is L2-sized and
+        # a 16 us launch is mostly ramp-up, these show what the kernels sustain out of HBM
+        ("fri_fold layer0 @2^27 points (2^24-trace size)", 4, 27, 6 << 27),
+        ("lde (all passes) @2^24 trace", 2, 24, 36 << 24),
     ]:
-        ms, msmin, _ = ctx.bench_kernel(which, ls, iters=10, flush_l2=True)
+        ms, msmin, _ = ctx.bench_kernel(which, ls, iters=10 if ls <= k + 3 else 4, flush_l2=True)
         gbs = nbytes / (ms * 1e-3) / 1e9
         rk[name] = {"bound": "hbm", "ms": ms, "algorithmic_bytes": nbytes, "achieved": gbs, "peak": hbm_peak,
                     "unit": "GB/s", "frac": gbs / hbm_peak}

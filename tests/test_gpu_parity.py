@@ -31,7 +31,7 @@ def test_merkle_reference_kat(ctx, kats):  # merkle.rs:112-182 through the CUDA 
         assert [t.hex() for t in m.trace(int(leaf))] == [k["heap"][s] for s in sibs]
 
 
-@pytest.mark.parametrize("log_size", [0, 1, 2, 3, 5, 9, 10, 11, 12, 13, 14, 16, 19])
+@pytest.mark.parametrize("log_size", list(range(0, 20)))   # every tile / warp-pair / leaf-pass regime
 def test_merkle_random_vs_oracle(ctx, orc, log_size):
     leaves = edge_values(1 << log_size, 100 + log_size)
     got = ctx.merkle_build(leaves)
@@ -198,6 +198,22 @@ def test_prove_full_size(ctx, orc):
     assert hashlib.sha256(tr).hexdigest() == hashlib.sha256(otr).hexdigest()
     assert st == ost
     assert orc.verify_fibsq(20, info.a_last, tr, True, st) == 0
+
+
+@pytest.mark.parametrize("log_n", [5, 12, 16])
+def test_prove_cp_forms_and_plain_hashing_agree(ctx, orc, log_n):
+    """The composition polynomial from the per-size constant tables and its per-point form, and the tile kernel with
+    and without two-warp node hashing, all give the oracle's bytes."""
+    otr, ost, _ = orc.prove_fibsq(log_n, 77)
+    try:
+        for cp_form, coop in [(-101, 128), (-100, 128), (-101, 0), (-101, 32)]:
+            ctx.bench_set(cp_form, 0)
+            ctx.bench_set(-1, (coop + 1) << 8)
+            tr, st = ctx.prove_fibsq(log_n, 77)
+            assert tr == otr and st == ost, (cp_form, coop)
+    finally:
+        ctx.bench_set(-101, 0)
+        ctx.bench_set(-1, (128 + 1) << 8)
 
 
 def test_prove_batch(ctx, orc):

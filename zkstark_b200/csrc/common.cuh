@@ -153,6 +153,41 @@ struct TreeArgs {
     CpArgs cp;
 };
 
+// ---- programmatic dependent launch.  Every kernel of the prove pipeline starts with pdl_wait() (griddepcontrol.wait:
+// until the previous kernel of the stream has completed and its memory is visible) and is launched through zk_launch()
+// with the programmatic-serialization attribute, so its CTAs may become resident while the previous kernel is still
+// running and the ~2-3 us launch/drain gap between dependent kernels shrinks to the wake-up of resident CTAs.
+// pdl_trigger() (griddepcontrol.launch_dependents) is what allows the NEXT kernel in: the small NTT / element-wise
+// kernels call it first thing; the tree kernels only in the closing CTA just before the channel step, because CTAs
+// that become resident early are packed onto whatever SMs are free at that moment and the latency-bound tile kernel
+// wants its 128 CTAs on 128 different SMs (measured: early trigger there costs +11 us per tree).
+// Without the launch attribute (ZK_NO_PDL=1) both instructions are no-ops and the stream serialises as usual.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter()
+{
+    pdl_trigger();
+    pdl_wait();
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t zk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- launchers (tree.cu)
 // Builds the whole tree over 2^log_size leaves taken from `src_kind`, per proof of the batch.
 cudaError_t launch_merkle_tree(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, int* n_launches);

@@ -130,6 +130,7 @@ __device__ __forceinline__ uint32_t sigma_pow_m(const NttPassArgs& a, uint32_t r
 template <int LOG_R, bool COSET>
 __global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_strided_kernel(const NttPassArgs a)
 {
+    pdl_enter();
     using C = NttCfg<LOG_R>;
     constexpr int R = C::R, RW = C::RW;
     extern __shared__ uint32_t smem[];
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_strided_kernel(con
 template <int LOG_R, int LOG_CS, bool COSET>
 __global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_final_kernel(const NttPassArgs a)
 {
+    pdl_enter();
     using C = NttCfg<LOG_R>;
     constexpr int R = C::R, RW = C::RW, CS = 1 << LOG_CS;
     extern __shared__ uint32_t smem[];
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_final_kernel(const
 // (equivalently: the transform of the trace extended by the phantom value -g sum a_i g^i).
 __global__ void phantom_fix_kernel(uint32_t* c, uint64_t stride, uint32_t log_n, PowTab hpow)
 {
+    pdl_enter();
     const uint32_t n = 1u << log_n;
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -277,6 +280,7 @@ __global__ void phantom_fix_kernel(uint32_t* c, uint64_t stride, uint32_t log_n,
 }
 __global__ void phantom_clear_kernel(uint32_t* c, uint64_t stride, uint32_t log_n)
 {
+    pdl_enter();
     c[(size_t)blockIdx.x * stride + (1u << log_n) - 1] = 0u;
 }
 
@@ -321,8 +325,7 @@ static cudaError_t launch_k(K kernel, dim3 grid, int threads, size_t smem, cudaS
         cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kernel<<<grid, threads, smem, s>>>(a);
-    return cudaGetLastError();
+    return zk_launch(kernel, grid, dim3(threads), smem, s, a);
 }
 
 template <int LOG_R>
@@ -436,8 +439,7 @@ cudaError_t launch_interpolate(cudaStream_t s, const uint32_t* tw_fwd, const uin
     cudaError_t e;
     const uint32_t n = 1u << log_n;
     if (phantom) {
-        phantom_clear_kernel<<<batch, 1, 0, s>>>(y, y_stride, log_n);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = zk_launch(phantom_clear_kernel, dim3(batch), dim3(1), 0, s, y, y_stride, log_n)) != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
     }
     uint32_t ninv_m = h_to_mont(h_inv(n % P));
@@ -449,10 +451,8 @@ cudaError_t launch_interpolate(cudaStream_t s, const uint32_t* tw_fwd, const uin
         dim3 grid(n / th, batch);
         // one CTA when n <= 256; for larger n the value t = c'[n-1] is only rewritten by the last CTA,
         // which is why the kernel never stores k = n-1 and a second tiny launch zeroes it.
-        phantom_fix_kernel<<<grid, th, 0, s>>>(coeffs, coeffs_stride, log_n, hpow);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        phantom_clear_kernel<<<batch, 1, 0, s>>>(coeffs, coeffs_stride, log_n);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = zk_launch(phantom_fix_kernel, grid, dim3(th), 0, s, coeffs, coeffs_stride, log_n, hpow)) != cudaSuccess) return e;
+        if ((e = zk_launch(phantom_clear_kernel, dim3(batch), dim3(1), 0, s, coeffs, coeffs_stride, log_n)) != cudaSuccess) return e;
         if (n_launches) (*n_launches) += 2;
     }
     return cudaSuccess;

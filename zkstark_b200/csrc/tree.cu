@@ -15,6 +15,7 @@
 // Leaf values can be produced in-kernel (north_star items 3/4): the FRI fold of the previous
 // layer (polynomial.rs:385-400 in evaluation form, proof.rs:110-112) or the composition
 // polynomial (prover.rs:101-173); the produced layer is written once and hashed from L1.
+#include <cstdlib>
 #include "common.cuh"
 #define ZK_SHA_DEVICE
 #include "sha256.cuh"
@@ -234,6 +235,7 @@ __device__ __forceinline__ void cp_chunk_tab(const CpArgs& c, const uint32_t* f,
 // Builds CpArgs::tab for one size (one thread per point, run once per context and size).
 __global__ void __launch_bounds__(256) cp_table_kernel(uint32_t* tab, CpArgs c, PowTab pw)
 {
+    pdl_enter();
     const uint32_t N = 1u << pw.log_N;
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
@@ -250,8 +252,7 @@ __global__ void __launch_bounds__(256) cp_table_kernel(uint32_t* tab, CpArgs c, 
 cudaError_t launch_cp_tables(cudaStream_t s, uint32_t* tab, CpArgs c, PowTab pow)
 {
     const uint32_t N = 1u << pow.log_N;
-    cp_table_kernel<<<(N + 255) / 256, 256, 0, s>>>(tab, c, pow);
-    return cudaGetLastError();
+    return zk_launch(cp_table_kernel, dim3((N + 255) / 256), dim3(256), 0, s, tab, c, pow);
 }
 
 template <int SRC>
@@ -297,6 +298,7 @@ __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, ui
 template <int SRC, int V = ZK_SHA_V, int UNI = ZK_SHA_UNI>
 __global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_kernel(const TreeArgs a)
 {
+    pdl_wait();
     const uint32_t b = blockIdx.y;
     const uint32_t t = blockIdx.x * PASS_THREADS + threadIdx.x;
     const uint32_t n_threads = 1u << (a.in_level - a.k);
@@ -707,6 +709,7 @@ __device__ __forceinline__ void tile_reduce(const TreeArgs& a, uint8_t* heap, co
 template <int SRC, int V = ZK_TILE_SHA_V>
 __global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
 {
+    pdl_wait();
     TileBufs tb;
     tb.P = blockDim.x;
     tb.A = tile_smem;
@@ -739,6 +742,7 @@ __global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
         __threadfence();
         tile_reduce<SRC_DIGESTS, V>(a, heap, vals, a.in_level - log_tile, 0, a.in_level - log_tile, true, tb, root);
     }
+    pdl_trigger();                                                 // every other CTA has exited: the next kernel may move in
     if (t == 0 && a.post != POST_NONE) post_root(a, b, root);
 }
 
@@ -746,6 +750,7 @@ __global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
 __global__ void __launch_bounds__(256) fold_kernel(const uint32_t* cur, uint32_t* next, FoldArgs f, PowTab pw,
                                                    uint64_t next_stride, const ProofState* st)
 {
+    pdl_enter();
     const uint32_t b = blockIdx.y;
     const uint32_t half = 1u << f.log_half;
     const uint32_t* c = cur + (size_t)b * f.cur_stride;
@@ -763,6 +768,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint32_t* cur, uint32_t
 __global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab pw, uint64_t out_stride,
                                                  const ProofState* st)
 {
+    pdl_enter();
     const uint32_t b = blockIdx.y;
     const uint32_t N = 1u << c.log_len;
     const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
@@ -809,6 +815,7 @@ __device__ __forceinline__ size_t sibling_node(uint32_t log_size, uint32_t leaf,
 // the 4 + L records one after the other, ~24 dependent DRAM round trips = 60 us at k = 20).
 __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
 {
+    pdl_enter();
     const uint32_t b = blockIdx.x;
     const uint32_t k = a.log_n, L = k, log_N = k + LOG_BLOWUP, N = 1u << log_N, B = 1u << LOG_BLOWUP;
     ProofState* ps = a.state + b;
@@ -909,6 +916,7 @@ __device__ __forceinline__ bool shard_locate(const ShardDecommitArgs& a, uint32_
 }
 __global__ void __launch_bounds__(256) shard_decommit_kernel(const ShardDecommitArgs a)
 {
+    pdl_enter();
     const uint32_t k = a.log_n, L = k, log_N = k + LOG_BLOWUP, N = 1u << log_N, B = 1u << LOG_BLOWUP;
     uint8_t* tr = a.out;
     const uint32_t x = (uint32_t)((size_t)a.state->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
@@ -970,8 +978,7 @@ __global__ void __launch_bounds__(256) shard_decommit_kernel(const ShardDecommit
 }
 cudaError_t launch_shard_decommit(cudaStream_t s, const ShardDecommitArgs& a)
 {
-    shard_decommit_kernel<<<1, 256, 0, s>>>(a);
-    return cudaGetLastError();
+    return zk_launch(shard_decommit_kernel, dim3(1), dim3(256), 0, s, a);
 }
 
 // channel.rs:19-26 over the decommitment records (prover.rs:274-288), one THREAD per proof: 4 + L sequential
@@ -989,6 +996,7 @@ __device__ __forceinline__ uint32_t tail_word(const uint32_t st[8], const uint32
 __global__ void __launch_bounds__(32) chan_tail_kernel(ProofState* states, const uint8_t* transcripts, uint64_t stride,
                                                        uint32_t log_n, uint32_t batch)
 {
+    pdl_enter();
     const uint32_t b = blockIdx.x * 32 + threadIdx.x;
     if (b >= batch) return;
     const uint32_t L = log_n, log_N = log_n + LOG_BLOWUP;
@@ -1022,14 +1030,14 @@ __global__ void __launch_bounds__(32) chan_tail_kernel(ProofState* states, const
 cudaError_t launch_chan_tail(cudaStream_t s, ProofState* states, const uint8_t* transcripts, uint64_t stride,
                              uint32_t log_n, uint32_t batch)
 {
-    chan_tail_kernel<<<(batch + 31) / 32, 32, 0, s>>>(states, transcripts, stride, log_n, batch);
-    return cudaGetLastError();
+    return zk_launch(chan_tail_kernel, dim3((batch + 31) / 32), dim3(32), 0, s, states, transcripts, stride, log_n, batch);
 }
 
 // channel.rs:12-17 + public inputs: zero state, a[0], a[n-2]
 __global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64_t trace_stride,
                                   uint32_t log_n, uint32_t batch)
 {
+    pdl_enter();
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     ProofState s;
@@ -1052,8 +1060,7 @@ static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch
 {
     uint32_t n_threads = 1u << (a.in_level - a.k);
     dim3 grid((n_threads + PASS_THREADS - 1) / PASS_THREADS, batch);
-    tree_pass_kernel<SRC><<<grid, PASS_THREADS, 0, s>>>(a);
-    return cudaGetLastError();
+    return zk_launch(tree_pass_kernel<SRC>, grid, dim3(PASS_THREADS), 0, s, a);
 }
 // a.in_level inputs per proof -> root (+ channel step); in_level <= 2 * TILE_LOG
 template <int SRC>
@@ -1098,8 +1105,7 @@ static cudaError_t launch_tile(cudaStream_t s, const TreeArgs& a, uint32_t batch
             attr_done[dev] = true;
         }
     }
-    tree_tile_kernel<SRC><<<dim3(n_tiles, batch), threads, smem, s>>>(b);
-    return cudaGetLastError();
+    return zk_launch(tree_tile_kernel<SRC>, dim3(n_tiles, batch), dim3(threads), smem, s, b);
 }
 static cudaError_t launch_tile_src(cudaStream_t s, int src, const TreeArgs& a, uint32_t batch)
 {
@@ -1213,6 +1219,11 @@ cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int*
 // trees of up to 2^g_tile_direct_log leaves (summed over the batch) skip the per-thread-subtree leaf pass
 uint32_t g_tile_direct_log = ZK_TILE_DIRECT_LOG;
 uint32_t g_tile_log_override = 0;
+bool pdl_enabled()
+{
+    static const bool on = [] { const char* e = getenv("ZK_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 uint32_t g_tile_shift = ZK_TILE_SHIFT;              // the tile kernel runs 2^g_tile_shift tiles per tree
 uint32_t g_pass_log_threads = ZK_PASS_LOG_THREADS;  // the leaf pass runs ~2^g_pass_log_threads threads (summed over the batch)
 uint32_t g_coop_cnt = ZK_COOP_CNT;                  // tile kernel: widest level hashed by warp pairs
@@ -1229,6 +1240,7 @@ void set_tile_direct_log(uint32_t v)
 
 __global__ void state_set_kernel(ProofState* st, uint32_t a_first, uint32_t a_last)
 {
+    pdl_enter();
     uint32_t* w = reinterpret_cast<uint32_t*>(st);
     for (int i = 0; i < 64; i++) w[i] = 0;
     st->a_first = a_first;
@@ -1236,8 +1248,7 @@ __global__ void state_set_kernel(ProofState* st, uint32_t a_first, uint32_t a_la
 }
 cudaError_t launch_state_set(cudaStream_t s, ProofState* st, uint32_t a_first, uint32_t a_last)
 {
-    state_set_kernel<<<1, 1, 0, s>>>(st, a_first, a_last);
-    return cudaGetLastError();
+    return zk_launch(state_set_kernel, dim3(1), dim3(1), 0, s, st, a_first, a_last);
 }
 
 cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant)
@@ -1306,15 +1317,13 @@ cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_ev
 {
     DecommitArgs a{log_n, f_eval, f_stride, f_heap, f_heap_stride, layers, layers_stride,
                    layer_heaps, layer_heaps_stride, state, transcript, transcript_stride};
-    decommit_kernel<<<batch, 256, 0, s>>>(a);
-    return cudaGetLastError();
+    return zk_launch(decommit_kernel, dim3(batch), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
                               uint32_t log_n, uint32_t batch)
 {
-    state_init_kernel<<<(batch + 127) / 128, 128, 0, s>>>(st, traces, trace_stride, log_n, batch);
-    return cudaGetLastError();
+    return zk_launch(state_init_kernel, dim3((batch + 127) / 128), dim3(128), 0, s, st, traces, trace_stride, log_n, batch);
 }
 
 cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uint32_t log_half, FoldArgs f,
@@ -1324,8 +1333,7 @@ cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uin
     uint32_t work = half >= 4 ? half / 4 : half;
     dim3 grid((work + 255) / 256, batch);
     f.log_half = log_half;
-    fold_kernel<<<grid, 256, 0, s>>>(cur, next, f, pow, next_stride, st);
-    return cudaGetLastError();
+    return zk_launch(fold_kernel, grid, dim3(256), 0, s, cur, next, f, pow, next_stride, st);
 }
 
 cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, uint32_t batch, uint64_t out_stride,
@@ -1334,8 +1342,7 @@ cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, ui
     if (c.log_len == 0) c.log_len = pow.log_N;
     uint32_t N = 1u << c.log_len;
     dim3 grid((N / 4 + 255) / 256, batch);
-    cp_kernel<<<grid, 256, 0, s>>>(cp_out, c, pow, out_stride, st);
-    return cudaGetLastError();
+    return zk_launch(cp_kernel, grid, dim3(256), 0, s, cp_out, c, pow, out_stride, st);
 }
 
 }  // namespace zk
