@@ -68,3 +68,75 @@ def test_two_rank_batch_gloo(orc):
         assert t == 11.0            # max over ranks
         assert total == n_proofs    # every proof done exactly once
         assert digests == want      # global order, identical on every rank
+
+
+# ---------------------------------------------------------------- sharded single proof: exchange logic on CPU
+def test_coset_to_block_exchange_is_blocked_cyclic():
+    """LDE cosets -> one all-to-all -> blocked-cyclic ownership (zkstark_b200/sharded.py), with virtual ranks."""
+    import torch
+    from zkstark_b200.sharded import LocalComm, local_to_global, pack_cosets, unpack_blocks
+    for G, log_n, lb in [(2, 8, 5), (4, 9, 6), (8, 10, 7), (1, 6, 4)]:
+        n, N = 1 << log_n, 8 << log_n
+        f_eval = torch.arange(N, dtype=torch.int32) * 7 + 3
+        send = []
+        for r in range(G):
+            E = torch.stack([f_eval[(r + c * G)::8] for c in range(8 // G)])      # coset r + cG: f_eval[8j + coset]
+            send.append(pack_cosets(E, G, lb))
+        recv = LocalComm(G).all_to_all(send)
+        for r in range(G):
+            local = unpack_blocks(recv[r], G, lb)
+            assert local.numel() == N // G
+            idx = torch.tensor([local_to_global(i, G, r, lb) for i in range(N // G)])
+            assert torch.equal(local, f_eval[idx])
+            # fold partners stay on the rank: i and i + N/2 map to local indices loc and loc + N/(2G)
+            half = N // G // 2
+            assert torch.equal(idx[:half] + N // 2, idx[half:])
+
+
+def _comm_worker(rank, ws, port, q):
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from zkstark_b200.sharded import TorchComm
+        comm = TorchComm()
+        x = torch.arange(8, dtype=torch.int32).view(ws, -1) + 100 * rank
+        a2a = comm.all_to_all([x])[0]
+        ag = comm.all_gather([torch.tensor([rank, rank + 10], dtype=torch.int32)])[0]
+        buf = torch.zeros(6, dtype=torch.uint8)
+        buf[rank * 3: rank * 3 + 3] = torch.tensor([1 + rank, 200, 7], dtype=torch.uint8)   # disjoint owners
+        mx = comm.all_reduce_max([buf])[0]
+        q.put((rank, a2a.tolist(), ag.tolist(), mx.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_torch_comm_matches_local_comm_gloo():
+    """The real collectives (here gloo, on the GPU box NCCL) and the virtual-rank shuffles agree."""
+    import torch
+    from zkstark_b200.sharded import LocalComm
+    ws = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_comm_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(ws))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lc = LocalComm(ws)
+    xs = [torch.arange(8, dtype=torch.int32).view(ws, -1) + 100 * r for r in range(ws)]
+    want_a2a = lc.all_to_all(xs)
+    want_ag = lc.all_gather([torch.tensor([r, r + 10], dtype=torch.int32) for r in range(ws)])
+    bufs = []
+    for r in range(ws):
+        b = torch.zeros(6, dtype=torch.uint8)
+        b[r * 3: r * 3 + 3] = torch.tensor([1 + r, 200, 7], dtype=torch.uint8)
+        bufs.append(b)
+    want_mx = lc.all_reduce_max(bufs)
+    for rank, a2a, ag, mx in res:
+        assert a2a == want_a2a[rank].view(ws, -1).tolist() or a2a == want_a2a[rank].tolist()
+        assert ag == want_ag[rank].tolist()
+        assert mx == want_mx[rank].tolist()

@@ -77,6 +77,29 @@ class TorchComm:
         return [xs[0]]
 
 
+def pack_cosets(E, G, log_block):
+    """E[c][j] = f_eval[8 j + (r + c G)] (the C = 8/G coset transforms of rank r, j < n) -> all-to-all send buffer
+    [d][c][bl][tt] with j = (bl G + d) jb + tt: destination rank d owns the blocks bl G + d."""
+    C_, n = E.shape
+    jb = 1 << (log_block - 3)                  # j-values per block (a block holds all 8 cosets of jb points)
+    nbl = n // jb // G                         # blocks per rank
+    return E.view(C_, nbl, G, jb).permute(2, 0, 1, 3).contiguous()
+
+
+def unpack_blocks(recv, G, log_block):
+    """all-to-all result [g][c][bl][tt] (from source rank g) -> rank-local evaluations in blocked-cyclic order:
+    local[(bl jb + tt) 8 + (c G + g)]."""
+    jb = 1 << (log_block - 3)
+    C_ = 8 // G
+    nbl = recv.numel() // (G * C_ * jb)
+    return recv.view(G, C_, nbl, jb).permute(2, 3, 1, 0).contiguous().view(-1)
+
+
+def local_to_global(loc, G, rank, log_block):
+    """index map of the blocked-cyclic ownership (csrc/common.cuh shard_global)"""
+    return ((((loc >> log_block) * G) + rank) << log_block) | (loc & ((1 << log_block) - 1))
+
+
 class _Tree:
     """One committed layer on one rank: local values, local heap (bottom levels), replicated upper heap."""
     def __init__(self, vals, heap, upper, length, distributed):
@@ -193,16 +216,14 @@ class ShardedProver:
             E = self._i32(C_, n)
             for c in range(C_):
                 ctx.shard_lde_coset(coeffs.data_ptr(), k, r + c * G, work.data_ptr(), E[c].data_ptr())
-            # E[c][j], j = ((bl*G + d) * jb + tt)  ->  send[d][c][bl][tt]
-            send.append(E.view(C_, nbl, G, jb).permute(2, 0, 1, 3).contiguous())
+            send.append(pack_cosets(E, G, lb))
         self._mark("lde_cosets+pack")
         recv = self.comm.all_to_all(send)
         self._mark("all_to_all")
         self.comm_bytes += 4 * N * (G - 1) // G
         f_local = []
         for idx in range(nr):
-            # recv[g][c][bl][tt] -> f_local[bl][tt][r = c*G + g]
-            f_local.append(recv[idx].view(G, C_, nbl, jb).permute(2, 3, 1, 0).contiguous().view(-1))
+            f_local.append(unpack_blocks(recv[idx], G, lb))
         del send, recv, work
         self._mark("unpack")
         f_trees = self._commit_tree(f_local, N, POST_F, 0, states, transcripts)
