@@ -163,6 +163,15 @@ int zk_shard_cp_dev(zk_ctx *ctx, const uint32_t *f_local, const uint32_t *halo, 
 /* FRI fold of the rank-local part of layer layer_k (beta from state_dev); log_N0 = log2 of the LDE size */
 int zk_shard_fold_dev(zk_ctx *ctx, const uint32_t *cur_local, uint64_t local_len, uint32_t layer_k, uint32_t log_N0,
                       uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void *state_dev, uint32_t *next_local);
+/* zk_shard_cp_dev followed by zk_shard_merkle_blocks_dev of the composition layer, fused in one pass */
+int zk_shard_cp_blocks_dev(zk_ctx *ctx, const uint32_t *f_local, const uint32_t *halo, uint64_t local_len,
+                           uint32_t log_n, uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void *state_dev,
+                           uint32_t *cp_local, uint8_t *heap_local);
+/* zk_shard_fold_dev followed by zk_shard_merkle_blocks_dev of the folded layer, fused in one pass (the fold feeds
+ * the leaf hashing): next_local gets local_len/2 values, heap_local their block subtrees */
+int zk_shard_fold_blocks_dev(zk_ctx *ctx, const uint32_t *cur_local, uint64_t local_len, uint32_t layer_k,
+                             uint32_t log_N0, uint32_t n_ranks, uint32_t rank, uint32_t log_block,
+                             const void *state_dev, uint32_t *next_local, uint8_t *heap_local);
 /* replicated tail once a layer is too small to shard: layer first_layer is complete at layers_arena[0..);
  * layers first_layer+1..L (values, heaps at 64 bytes per value of the preceding layers) are appended */
 int zk_shard_fri_tail_dev(zk_ctx *ctx, uint32_t log_n, uint32_t first_layer, uint32_t *layers_arena,

@@ -83,6 +83,8 @@ def lib():
         "zk_shard_cp_dev": ([vp, vp, vp, u64, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fold_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fri_tail_dev": ([vp, u32, u32, vp, vp, vp, vp], i32),
+        "zk_shard_fold_blocks_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp, vp], i32),
+        "zk_shard_cp_blocks_dev": ([vp, vp, vp, u64, u32, u32, u32, u32, vp, vp, vp], i32),
         "zk_shard_decommit_dev": ([vp, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp], i32),
         "zk_bench_set": ([vp, i32, u32], i32),
         "zk_bench_set_tile_direct_log": ([vp, u32], i32),
@@ -306,6 +308,14 @@ class Context:
         self._ck(lib().zk_shard_decommit_dev(self._h, log_n, n_ranks, rank, log_block, first_tail, arr,
                                              C.c_void_p(tail_vals_ptr), C.c_void_p(tail_heaps_ptr),
                                              C.c_void_p(state_ptr), C.c_void_p(transcript_ptr)))
+
+    def shard_cp_blocks(self, f_ptr, halo_ptr, local_len, log_n, n_ranks, rank, log_block, state_ptr, cp_ptr, heap_ptr):
+        self._ck(lib().zk_shard_cp_blocks_dev(self._h, C.c_void_p(f_ptr), C.c_void_p(halo_ptr), local_len, log_n, n_ranks, rank,
+                                              log_block, C.c_void_p(state_ptr), C.c_void_p(cp_ptr), C.c_void_p(heap_ptr)))
+
+    def shard_fold_blocks(self, cur_ptr, local_len, layer_k, log_N0, n_ranks, rank, log_block, state_ptr, next_ptr, heap_ptr):
+        self._ck(lib().zk_shard_fold_blocks_dev(self._h, C.c_void_p(cur_ptr), local_len, layer_k, log_N0, n_ranks, rank, log_block,
+                                                C.c_void_p(state_ptr), C.c_void_p(next_ptr), C.c_void_p(heap_ptr)))
 
     def shard_fri_tail(self, log_n, first_layer, layers_ptr, heaps_ptr, state_ptr, transcript_ptr):
         self._ck(lib().zk_shard_fri_tail_dev(self._h, log_n, first_layer, C.c_void_p(layers_ptr), C.c_void_p(heaps_ptr),

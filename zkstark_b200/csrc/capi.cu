@@ -217,6 +217,27 @@ CpArgs make_cp_args(uint32_t log_n)
     return c;
 }
 
+// Points c.tab at the per-size constant tables of the composition polynomial, building them on first use (once per
+// context and size: input-independent domain constants, 12 N bytes).  Leaves c.tab null when they are switched off or
+// do not fit in memory; the kernels then compute the same factors per point.
+cudaError_t attach_cp_tab(zk_ctx* ctx, SizeTables* T, CpArgs& c, int* nl)
+{
+    c.tab = nullptr;
+    if (!ctx->use_cp_tab) return cudaSuccess;
+    const size_t N = (size_t)1 << T->h.tab.log_N;
+    if (!T->cp_tab.p) {
+        if (T->cp_tab.ensure(12 * N) != cudaSuccess) {
+            cudaGetLastError();
+            return cudaSuccess;
+        }
+        cudaError_t e = launch_cp_tables(ctx->stream, (uint32_t*)T->cp_tab.p, c, T->h.tab);
+        if (e != cudaSuccess) return e;
+        if (nl) (*nl)++;
+    }
+    c.tab = (const uint32_t*)T->cp_tab.p;
+    return cudaSuccess;
+}
+
 struct StageTimer {
     zk_ctx* ctx;
     int idx = 0;
@@ -333,17 +354,7 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
     a.cp.f = f_eval;
     a.cp.f_stride = N;
     a.cp.alpha_from_state = 1;
-    if (ctx->use_cp_tab) {
-        if (!T->cp_tab.p) {   // once per context and size: input-independent domain constants (12 N bytes)
-            if (T->cp_tab.ensure(12 * N) == cudaSuccess) {
-                CK(launch_cp_tables(s, (uint32_t*)T->cp_tab.p, a.cp, T->h.tab));
-                nl++;
-            } else {
-                cudaGetLastError();   // not enough memory for the tables: fall back to computing them per point
-            }
-        }
-        a.cp.tab = (const uint32_t*)T->cp_tab.p;
-    }
+    CK(attach_cp_tab(ctx, T, a.cp, &nl));
     CK(launch_merkle_tree(s, SRC_CP, a, nb, &nl));
     tm.mark();
     // Part 3 (prover.rs:192-254)
@@ -593,8 +604,10 @@ int zk_cp_eval_fibsq_dev(zk_ctx* ctx, const uint32_t* f_eval, uint32_t log_n, ui
     for (int j = 0; j < 3; j++) c.alpha_raw[j] = alpha_raw[j];
     c.a_first = a_first % P;
     c.a_last = a_last % P;
+    int nl = 1;
+    CK(attach_cp_tab(ctx, T, c, &nl));
     CK(launch_cp(ctx->stream, cp_out, c, T->h.tab, 1, 0));
-    ctx->launches += 1;
+    ctx->launches += nl;
     return ZK_OK;
 }
 
@@ -940,6 +953,76 @@ int zk_shard_fold_dev(zk_ctx* ctx, const uint32_t* cur_local, uint64_t local_len
     return ZK_OK;
 }
 
+// zk_shard_cp_dev + zk_shard_merkle_blocks_dev in one pass (north_star item 3 fused into the CP tree's leaf pass).
+int zk_shard_cp_blocks_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, uint64_t local_len, uint32_t log_n,
+                           uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev, uint32_t* cp_local,
+                           uint8_t* heap_local)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!f_local || !halo || !state_dev || !cp_local || !heap_local || !is_pow2(local_len) || n_ranks == 0 || rank >= n_ranks)
+        return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    if ((local_len * n_ranks) != ((uint64_t)1 << (log_n + LOG_BLOWUP)) || local_len < ((uint64_t)1 << log_block) || log_block < 5)
+        return fail(ctx, ZK_ERR_INVALID, "local_len * n_ranks must be 8n and hold at least one block of >= 32");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
+    const uint32_t lg = ilog2(local_len);
+    TreeArgs a{};
+    a.counters = (uint32_t*)ctx->counters.p;
+    a.state = (ProofState*)const_cast<void*>(state_dev);
+    a.pow = T->h.tab;
+    a.cp = make_cp_args(log_n);
+    a.cp.f = f_local;
+    a.cp.halo = halo;
+    a.cp.log_len = lg;
+    a.cp.shard = ShardMap{n_ranks, rank, log_block, 0};
+    a.cp.alpha_from_state = 1;
+    a.vals = cp_local;
+    a.heap = heap_local;
+    a.log_size = lg;
+    int nl = 0;
+    CK(launch_merkle_partial(ctx->stream, SRC_CP, a, 1, lg - log_block, &nl));
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
+// zk_shard_fold_dev + zk_shard_merkle_blocks_dev in one pass: the leaf pass of the block subtrees folds the previous
+// layer first (north_star item 4: fold, beta-mix and next-layer leaf hashing fused), so the new layer is written once
+// and hashed from L1 instead of being re-read by a second kernel.
+int zk_shard_fold_blocks_dev(zk_ctx* ctx, const uint32_t* cur_local, uint64_t local_len, uint32_t layer_k, uint32_t log_N0,
+                             uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev,
+                             uint32_t* next_local, uint8_t* heap_local)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!cur_local || !next_local || !heap_local || !state_dev || !is_pow2(local_len) || local_len < 2 || n_ranks == 0 ||
+        rank >= n_ranks || log_N0 > 30)
+        return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    const uint32_t lg_next = ilog2(local_len) - 1;
+    if (log_block < 5 || lg_next < log_block)
+        return fail(ctx, ZK_ERR_INVALID, "the folded layer must hold at least one block of >= 32 values per rank");
+    CK(cudaSetDevice(ctx->device));
+    SizeTables* T;
+    int rc = get_tables(ctx, log_N0, &T);
+    if (rc) return rc;
+    TreeArgs a{};
+    a.counters = (uint32_t*)ctx->counters.p;
+    a.state = (ProofState*)const_cast<void*>(state_dev);
+    a.pow = T->h.tab;
+    a.fold = make_fold_args(layer_k);
+    a.fold.cur = cur_local;
+    a.fold.log_half = lg_next;
+    a.fold.beta_from_state = 1;
+    a.fold.shard = ShardMap{n_ranks, rank, log_block, 0};
+    a.vals = next_local;
+    a.heap = heap_local;
+    a.log_size = lg_next;
+    int nl = 0;
+    CK(launch_merkle_partial(ctx->stream, SRC_FOLD, a, 1, lg_next - log_block, &nl));
+    ctx->launches += nl;
+    return ZK_OK;
+}
+
 // Replicated tail: layer `first_layer` (its tree already committed) is complete in layers_arena[0 .. N>>first_layer);
 // folds + trees + channel steps of layers first_layer+1 .. L follow, appended in the arenas.
 int zk_shard_fri_tail_dev(zk_ctx* ctx, uint32_t log_n, uint32_t first_layer, uint32_t* layers_arena, uint8_t* heaps_arena,
@@ -1090,6 +1173,7 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
             ca = make_cp_args(log_size); ca.f = (const uint32_t*)ctx->s0.p;
             ca.alpha_raw[0] = 361545003u; ca.alpha_raw[1] = 3235878091u; ca.alpha_raw[2] = 2708123352u;
             ca.a_first = 1; ca.a_last = 2338775057u;
+            CK(attach_cp_tab(ctx, T, ca, nullptr));
             break;
         default:
             CK(ctx->s0.ensure(4096));

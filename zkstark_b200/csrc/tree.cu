@@ -765,6 +765,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint32_t* cur, uint32_t
     }
 }
 
+template <bool TAB>
 __global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab pw, uint64_t out_stride,
                                                  const ProofState* st)
 {
@@ -774,10 +775,18 @@ __global__ void __launch_bounds__(256) cp_kernel(uint32_t* out, CpArgs c, PowTab
     const uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (base >= N) return;
     const bool from_state = c.alpha_from_state && st;
-    CpCoef k;
-    if (from_state) cp_coef(c, st[b].alpha_raw, reduce_u32(st[b].a_first), reduce_u32(st[b].a_last), k);
-    else cp_coef(c, c.alpha_raw, reduce_u32(c.a_first), reduce_u32(c.a_last), k);
-    cp_chunk<4>(c, pw, c.f + (size_t)b * c.f_stride, out + (size_t)b * out_stride, base, k);
+    const uint32_t* al = from_state ? st[b].alpha_raw : c.alpha_raw;
+    const uint32_t a_first = reduce_u32(from_state ? st[b].a_first : c.a_first);
+    const uint32_t a_last = reduce_u32(from_state ? st[b].a_last : c.a_last);
+    if (TAB) {
+        CpCoefTab k;
+        cp_coef_tab(al, a_first, a_last, k);
+        cp_chunk_tab<4>(c, c.f + (size_t)b * c.f_stride, out + (size_t)b * out_stride, base, k);
+    } else {
+        CpCoef k;
+        cp_coef(c, al, a_first, a_last, k);
+        cp_chunk<4>(c, pw, c.f + (size_t)b * c.f_stride, out + (size_t)b * out_stride, base, k);
+    }
 }
 
 // ---------------------------------------------------------------- decommit gather (prover.rs:263-289)
@@ -1342,7 +1351,8 @@ cudaError_t launch_cp(cudaStream_t s, uint32_t* cp_out, CpArgs c, PowTab pow, ui
     if (c.log_len == 0) c.log_len = pow.log_N;
     uint32_t N = 1u << c.log_len;
     dim3 grid((N / 4 + 255) / 256, batch);
-    return zk_launch(cp_kernel, grid, dim3(256), 0, s, cp_out, c, pow, out_stride, st);
+    return c.tab ? zk_launch(cp_kernel<true>, grid, dim3(256), 0, s, cp_out, c, pow, out_stride, st)
+                 : zk_launch(cp_kernel<false>, grid, dim3(256), 0, s, cp_out, c, pow, out_stride, st);
 }
 
 }  // namespace zk

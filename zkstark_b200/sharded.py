@@ -140,8 +140,11 @@ class ShardedProver:
     def _u8(self, *shape):
         return self.torch.empty(shape, dtype=self.torch.uint8, device=self.dev)
 
-    def _commit_tree(self, vals_by_rank, length, post, fri_layer, states, transcripts):
-        """Distributed Merkle tree of a layer of global length `length`; returns per-rank _Tree."""
+    def _commit_tree(self, vals_by_rank, length, post, fri_layer, states, transcripts, fold_from=None, cp_from=None):
+        """Distributed Merkle tree of a layer of global length `length`; returns per-rank _Tree.
+        fold_from = (cur_by_rank, layer_k): the layer does not exist yet -- the leaf pass of the block subtrees
+        folds layer_k into vals_by_rank first (one fused pass).  cp_from = (f_by_rank, halo_by_rank): likewise for the
+        composition polynomial."""
         t, lb, G = self.torch, self.lb, self.G
         local_len = length // G
         nbl = local_len >> lb
@@ -149,7 +152,16 @@ class ShardedProver:
         heaps, roots = [], []
         for idx, r in enumerate(self.comm.my_ranks):
             heap = self._u8(32 * (2 * local_len - 1))
-            self.ctx.shard_merkle_blocks(vals_by_rank[idx].data_ptr(), local_len, lb, heap.data_ptr())
+            if cp_from is not None:
+                f_loc, halos = cp_from
+                self.ctx.shard_cp_blocks(f_loc[idx].data_ptr(), halos[idx].data_ptr(), local_len, self.k, G, r, lb,
+                                         states[idx].data_ptr(), vals_by_rank[idx].data_ptr(), heap.data_ptr())
+            elif fold_from is None:
+                self.ctx.shard_merkle_blocks(vals_by_rank[idx].data_ptr(), local_len, lb, heap.data_ptr())
+            else:
+                cur, layer_k = fold_from
+                self.ctx.shard_fold_blocks(cur[idx].data_ptr(), 2 * local_len, layer_k, self.log_N, G, r, lb,
+                                           states[idx].data_ptr(), vals_by_rank[idx].data_ptr(), heap.data_ptr())
             heaps.append(heap)
             roots.append(heap[32 * (nbl - 1): 32 * (2 * nbl - 1)].view(nbl, 32))
         gathered = self.comm.all_gather(roots)           # [G, nbl, 32] on every rank
@@ -233,30 +245,24 @@ class ShardedProver:
         heads = [f.view(nbl, 1 << lb)[:, :16].contiguous() for f in f_local]
         heads_all = self.comm.all_gather(heads)  # [G, nbl, 16]
         self.comm_bytes += 4 * 16 * (N >> lb)
-        cp_local = []
+        halos = []
         for idx, r in enumerate(ranks):
             if r + 1 < G:
-                halo = heads_all[idx][r + 1].contiguous()
+                halos.append(heads_all[idx][r + 1].contiguous())
             else:
-                halo = t.roll(heads_all[idx][0], shifts=-1, dims=0).contiguous()   # block b+1 wraps to rank 0, next bl
-            cp = self._i32(N // G)
-            ctx.shard_cp(f_local[idx].data_ptr(), halo.data_ptr(), N // G, k, G, r, lb, states[idx].data_ptr(), cp.data_ptr())
-            cp_local.append(cp)
-        self._mark("cp_eval+halo")
-        layers = [self._commit_tree(cp_local, N, POST_CP, 0, states, transcripts)]
+                halos.append(t.roll(heads_all[idx][0], shifts=-1, dims=0).contiguous())   # block b+1 wraps to rank 0, next bl
+        cp_local = [self._i32(N // G) for _ in ranks]
+        self._mark("halo")
+        layers = [self._commit_tree(cp_local, N, POST_CP, 0, states, transcripts, cp_from=(f_local, halos))]
         self._mark("cp_tree")
 
         # Part 3: FRI.  Folds stay rank-local while a layer has >= 2 blocks per rank.
         cur, length, i = cp_local, N, 0
         while (length // G) >= (2 << lb):
-            nxt = []
-            for idx, r in enumerate(ranks):
-                o = self._i32(length // G // 2)
-                ctx.shard_fold(cur[idx].data_ptr(), length // G, i, log_N, G, r, lb, states[idx].data_ptr(), o.data_ptr())
-                nxt.append(o)
+            nxt = [self._i32(length // G // 2) for _ in ranks]
+            layers.append(self._commit_tree(nxt, length // 2, POST_FRI, i + 1, states, transcripts, fold_from=(cur, i)))
             i += 1
             length //= 2
-            layers.append(self._commit_tree(nxt, length, POST_FRI, i, states, transcripts))
             cur = nxt
         self._mark("fri_sharded_layers")
         # replicated tail: gather layer i (one block per rank) and finish on every rank
