@@ -745,13 +745,16 @@ int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t* out)
     if (!out || log_n < 1 || log_n > 30) return ZK_ERR_INVALID;
     const uint64_t n1 = ((uint64_t)1 << log_n) - 1;
     // Montgomery domain for the sequential recurrence a_i = a_{i-2}^2 + a_{i-1}^2 (prover.rs:32-39)
+    // (one dependent squaring per step: a_{i-1}^2 of step i is a_{i-2}^2 of step i+1)
     uint32_t x = to_mont(1), y = to_mont(secret % P);
+    uint32_t xx = mont_mul(x, x);
     out[0] = 1;
     if (n1 > 1) out[1] = secret % P;
     for (uint64_t i = 2; i < n1; i++) {
-        uint32_t z = fadd(mont_mul(x, x), mont_mul(y, y));
+        const uint32_t yy = mont_mul(y, y);
+        const uint32_t z = fadd(xx, yy);
         out[i] = from_mont(z);
-        x = y;
+        xx = yy;
         y = z;
     }
     return ZK_OK;

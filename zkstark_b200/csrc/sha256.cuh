@@ -133,8 +133,8 @@ __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { re
            chain; the three sums that consume the fresh e / a are single 3-input adds (IADD3) */            \
         uint32_t hk = addv<1, 1>(h, (kw));                               \
         uint32_t dhk = addv<1, 1>(d, hk);                                \
-        uint32_t s1 = bsig1<0>(e), cc = ch(e, f, g);                     \
-        uint32_t t2 = hk + bsig0<0>(a) + maj(a, b, c);                   \
+        uint32_t s1 = bsig1<(V) & 4>(e), cc = ch(e, f, g);               \
+        uint32_t t2 = hk + bsig0<(V) & 8>(a) + maj(a, b, c);             \
         d = dhk + s1 + cc;                                               \
         h = t2 + s1 + cc;                                                \
     } else {                                                             \
