@@ -36,11 +36,11 @@ constexpr uint32_t TILE_MIN_LOG = 7;
 #define ZK_COOP_CNT 128         // tile kernel: levels with <= this many nodes hash each node with a warp pair (0: off)
 #endif
 #ifndef ZK_PASS_THREADS
-#define ZK_PASS_THREADS 128
+#define ZK_PASS_THREADS 256
 #endif
 constexpr uint32_t PASS_THREADS = ZK_PASS_THREADS;
 #ifndef ZK_PASS_MINBLOCKS
-#define ZK_PASS_MINBLOCKS 1
+#define ZK_PASS_MINBLOCKS 5       // 256 x 5: <= 51 registers, no spills in any source variant; 1354 -> 1333 us per 2^23 leaves (swept 32..1024 x 1..16)
 #endif
 constexpr uint32_t MAX_PASS_K = 6;
 #ifndef ZK_SHA_UNI
