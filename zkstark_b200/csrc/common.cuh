@@ -43,6 +43,9 @@ constexpr uint32_t PASS_THREADS = ZK_PASS_THREADS;
 #define ZK_PASS_MINBLOCKS 5       // 256 x 5: <= 51 registers, no spills in any source variant; 1354 -> 1333 us per 2^23 leaves (swept 32..1024 x 1..16)
 #endif
 constexpr uint32_t MAX_PASS_K = 6;
+#ifndef ZK_PASS_MAX_K
+#define ZK_PASS_MAX_K 6
+#endif
 #ifndef ZK_SHA_UNI
 #define ZK_SHA_UNI 2  // 1: leaf and node hashes share one copy of the data-block compression; 2: + leaf-specialised prologue and schedule
 #endif

@@ -1064,6 +1064,7 @@ extern uint32_t g_tile_log_override;
 extern uint32_t g_tile_shift;
 extern uint32_t g_pass_log_threads;
 extern uint32_t g_coop_cnt;
+static uint32_t pass_max_k();
 template <int SRC>
 static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch)
 {
@@ -1164,7 +1165,7 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
         // leaf pass: enough threads to fill 148 SMs several times over, else fewer levels per thread
         int k = (int)a.log_size + (int)lb - (int)g_pass_log_threads;
         if (k < 1) k = 1;
-        if (k > (int)MAX_PASS_K) k = MAX_PASS_K;
+        if (k > (int)pass_max_k()) k = pass_max_k();
         if (k > (int)(a.log_size - TILE_LOG)) k = a.log_size - TILE_LOG;
         a.k = k;
         switch (src) {
@@ -1228,6 +1229,16 @@ cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int*
 // trees of up to 2^g_tile_direct_log leaves (summed over the batch) skip the per-thread-subtree leaf pass
 uint32_t g_tile_direct_log = ZK_TILE_DIRECT_LOG;
 uint32_t g_tile_log_override = 0;
+// deepest per-thread subtree of the leaf pass (ZK_PASS_MAX_K overrides the default for experiments)
+static uint32_t pass_max_k()
+{
+    static const uint32_t v = [] {
+        const char* e = getenv("ZK_PASS_MAX_K");
+        uint32_t k = e ? (uint32_t)atoi(e) : (uint32_t)ZK_PASS_MAX_K;
+        return k < 1 ? 1u : (k > MAX_PASS_K ? MAX_PASS_K : k);
+    }();
+    return v;
+}
 bool pdl_enabled()
 {
     static const bool on = [] { const char* e = getenv("ZK_NO_PDL"); return !(e && e[0] == '1'); }();
