@@ -258,7 +258,7 @@ def main():
     }
 
     if rank == 0 and not args.no_extras:
-        extras(args, ctx, zk, line, clocks, world)
+        extras(args, ctx, zk, line, clocks, world, step_resident)
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -312,7 +312,7 @@ def run_sharded(args, ctx, zk, torch, dist, world, rank, local, stream, barrier)
         dist.destroy_process_group()
 
 
-def extras(args, ctx, zk, line, clocks, world):
+def extras(args, ctx, zk, line, clocks, world, step_resident):
     """Stage breakdown, per-kernel rooflines (live CUDA-event timings) and the CPU baseline."""
     import numpy as np
     k = args.log_n
@@ -335,7 +335,17 @@ def extras(args, ctx, zk, line, clocks, world):
         if best is None or st["total"] < best["total"]:
             best = st
     stages = best
+    # the same breakdown for one batched step (all proofs of the step advance through a stage together)
+    bst = None
+    for _ in range(3):
+        step_resident()
+        st = ctx.last_stage_ms()
+        if bst is None or st["total"] < bst["total"]:
+            bst = st
     ctx.set_stage_timing(False)
+    line["stage_ms_batched_step"] = bst
+    if bst["interpolate"] + bst["lde"] > 0:
+        line["lde_elems_per_s_batched"] = args.batch * N / ((bst["interpolate"] + bst["lde"]) * 1e-3)
     line["prove_ms_single"] = stages["total"]
     line["stage_ms"] = stages
     if stages["interpolate"] + stages["lde"] > 0:

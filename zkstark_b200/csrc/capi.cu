@@ -16,7 +16,8 @@
 namespace zk {
 cudaError_t launch_interpolate(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow,
                                PowTab wpow, uint32_t log_n, bool phantom, uint32_t* y, uint64_t y_stride,
-                               uint32_t* coeffs, uint64_t coeffs_stride, uint32_t batch, int* n_launches);
+                               uint32_t* coeffs, uint64_t coeffs_stride, uint32_t batch, int* n_launches,
+                               unsigned long long* acc);
 cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
                        uint32_t log_n, const uint32_t* coeffs, uint64_t coeffs_stride, uint32_t* work,
                        uint64_t work_stride, uint32_t* evals, uint64_t evals_stride, uint32_t batch,
@@ -140,6 +141,11 @@ void free_powtab(PowTabOwned& t)
     if (t.lo) cudaFree(t.lo);
     if (t.hi) cudaFree(t.hi);
     t = PowTabOwned{};
+}
+
+unsigned long long* phantom_acc(zk_ctx* ctx)
+{
+    return (unsigned long long*)((char*)ctx->counters.p + 4 * 256 /* MAX_BATCH */);
 }
 
 int get_tables(zk_ctx* ctx, uint32_t log_N, SizeTables** out)
@@ -324,7 +330,7 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
     CK(launch_state_init(s, states, traces, n, log_n, nb));
     nl++;
     // Part 1 (prover.rs:60-85)
-    CK(launch_interpolate(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, true, traces, n, coeffs, n, nb, &nl));
+    CK(launch_interpolate(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, true, traces, n, coeffs, n, nb, &nl, phantom_acc(ctx)));
     tm.mark();
     CK(launch_lde(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, coeffs, n, (uint32_t*)ctx->work.p, N,
                   f_eval, N, nb, &nl));
@@ -467,8 +473,9 @@ int zk_ctx_create_on_stream(int device, void* cuda_stream, zk_ctx** out)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
     int rc = init_tw(ctx);
     if (rc == ZK_OK && sha_init_constants() != cudaSuccess) rc = ZK_ERR_CUDA;
-    if (rc == ZK_OK && (ctx->counters.ensure(4 * MAX_BATCH) != cudaSuccess ||
-                        cudaMemset(ctx->counters.p, 0, 4 * MAX_BATCH) != cudaSuccess)) rc = ZK_ERR_CUDA;
+    // [0, 4 MAX_BATCH): tile-arrival counters; [4 MAX_BATCH, 12 MAX_BATCH): 64-bit phantom-point accumulators
+    if (rc == ZK_OK && (ctx->counters.ensure(12 * MAX_BATCH) != cudaSuccess ||
+                        cudaMemset(ctx->counters.p, 0, 12 * MAX_BATCH) != cudaSuccess)) rc = ZK_ERR_CUDA;
     if (rc) { delete ctx; return rc; }
     *out = ctx;
     return ZK_OK;
@@ -533,7 +540,7 @@ int zk_interpolate_subgroup_dev(zk_ctx* ctx, uint32_t* y, uint32_t n_points, uin
     if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
     int nl = 0;
     CK(launch_interpolate(ctx->stream, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, n_points == n - 1, y, n,
-                          coeffs_out, n, 1, &nl));
+                          coeffs_out, n, 1, &nl, phantom_acc(ctx)));
     ctx->launches += nl;
     return ZK_OK;
 }
@@ -1204,7 +1211,8 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
             case 2: e = launch_lde(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_size, (const uint32_t*)ctx->s0.p, 0,
                                    (uint32_t*)ctx->s2.p, N8, (uint32_t*)ctx->s1.p, N8, 1, &nl); break;
             case 3: e = launch_interpolate(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_size, true,
-                                           (uint32_t*)ctx->s0.p, n_in, (uint32_t*)ctx->s1.p, n_in, 1, &nl); break;
+                                           (uint32_t*)ctx->s0.p, n_in, (uint32_t*)ctx->s1.p, n_in, 1, &nl,
+                                           ctx->bench_variant == -200 ? nullptr : phantom_acc(ctx)); break;
             case 4: e = launch_fold(s, (const uint32_t*)ctx->s0.p, (uint32_t*)ctx->s1.p, log_size - 1, fa, T->h.tab, 1, 0); nl++; break;
             case 5: e = launch_cp(s, (uint32_t*)ctx->s1.p, ca, T->h.tab, 1, 0); nl++; break;
             default: ops = bench_intpipe(s, (uint32_t*)ctx->s0.p, n_sm, (int)log_size); e = cudaGetLastError(); nl++; break;

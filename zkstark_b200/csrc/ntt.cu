@@ -284,6 +284,56 @@ __global__ void phantom_clear_kernel(uint32_t* c, uint64_t stride, uint32_t log_
     c[(size_t)blockIdx.x * stride + (1u << log_n) - 1] = 0u;
 }
 
+// The phantom point up front (used when the caller provides an accumulator): the interpolant of the n-1 trace points
+// is the size-n inverse transform of (a_0 .. a_{n-2}, y) with y chosen so that the top coefficient vanishes,
+//   c_{n-1} = n^-1 sum_i y_i g^(-i(n-1)) = n^-1 sum_i y_i g^i = 0   =>   y = -g sum_{i<n-1} a_i g^i,
+// so one reduction over the trace replaces the post-transform correction pass (read + write of all n coefficients).
+// Partial sums are canonical residues < 2^32, at most 2^19 of them: their plain 64-bit sum cannot overflow, so CTAs
+// combine with one integer atomicAdd and the last kernel reduces mod p.
+constexpr int PH_CH = 8;  // trace values per thread
+__global__ void __launch_bounds__(256) phantom_sum_kernel(const uint32_t* y, uint64_t stride, uint32_t log_n, PowTab hpow,
+                                                          unsigned long long* acc)
+{
+    pdl_enter();
+    __shared__ uint32_t red[8];
+    const uint32_t n1 = (1u << log_n) - 1u;                    // points 0 .. n-2
+    const uint32_t* yb = y + (size_t)blockIdx.y * stride;
+    const uint32_t i0 = (blockIdx.x * 256 + threadIdx.x) * PH_CH;
+    uint32_t sum = 0;
+    if (i0 < n1) {
+        const uint32_t sh = hpow.log_N - log_n;                // g = h^(N/n)
+        const uint32_t g_m = pw(hpow, 1u << sh);
+        uint32_t gp = pw(hpow, (i0 << sh) & ((1u << hpow.log_N) - 1u));
+#pragma unroll
+        for (int j = 0; j < PH_CH; j++) {
+            if (i0 + j < n1) sum = fadd(sum, mont_mul(yb[i0 + j], gp));
+            gp = mont_mul(gp, g_m);
+        }
+    }
+    // block sum of canonical residues (64-bit plain sum of <= 256 values, reduced once)
+    unsigned long long w = sum;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (uint32_t)(w % P);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        atomicAdd(acc + blockIdx.y, t % P);
+    }
+}
+__global__ void phantom_set_kernel(uint32_t* y, uint64_t stride, uint32_t log_n, PowTab hpow, unsigned long long* acc, uint32_t batch)
+{
+    pdl_enter();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const uint32_t sh = hpow.log_N - log_n;
+    const uint32_t g_m = pw(hpow, 1u << sh);
+    const uint32_t S = (uint32_t)(acc[b] % P);
+    acc[b] = 0;                                                // re-arm for the next call on this stream
+    y[(size_t)b * stride + (1u << log_n) - 1u] = fneg(mont_mul(S, g_m));
+}
+
 // ---------------------------------------------------------------- host side
 struct NttPlan {
     uint32_t n_pass;
@@ -433,11 +483,22 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
 // y[n-1] ignored when n_points == n-1.  coeffs may alias y (in place).
 cudaError_t launch_interpolate(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow,
                                PowTab wpow, uint32_t log_n, bool phantom, uint32_t* y, uint64_t y_stride,
-                               uint32_t* coeffs, uint64_t coeffs_stride, uint32_t batch, int* n_launches)
+                               uint32_t* coeffs, uint64_t coeffs_stride, uint32_t batch, int* n_launches,
+                               unsigned long long* acc)
 {
     NttTables T{tw_fwd, tw_inv, hpow, wpow};
     cudaError_t e;
     const uint32_t n = 1u << log_n;
+    if (phantom && acc && log_n >= 1) {
+        // phantom value first, then a plain inverse transform (acc: one zeroed 64-bit word per proof)
+        const uint32_t per_cta = 256 * PH_CH;
+        dim3 grid((n - 1 + per_cta - 1) / per_cta, batch);
+        if ((e = zk_launch(phantom_sum_kernel, grid, dim3(256), 0, s, (const uint32_t*)y, y_stride, log_n, hpow, acc)) != cudaSuccess) return e;
+        if ((e = zk_launch(phantom_set_kernel, dim3((batch + 63) / 64), dim3(64), 0, s, y, y_stride, log_n, hpow, acc, batch)) != cudaSuccess) return e;
+        if (n_launches) (*n_launches) += 2;
+        uint32_t ninv_m = h_to_mont(h_inv(n % P));
+        return run_ntt(s, T, log_n, 1, false, true, y, y_stride, y, y_stride, coeffs, coeffs_stride, true, ninv_m, batch, n_launches);
+    }
     if (phantom) {
         if ((e = zk_launch(phantom_clear_kernel, dim3(batch), dim3(1), 0, s, y, y_stride, log_n)) != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
