@@ -825,7 +825,7 @@ __device__ __forceinline__ size_t sibling_node(uint32_t log_size, uint32_t leaf,
 __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
 {
     pdl_enter();
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = blockIdx.y;                               // proof; blockIdx.x: slice of the gather items
     const uint32_t k = a.log_n, L = k, log_N = k + LOG_BLOWUP, N = 1u << log_N, B = 1u << LOG_BLOWUP;
     ProofState* ps = a.state + b;
     uint8_t* tr = a.transcript + (size_t)b * a.transcript_stride;
@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
     const uint32_t x = (uint32_t)((size_t)ps->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
     const size_t off0 = 84 + 36 * (size_t)L;
     const size_t rec0 = 12 + 32 * (size_t)log_N;
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         // prover.rs:238: the last FRI polynomial has degree 0, i.e. its 8 evaluations are equal
         const size_t voff = layer_vals_off_dev(log_N, L);
         uint32_t bad = 0;
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
         ps->pad[0] = bad;
     }
     // values and length prefixes: one thread per record
-    for (uint32_t r = threadIdx.x; r < 4 + L; r += blockDim.x) {
+    for (uint32_t r = threadIdx.x; blockIdx.x == 0 && r < 4 + L; r += blockDim.x) {
         if (r < 4) {                                             // prover.rs:266-277
             uint8_t* rec = tr + off0 + r * rec0;
             *reinterpret_cast<uint32_t*>(rec) = (r < 3) ? f[x + r * B] : lay[x];
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
     const uint32_t per_rec_f = log_N;
     const uint32_t n_items = 4 * per_rec_f + 2 * (L * log_N - L * (L - 1) / 2);
     const uint32_t sub = threadIdx.x & 7;
-    for (uint32_t it = threadIdx.x >> 3; it < n_items; it += blockDim.x >> 3) {
+    for (uint32_t it = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); it < n_items; it += gridDim.x * (blockDim.x >> 3)) {
         const uint8_t* heap;
         uint8_t* dst;
         uint32_t lg, leaf, s;
@@ -1337,7 +1337,11 @@ cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_ev
 {
     DecommitArgs a{log_n, f_eval, f_stride, f_heap, f_heap_stride, layers, layers_stride,
                    layer_heaps, layer_heaps_stride, state, transcript, transcript_stride};
-    return zk_launch(decommit_kernel, dim3(batch), dim3(256), 0, s, a);
+    // 32 digests per CTA pass: enough CTAs that every sibling load of a proof is in flight at once
+    const uint32_t log_N = log_n + LOG_BLOWUP, n_items = 4 * log_N + 2 * (log_n * log_N - log_n * (log_n - 1) / 2);
+    uint32_t slices = (n_items + 31) / 32;
+    if (batch > 16) slices = 1 + (slices - 1) / (batch / 16);        // large batches fill the machine on their own
+    return zk_launch(decommit_kernel, dim3(slices, batch), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
