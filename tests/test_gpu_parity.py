@@ -226,6 +226,17 @@ def test_prove_batch(ctx, orc):
         assert trs[j].tobytes() == otr and sts[j].tobytes() == ost
 
 
+@pytest.mark.parametrize("log_n", [3, 6, 14])
+def test_prove_batch_device_channel_tail(ctx, orc, log_n):
+    """Batches of >= 8 proofs finish the channel over the decommitment records on the device (chan_tail_kernel)."""
+    nb = 9
+    traces = np.stack([zk.trace_fibsq(log_n, 500 + j) for j in range(nb)])
+    trs, sts = ctx.prove_fibsq_batch(log_n, traces)
+    for j in range(nb):
+        otr, ost, _ = orc.prove_fibsq(log_n, 500 + j)
+        assert trs[j].tobytes() == otr and sts[j].tobytes() == ost
+
+
 def test_prove_batch_sub_batching(ctx, orc):
     log_n, nb = 8, 7
     ctx.set_memory_budget(3 * 1672 * (1 << log_n) + 4096)  # forces sub-batches of <= 3 proofs

@@ -990,48 +990,105 @@ cudaError_t launch_shard_decommit(cudaStream_t s, const ShardDecommitArgs& a)
     return zk_launch(shard_decommit_kernel, dim3(1), dim3(256), 0, s, a);
 }
 
-// channel.rs:19-26 over the decommitment records (prover.rs:274-288), one THREAD per proof: 4 + L sequential
-// commits, each state = SHA256(state || record).  Used for batches (the chains of all proofs advance in
-// parallel); for a single proof the host does the same ~340 compressions faster than one GPU thread.
-__device__ __forceinline__ uint32_t tail_word(const uint32_t st[8], const uint32_t* rec, uint32_t nw, uint32_t i,
-                                              uint32_t last, uint32_t bits)
+// channel.rs:19-26 over the decommitment records (prover.rs:274-288): 4 + L sequential commits, each
+// state = SHA256(state || record) -- ~340 dependent compressions at k = 20, used for batches (the chains of all proofs
+// advance in parallel; for a single proof the host does it after the copy).  One CTA per proof:
+//   1. all threads stage the records in shared memory as big-endian message words;
+//   2. only the FIRST block of a record contains the running state, so the message schedules K[t] + W[t] of every
+//      other block (93 % of them) are computed up front, one block per thread, into shared memory;
+//   3. thread 0 walks the chain: a full compression for the first block of a record, rounds only for the rest.
+// The first version (one thread per proof, message words fetched from global memory block by block) took 0.9 ms.
+__device__ __forceinline__ uint32_t tail_rec_len(uint32_t r, uint32_t log_N)    // bytes of record r
 {
-    if (i < 8) return st[i];
-    if (i < nw) return sha::bswap32(rec[i - 8]);
+    return r < 4 ? 12 + 32 * log_N : 24 + 64 * (log_N - (r - 4));
+}
+// message word i of record r's commit (state || record, padded): i >= 8 only (the state words are handled by the caller)
+__device__ __forceinline__ uint32_t tail_msg_word(const uint32_t* recw, uint32_t nw, uint32_t i, uint32_t last)
+{
+    if (i < nw) return recw[i - 8];
     if (i == nw) return 0x80000000u;
-    if (i == last) return bits;  // message < 2^29 bytes: the high length word is 0
+    if (i == last) return 32u * nw;  // message < 2^29 bytes: the high length word is 0
     return 0u;
 }
-__global__ void __launch_bounds__(32) chan_tail_kernel(ProofState* states, const uint8_t* transcripts, uint64_t stride,
-                                                       uint32_t log_n, uint32_t batch)
+template <int V>
+__device__ __forceinline__ void compress_kw(uint32_t st[8], const uint32_t* kw)   // rounds only, K[t] + W[t] given
+{
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+    using sha::addv; using sha::bsig0; using sha::bsig1; using sha::ch; using sha::maj;
+#pragma unroll 1
+    for (int i = 0; i < 64; i += 16) {
+        uint32_t kk[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) kk[q] = kw[i + q];
+#define ZK_KW_T(j) (kk[j])
+        ZK_SHA_16ROUNDS(V, ZK_KW_T)
+#undef ZK_KW_T
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+__global__ void __launch_bounds__(256) chan_tail_kernel(ProofState* states, const uint8_t* transcripts, uint64_t stride,
+                                                        uint32_t log_n)
 {
     pdl_enter();
-    const uint32_t b = blockIdx.x * 32 + threadIdx.x;
-    if (b >= batch) return;
-    const uint32_t L = log_n, log_N = log_n + LOG_BLOWUP;
-    ProofState* ps = states + b;
-    const uint8_t* tr = transcripts + (size_t)b * stride;
+    extern __shared__ __align__(16) uint32_t tail_smem[];
+    __shared__ uint32_t rec_word0[40], rec_blk0[40];            // first word / first precomputed block of record r
+    const uint32_t L = log_n, log_N = log_n + LOG_BLOWUP, n_rec = 4 + L;
+    ProofState* ps = states + blockIdx.x;
+    const uint32_t* tr = reinterpret_cast<const uint32_t*>(transcripts + (size_t)blockIdx.x * stride + 84 + 36 * (size_t)L);
+    if (threadIdx.x == 0) {
+        uint32_t w = 0, bk = 0;
+        for (uint32_t r = 0; r < n_rec; r++) {
+            rec_word0[r] = w; rec_blk0[r] = bk;
+            const uint32_t nw = 8 + tail_rec_len(r, log_N) / 4;
+            w += nw - 8;
+            bk += (nw + 3 + 15) / 16 - 1;                        // blocks after the first
+        }
+        rec_word0[n_rec] = w; rec_blk0[n_rec] = bk;
+    }
+    __syncthreads();
+    const uint32_t n_words = rec_word0[n_rec], n_blk = rec_blk0[n_rec];
+    uint32_t* recw = tail_smem;                                  // [n_words] big-endian message words of all records
+    uint32_t* kw = tail_smem + ((n_words + 3) & ~3u);            // [n_blk][64]
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) recw[i] = sha::bswap32(tr[i]);
+    __syncthreads();
+    for (uint32_t bk = threadIdx.x; bk < n_blk; bk += blockDim.x) {
+        uint32_t r = 0;
+        while (rec_blk0[r + 1] <= bk) r++;
+        const uint32_t j = bk - rec_blk0[r] + 1;                 // block index inside the record's message (>= 1)
+        const uint32_t nw = 8 + tail_rec_len(r, log_N) / 4, last = 16 * ((nw + 3 + 15) / 16) - 1;
+        const uint32_t* rw = recw + rec_word0[r];
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) w[q] = tail_msg_word(rw, nw, 16 * j + q, last);
+        uint32_t* o = kw + 64 * (size_t)bk;
+#pragma unroll
+        for (int q = 0; q < 16; q++) o[q] = w[q] + sha::c_k[q];
+#pragma unroll 1
+        for (int i = 16; i < 64; i += 16) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                w[q] = w[q] + sha::ssig1<0>(w[(q + 14) & 15]) + w[(q + 9) & 15] + sha::ssig0<0>(w[(q + 1) & 15]);
+                o[i + q] = w[q] + sha::c_k[i + q];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     uint32_t st[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) st[i] = ps->chan_at_query[i];
-    size_t off = 84 + 36 * (size_t)L;
-    for (uint32_t r = 0; r < 4 + L; r++) {
-        const uint32_t len = r < 4 ? 12 + 32 * log_N : 24 + 64 * (log_N - (r - 4));
-        const uint32_t* rec = reinterpret_cast<const uint32_t*>(tr + off);
-        const uint32_t nw = 8 + len / 4;                 // message words (state || record)
-        const uint32_t n_blocks = (nw + 3 + 15) / 16;    // + 0x80 word + 64-bit length
-        const uint32_t last = 16 * n_blocks - 1, bits = 32 * nw;
-        uint32_t out[8];
+    for (uint32_t r = 0; r < n_rec; r++) {
+        const uint32_t nw = 8 + tail_rec_len(r, log_N) / 4, n_blocks = (nw + 3 + 15) / 16, last = 16 * n_blocks - 1;
+        const uint32_t* rw = recw + rec_word0[r];
+        uint32_t out[8], w[16];
         sha::init_iv(out);
-        for (uint32_t blk = 0; blk < n_blocks; blk++) {
-            uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) w[j] = tail_word(st, rec, nw, 16 * blk + j, last, bits);
-            sha::compress<0>(out, w);
-        }
+        for (int q = 0; q < 8; q++) { w[q] = st[q]; w[8 + q] = tail_msg_word(rw, nw, 8 + q, last); }
+        sha::compress<0>(out, w);
+        const uint32_t* kb = kw + 64 * (size_t)rec_blk0[r];
+        for (uint32_t j = 1; j < n_blocks; j++) compress_kw<64>(out, kb + 64 * (size_t)(j - 1));
 #pragma unroll
         for (int i = 0; i < 8; i++) st[i] = out[i];
-        off += len;
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) ps->chan[i] = st[i];
@@ -1039,7 +1096,25 @@ __global__ void __launch_bounds__(32) chan_tail_kernel(ProofState* states, const
 cudaError_t launch_chan_tail(cudaStream_t s, ProofState* states, const uint8_t* transcripts, uint64_t stride,
                              uint32_t log_n, uint32_t batch)
 {
-    return zk_launch(chan_tail_kernel, dim3((batch + 31) / 32), dim3(32), 0, s, states, transcripts, stride, log_n, batch);
+    const uint32_t log_N = log_n + LOG_BLOWUP;
+    size_t words = 0, blocks = 0;
+    for (uint32_t r = 0; r < 4 + log_n; r++) {
+        const uint32_t len = r < 4 ? 12 + 32 * log_N : 24 + 64 * (log_N - (r - 4));
+        const uint32_t nw = 8 + len / 4;
+        words += nw - 8;
+        blocks += (nw + 3 + 15) / 16 - 1;
+    }
+    const size_t smem = 4 * (((words + 3) & ~(size_t)3) + 64 * blocks);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(chan_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    return zk_launch(chan_tail_kernel, dim3(batch), dim3(256), smem, s, states, transcripts, stride, log_n);
 }
 
 // channel.rs:12-17 + public inputs: zero state, a[0], a[n-2]
