@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the zkstark_b200 hot path (contract: see DESIGN.md "Measurement").
 
-A "step" is `--batch` (default 16) independent prove() calls (interpolate -> LDE -> Merkle -> CP -> FRI ->
+A "step" is `--batch` (default 32) independent prove() calls (interpolate -> LDE -> Merkle -> CP -> FRI ->
 decommit; prover.rs:9-293) per rank, each of one synthetic FibonacciSq trace of BASELINE.json configs[2]:
 trace 2^20, blow-up 8 (8,388,608-point LDE), secret 3141592 + global proof index.  The proofs of a step run
 as one batched launch sequence (the latency-bound upper Merkle levels and Fiat-Shamir steps of one proof
@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the trace domain (BASELINE configs[2] = 20)")
-    ap.add_argument("--batch", type=int, default=16, help="independent proofs per rank per step (proofs of one step run as one batched launch sequence)")
+    ap.add_argument("--batch", type=int, default=32, help="independent proofs per rank per step (proofs of one step run as one batched launch sequence)")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / stage breakdown")
     ap.add_argument("--workload", default="batch", choices=["batch", "sharded"],
                     help="batch: independent proofs per rank (headline, weak scaling); sharded: ONE proof of 2^log-n "

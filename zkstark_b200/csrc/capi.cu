@@ -397,9 +397,23 @@ int enqueue_prove(zk_ctx* ctx, cudaStream_t s, uint32_t log_n, uint32_t p0, uint
 // Batches of >= 4 proofs run as TWO lanes on two streams (the ctx stream and a side stream, event fork / join): while
 // one lane is in the latency-bound upper levels and Fiat-Shamir steps of a tree, the other lane's bulk hashing fills the
 // machine (measured with two contexts: +2.4 % proofs/s at 16 proofs per step).
-int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcripts_out, uint8_t* states_out)
+// host_rows (optional): nb rows of n-1 trace values in (pinned) host memory, uploaded here -- the second lane's rows on
+// its own stream, so that their copy overlaps the first lane's kernels.
+int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcripts_out, uint8_t* states_out,
+                   const uint32_t* host_rows = nullptr)
 {
     const uint32_t log_N = log_n + LOG_BLOWUP;
+    const size_t n_row = (size_t)1 << log_n;
+    // rows of n-1 host values -> rows of n device words (one plain copy per row: a pitched 2-D copy of rows this wide
+    // falls off the DMA fast path)
+    auto upload = [&](cudaStream_t st, uint32_t b0, uint32_t b1) -> cudaError_t {
+        for (uint32_t b = b0; host_rows && b < b1; b++) {
+            cudaError_t e = cudaMemcpyAsync((uint32_t*)ctx->traces.p + n_row * b, host_rows + (n_row - 1) * (size_t)b, 4 * (n_row - 1),
+                                            cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
     const size_t trs = (transcript_len(log_n) + 63) & ~(size_t)63, trl = transcript_len(log_n);
     SizeTables* T;
     int rc = get_tables(ctx, log_N, &T);
@@ -415,12 +429,15 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
     CK(attach_cp_tab(ctx, T, cp0, &nl));
     const bool two_lanes = ctx->lanes && nb >= 4 && !ctx->stage_timing && ctx->lane_stream;
     if (!two_lanes) {
+        CK(upload(s, 0, nb));
         if ((rc = enqueue_prove(ctx, s, log_n, 0, nb, T, cp0.tab, device_tail, &tm, &nl))) return rc;
     } else {
         const uint32_t nb0 = (nb + 1) / 2;
         CK(cudaEventRecord(ctx->ev_fork, s));
         CK(cudaStreamWaitEvent(ctx->lane_stream, ctx->ev_fork, 0));
+        CK(upload(s, 0, nb0));
         if ((rc = enqueue_prove(ctx, s, log_n, 0, nb0, T, cp0.tab, device_tail, nullptr, &nl))) return rc;
+        CK(upload(ctx->lane_stream, nb0, nb));
         if ((rc = enqueue_prove(ctx, ctx->lane_stream, log_n, nb0, nb - nb0, T, cp0.tab, device_tail, nullptr, &nl))) return rc;
         CK(cudaEventRecord(ctx->ev_join, ctx->lane_stream));
         CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
@@ -841,12 +858,8 @@ int zk_prove_fibsq_batch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const u
     if ((rc = ensure_workspace(ctx, log_n, nbmax))) return rc;
     for (uint32_t done = 0; done < n_proofs; done += nbmax) {
         uint32_t nb = n_proofs - done < nbmax ? n_proofs - done : nbmax;
-        // rows of n-1 host values -> rows of n device words (one plain copy per row: a pitched 2-D copy
-        // of rows this wide falls off the DMA fast path)
-        for (uint32_t b = 0; b < nb; b++)
-            CK(cudaMemcpyAsync((uint32_t*)ctx->traces.p + n * b, traces + (n - 1) * (size_t)(done + b), 4 * (n - 1),
-                               cudaMemcpyHostToDevice, ctx->stream));
-        if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done))) return rc;
+        if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done,
+                                 traces + (n - 1) * (size_t)done))) return rc;
     }
     return ZK_OK;
 }
