@@ -237,6 +237,21 @@ def test_prove_batch_device_channel_tail(ctx, orc, log_n):
         assert trs[j].tobytes() == otr and sts[j].tobytes() == ost
 
 
+def test_prove_is_repeatable_under_concurrency(ctx, orc):
+    """Races in the cooperative hashing, the last-arriver tile reduction, the two-lane batches or the programmatic
+    launches would show up as run-to-run differences: 40 repetitions, one answer."""
+    log_n, nb = 11, 12
+    traces = np.stack([zk.trace_fibsq(log_n, 900 + j) for j in range(nb)])
+    want = [orc.prove_fibsq(log_n, 900 + j)[:2] for j in range(nb)]
+    for rep in range(20):
+        trs, sts = ctx.prove_fibsq_batch(log_n, traces)
+        for j in range(nb):
+            assert trs[j].tobytes() == want[j][0] and sts[j].tobytes() == want[j][1], (rep, j)
+    otr, ost, _ = orc.prove_fibsq(15, 4242)
+    for rep in range(20):
+        assert ctx.prove_fibsq(15, 4242) == (otr, ost), rep
+
+
 def test_prove_batch_sub_batching(ctx, orc):
     log_n, nb = 8, 7
     ctx.set_memory_budget(3 * 1672 * (1 << log_n) + 4096)  # forces sub-batches of <= 3 proofs

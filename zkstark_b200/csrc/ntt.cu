@@ -489,8 +489,10 @@ cudaError_t launch_interpolate(cudaStream_t s, const uint32_t* tw_fwd, const uin
     NttTables T{tw_fwd, tw_inv, hpow, wpow};
     cudaError_t e;
     const uint32_t n = 1u << log_n;
-    if (phantom && acc && log_n >= 1) {
-        // phantom value first, then a plain inverse transform (acc: one zeroed 64-bit word per proof)
+    if (phantom && acc && log_n >= 22) {
+        // phantom value first, then a plain inverse transform (acc: one zeroed 64-bit word per proof).  Pays from 2^22
+        // (57 vs 71 us; 193 vs 224 us at 2^24); below that the two small extra launches cost more than the correction pass
+        // over an L2-resident array (2^20: 35 vs 29 us).
         const uint32_t per_cta = 256 * PH_CH;
         dim3 grid((n - 1 + per_cta - 1) / per_cta, batch);
         if ((e = zk_launch(phantom_sum_kernel, grid, dim3(256), 0, s, (const uint32_t*)y, y_stride, log_n, hpow, acc)) != cudaSuccess) return e;
