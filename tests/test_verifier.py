@@ -57,3 +57,18 @@ def test_reference_checks_alone_miss_forged_challenges(orc):
             assert zk.verify_fibsq(log_n, info.a_last, bytes(forged), None, rederive=True)[0] is False
             return
     pytest.skip("no alpha below 2^32 - p in this transcript")
+
+
+def test_proof_wire_format_round_trip(orc, transcripts):
+    """state || u64 length || transcript: what bincode 1.x writes for `struct Proof`."""
+    import zkstark_b200 as zk
+    tr, st, info = orc.prove_fibsq(10, 3141592)
+    blob = zk.Proof(st, tr).to_bytes()
+    assert len(blob) == 32 + 8 + 7836 and blob[32:40] == (7836).to_bytes(8, "little")
+    back = zk.Proof.from_bytes(blob)
+    assert back.state == st and back.data == tr
+    back.verify()                                      # product verifier (host C++), replays the channel
+    with pytest.raises(zk.ZkError):
+        zk.Proof.from_bytes(blob[:-1])
+    with pytest.raises(zk.ZkError):
+        zk.Proof.from_bytes(blob[:20])

@@ -93,6 +93,23 @@ class Proof:
         if not ok:
             raise ZkError(-6, f"proof rejected: the assert at proof.rs:{line} fails")
 
+    # ---- wire format.  The reference never serialises a Proof itself (proof.rs:5-13 has no
+    # Serialize derive; `Proof::new(state, data)` takes the two parts), so the stable container is what bincode 1.x
+    # would write for the struct: the 32 raw state bytes, the u64 little-endian length of `data`, then `data` --
+    # `data` being the channel transcript, already bincode (channel.rs:19-26), which the untouched Rust
+    # `Proof::new(state, data.into_boxed_slice()).verify()` consumes as is.
+    def to_bytes(self):
+        return bytes(self.state) + len(self.data).to_bytes(8, "little") + bytes(self.data)
+
+    @staticmethod
+    def from_bytes(blob):
+        if len(blob) < 40:
+            raise ZkError(-1, "truncated proof")
+        n = int.from_bytes(blob[32:40], "little")
+        if len(blob) != 40 + n:
+            raise ZkError(-1, "proof length prefix does not match the payload")
+        return Proof(bytes(blob[:32]), bytes(blob[40:]))
+
     def size(self):  # proof.rs:151-154: size_of::<Proof>() == 48 (32-byte array + Box<[u8]> fat pointer)
         return 48 + len(self.data)
 
