@@ -71,6 +71,8 @@ constexpr Consts make_consts()
 // `V` is a bit mask choosing which groups of operations move (tuned on the GPU):
 //   1 round adds   2 schedule adds   4 Sigma1 rotations   8 Sigma0 rotations   16 sigma0/1 shifts   32 K+W adds
 //   64 latency form of the round (see ZK_SHA_ROUND): for code that runs one warp per sub-partition
+//   128 / 256: give two of the round's sums back to the ALU pipe as 3-input adds (IADD3): IMAD issues at about one warp
+//   instruction per 3.6 cycles per sub-partition, not per 2, so a kernel with 7 IMAD per round is FMA-pipe bound
 enum ShaConst { SC_ONE = 0, SC_R6, SC_R11, SC_R2, SC_R13, SC_S3, SC_S10, SC_R18, SC_R19, SC_COUNT };
 __constant__ uint32_t c_sha[16];  // one translation unit (tree.cu) owns the hashing kernels
 
@@ -138,12 +140,13 @@ __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { re
         d = dhk + s1 + cc;                                               \
         h = t2 + s1 + cc;                                                \
     } else {                                                             \
-        uint32_t hk = addv<V, 1>(h, (kw));                               \
+        /* bit 128: h + K + W as one 3-input add on the ALU pipe; bit 256: the sum that produces the new a likewise */ \
+        uint32_t hk = ((V) & 128) ? h + (kw) : addv<V, 1>(h, (kw));      \
         uint32_t dhk = addv<V, 1>(d, hk);                                \
         uint32_t y = addv<V, 1>(ch(e, f, g), bsig1<V>(e));               \
         uint32_t s0m = addv<V, 1>(bsig0<V>(a), maj(a, b, c));            \
         d = addv<V, 1>(dhk, y);                                          \
-        h = addv<V, 1>(addv<V, 1>(hk, y), s0m);                          \
+        h = ((V) & 256) ? hk + y + s0m : addv<V, 1>(addv<V, 1>(hk, y), s0m); \
     }
 
 // Round constants for the rolled loops (indexed by the loop counter: a uniform constant-bank load).
