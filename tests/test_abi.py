@@ -79,3 +79,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "orc_" not in txt, f
+
+
+def test_host_sha256_matches_hashlib():
+    """The host SHA-256 of the channel tail / verifier (SHA-NI when the CPU has it, portable otherwise) against hashlib."""
+    import ctypes
+    import hashlib
+    import random
+    import subprocess
+    sym = [l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", zk.LIB_PATH], text=True).splitlines()
+           if "host_sha256" in l]
+    assert sym, "host_sha256 not found in the library"
+    f = getattr(zk.lib(), sym[0])
+    f.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    f.restype = None
+    rnd = random.Random(7)
+    for n in list(range(0, 140)) + [255, 256, 257, 780, 1000, 4097]:
+        d = bytes(rnd.getrandbits(8) for _ in range(n))
+        out = ctypes.create_string_buffer(32)
+        f(d, n, out)
+        assert out.raw == hashlib.sha256(d).digest(), n
