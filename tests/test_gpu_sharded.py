@@ -28,7 +28,7 @@ def test_sharded_virtual_ranks_match_oracle(tctx, orc, log_n, G, lb):
     ctx, s = tctx
     with torch.cuda.stream(s):
         trace = zk.trace_fibsq(log_n, 3141592 + G)
-        prover = ShardedProver(ctx, log_n, LocalComm(G), log_block=lb)
+        prover = ShardedProver(ctx, log_n, LocalComm(G), log_block=lb, tail_len=0)   # shard every layer that can be sharded
         res = prover.prove(trace)
     res = [res] if G == 1 else res
     otr, ost, info = orc.prove_fibsq(log_n, 3141592 + G)
@@ -36,6 +36,24 @@ def test_sharded_virtual_ranks_match_oracle(tctx, orc, log_n, G, lb):
         assert hashlib.sha256(tr).hexdigest() == hashlib.sha256(otr).hexdigest()
         assert st == ost
     assert orc.verify_fibsq(log_n, info.a_last, res[0][0], True, res[0][1]) == 0
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_sharded_full_size_matches_single_gpu(tctx, G):
+    """BASELINE config 3 size (2^20 trace, 2^23-point LDE) through the sharded driver with G virtual ranks: every
+    tile / leaf-pass regime of the block subtrees, 13 sharded FRI layers, the replicated tail and the decommit gather;
+    the transcript must equal the monolithic pipeline's (itself checked against the oracle in test_gpu_parity)."""
+    import torch
+    from zkstark_b200.sharded import LocalComm, ShardedProver
+    ctx, s = tctx
+    log_n = 20
+    with torch.cuda.stream(s):
+        trace = zk.trace_fibsq(log_n, 3141592)
+        want = ctx.prove_fibsq_from_trace(log_n, trace)
+        res = ShardedProver(ctx, log_n, LocalComm(G)).prove(trace)
+    for tr, st in res:
+        assert hashlib.sha256(tr).hexdigest() == hashlib.sha256(want[0]).hexdigest()
+        assert st == want[1]
 
 
 def test_sharded_rejects_too_small(tctx):

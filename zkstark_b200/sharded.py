@@ -107,7 +107,7 @@ class _Tree:
 
 
 class ShardedProver:
-    def __init__(self, ctx, log_n, comm, log_block=10, device=None):
+    def __init__(self, ctx, log_n, comm, log_block=10, device=None, tail_len=1 << 18):
         import torch
         self.torch = torch
         self.ctx, self.k, self.comm, self.lb = ctx, log_n, comm, log_block
@@ -119,6 +119,9 @@ class ShardedProver:
             raise ValueError("world size must be 1, 2, 4 or 8 (the LDE has 8 cosets)")
         if log_block < 5 or (self.N // self.G) < (1 << (log_block + 1)):
             raise ValueError("proof too small to shard: need at least two blocks per rank")
+        # layers of at most tail_len points are gathered and finished replicated on every rank: below ~2^18 points a
+        # sharded layer costs more in launches and collectives (~110 us) than hashing it whole on one GPU
+        self.tail_len = tail_len
         self.comm_bytes = 0
         self.profile = None      # set to {} to collect per-phase wall times (synchronising: for diagnosis only)
         self._t_last = None
@@ -258,7 +261,7 @@ class ShardedProver:
 
         # Part 3: FRI.  Folds stay rank-local while a layer has >= 2 blocks per rank.
         cur, length, i = cp_local, N, 0
-        while (length // G) >= (2 << lb):
+        while (length // G) >= (2 << lb) and length > self.tail_len:
             nxt = [self._i32(length // G // 2) for _ in ranks]
             layers.append(self._commit_tree(nxt, length // 2, POST_FRI, i + 1, states, transcripts, fold_from=(cur, i)))
             i += 1
