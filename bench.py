@@ -379,7 +379,9 @@ def extras(args, ctx, zk, line, clocks, world, step_resident):
         "peak_source": "measured live: zk_bench_kernel(6) SHF/LOP3/IADD3 microbenchmark on this GPU",
         "ms_per_launch": ms_leaf, "compressions_per_s": 3 * leaves / (ms_leaf * 1e-3),
         "hbm": {"achieved": alg_bytes / (ms_leaf * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / (ms_leaf * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+                "frac": alg_bytes / (ms_leaf * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "bound": "hbm", "traffic": counts.get("dram_bytes_per_launch") if log_leaves == 23 else None,
+                "note": "the contract's HBM view of the same launch: 6 % of the copy bandwidth, i.e. NOT the bound of this kernel"},
         # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed `ncu --set full` capture
         "traffic": counts.get("dram_bytes_per_launch") if log_leaves == 23 else None,
         "share_of_step": None,
