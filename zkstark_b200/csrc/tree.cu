@@ -31,18 +31,25 @@ __device__ __forceinline__ uint32_t pow_h_m(const PowTab& t, uint32_t e)
 // ---------------------------------------------------------------- fused sources
 // FRI fold, evaluation form.  next[i] = 2^-1 * [ (u+v) + beta * x_i^-1 * (u-v) ],
 //   u = cur[i], v = cur[i+half], x_i = (5 h^i)^(2^k)  =>  x_i^-1 = 5^-(2^k) * h^(-i 2^k).
+struct FoldCoef { uint32_t cb_m, step_m; };   // beta * 5^-(2^k) and h^-(2^k), Montgomery form: per layer, not per point
+__device__ __forceinline__ FoldCoef fold_coef(const FoldArgs& f, const PowTab& pw, uint32_t beta_raw)
+{
+    const uint32_t N = 1u << pw.log_N;
+    FoldCoef k;
+    k.cb_m = mont_mul(to_mont(reduce_u32(beta_raw)), f.winv2k_m);            // field.rs:20-24
+    k.step_m = pow_h_m(pw, (N - (1u << f.layer_k)) & (N - 1));
+    return k;
+}
 template <int C>
 __device__ __forceinline__ void fold_chunk(const FoldArgs& f, const PowTab& pw, const uint32_t* cur,
-                                           uint32_t* next, uint32_t base, uint32_t beta_raw)
+                                           uint32_t* next, uint32_t base, const FoldCoef& k)
 {
     const uint32_t half = 1u << f.log_half;
     const uint32_t N = 1u << pw.log_N;
-    const uint32_t beta_m = to_mont(reduce_u32(beta_raw));                // field.rs:20-24
-    const uint32_t cb_m = mont_mul(beta_m, f.winv2k_m);                   // beta * 5^-(2^k)
-    const uint32_t step_m = pow_h_m(pw, (N - (1u << f.layer_k)) & (N - 1));  // h^-(2^k)
+    const uint32_t step_m = k.step_m;
     const uint32_t gbase = shard_global(f.shard, base);                   // chunks never straddle a shard block
     uint32_t e = (N - ((gbase << f.layer_k) & (N - 1))) & (N - 1);
-    uint32_t t_m = mont_mul(cb_m, pow_h_m(pw, e));                        // beta * x_base^-1
+    uint32_t t_m = mont_mul(k.cb_m, pow_h_m(pw, e));                      // beta * x_base^-1
     uint32_t u[C], v[C];
     if (C >= 4) {
 #pragma unroll
@@ -262,10 +269,11 @@ __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, ui
         const uint32_t* cur = a.fold.cur + (size_t)b * a.fold.cur_stride;
         uint32_t* next = a.vals + (size_t)b * a.vals_stride;
         uint32_t beta = a.fold.beta_from_state ? a.state[b].beta_raw[a.fold.layer_k] : a.fold.beta_raw;
-        if (count >= 8) { for (uint32_t o = 0; o < count; o += 8) fold_chunk<8>(a.fold, a.pow, cur, next, base + o, beta); }
-        else if (count == 4) fold_chunk<4>(a.fold, a.pow, cur, next, base, beta);
-        else if (count == 2) fold_chunk<2>(a.fold, a.pow, cur, next, base, beta);
-        else fold_chunk<1>(a.fold, a.pow, cur, next, base, beta);
+        const FoldCoef fk = fold_coef(a.fold, a.pow, beta);
+        if (count >= 8) { for (uint32_t o = 0; o < count; o += 8) fold_chunk<8>(a.fold, a.pow, cur, next, base + o, fk); }
+        else if (count == 4) fold_chunk<4>(a.fold, a.pow, cur, next, base, fk);
+        else if (count == 2) fold_chunk<2>(a.fold, a.pow, cur, next, base, fk);
+        else fold_chunk<1>(a.fold, a.pow, cur, next, base, fk);
     } else if (SRC == SRC_CP_TAB) {
         const uint32_t* f = a.cp.f + (size_t)b * a.cp.f_stride;
         uint32_t* out = a.vals + (size_t)b * a.vals_stride;
@@ -302,12 +310,39 @@ __global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_ker
     const uint32_t b = blockIdx.y;
     const uint32_t t = blockIdx.x * PASS_THREADS + threadIdx.x;
     const uint32_t n_threads = 1u << (a.in_level - a.k);
-    if (t >= n_threads) return;
     const uint32_t cnt = 1u << a.k;
     const uint32_t base = t << a.k;
     uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
 
-    if (SRC == SRC_FOLD || SRC == SRC_CP || SRC == SRC_CP_TAB) produce_values<SRC>(a, b, base, cnt);
+    if (SRC == SRC_FOLD || SRC == SRC_CP_TAB) {
+        // The CTA produces the values of all its threads cooperatively, four consecutive points per thread and trip, so
+        // the reads of the previous layer / of f and the constant tables and the writes of the new layer are coalesced
+        // 128-bit accesses (a thread walking its own 2^k points touches 32 different lines per warp instruction);
+        // the hashing below then reads the CTA's own 2^k * 256 values back from L1 / L2.
+        const uint32_t cta_base = (blockIdx.x * PASS_THREADS) << a.k;
+        const uint32_t total = 1u << a.in_level;
+        if (cnt >= 4) {
+            const uint32_t end = (PASS_THREADS << a.k) < total - cta_base ? (PASS_THREADS << a.k) : total - cta_base;
+            if (SRC == SRC_FOLD) {
+                const uint32_t* cur = a.fold.cur + (size_t)b * a.fold.cur_stride;
+                uint32_t* next = a.vals + (size_t)b * a.vals_stride;
+                const FoldCoef fk = fold_coef(a.fold, a.pow, a.fold.beta_from_state ? a.state[b].beta_raw[a.fold.layer_k] : a.fold.beta_raw);
+                for (uint32_t o = threadIdx.x * 4; o < end; o += PASS_THREADS * 4) fold_chunk<4>(a.fold, a.pow, cur, next, cta_base + o, fk);
+            } else {
+                const uint32_t* f = a.cp.f + (size_t)b * a.cp.f_stride;
+                uint32_t* out = a.vals + (size_t)b * a.vals_stride;
+                CpCoefTab kt;
+                if (a.cp.alpha_from_state) cp_coef_tab(a.state[b].alpha_raw, a.state[b].a_first, a.state[b].a_last, kt);
+                else cp_coef_tab(a.cp.alpha_raw, a.cp.a_first, a.cp.a_last, kt);
+                for (uint32_t o = threadIdx.x * 4; o < end; o += PASS_THREADS * 4) cp_chunk_tab<4>(a.cp, f, out, cta_base + o, kt);
+            }
+        } else if (t < n_threads) {
+            produce_values<SRC>(a, b, base, cnt);
+        }
+        __syncthreads();
+    }
+    if (t >= n_threads) return;
+    if (SRC == SRC_CP) produce_values<SRC>(a, b, base, cnt);
     const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
 
     uint32_t stack[MAX_PASS_K][8];
@@ -758,10 +793,10 @@ __global__ void __launch_bounds__(256) fold_kernel(const uint32_t* cur, uint32_t
     const uint32_t beta = (f.beta_from_state && st) ? st[b].beta_raw[f.layer_k] : f.beta_raw;
     if (half >= 4) {
         uint32_t base = (blockIdx.x * 256 + threadIdx.x) * 4;
-        if (base < half) fold_chunk<4>(f, pw, c, o, base, beta);
+        if (base < half) fold_chunk<4>(f, pw, c, o, base, fold_coef(f, pw, beta));
     } else {
         uint32_t base = blockIdx.x * 256 + threadIdx.x;
-        if (base < half) fold_chunk<1>(f, pw, c, o, base, beta);
+        if (base < half) fold_chunk<1>(f, pw, c, o, base, fold_coef(f, pw, beta));
     }
 }
 
