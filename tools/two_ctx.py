@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import zkstark_b200 as zk
 k = 20
-for T, B in [(1, 16), (2, 8), (2, 16), (4, 4), (3, 8)]:
+for T, B in [(1, 32), (2, 16), (4, 8), (1, 64), (2, 32)]:
     ctxs, bufs = [], []
     for t in range(T):
         s = torch.cuda.Stream()
