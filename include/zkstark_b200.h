@@ -137,6 +137,16 @@ int zk_merkle_build_dev(zk_ctx *ctx, const uint32_t *leaves, uint64_t size, uint
 int zk_prove_fibsq_resident(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t *traces_dev,
                             uint8_t *transcripts_out, uint8_t *states_out);
 
+/* ---- further query openings (the reference opens ONE position, prover.rs:263-289; soundness wants many).
+ * The arrays and heaps of the last prove call on this context are still resident: for every position xs[q] < 8n - 16
+ * of its proof `proof_index`, writes the same 4 + log_n records the prover commits for its own query
+ * (f at x, x+8, x+16 and cp at x with their paths; every FRI layer at x_i and x_i + len/2 with theirs), in the same
+ * bincode layout, zk_decommit_len(log_n) bytes per position (out: n_queries * zk_decommit_len bytes, host memory).
+ * Spliced behind the head of the transcript with the query word replaced, each opening passes the reference's own
+ * checks (proof.rs:63-148). */
+size_t zk_decommit_len(uint32_t log_n);
+int zk_open_queries(zk_ctx *ctx, uint32_t proof_index, const uint32_t *xs, uint32_t n_queries, uint8_t *out);
+
 /* ---- one proof sharded over several GPUs (BASELINE configs[4]; driver: zkstark_b200/sharded.py) ------------
  * Ownership of every evaluation array is blocked-cyclic: global index i lives on rank (i >> log_block) % n_ranks
  * at local index ((i >> log_block) / n_ranks) << log_block | (i & (2^log_block - 1)).  FRI folds (partner

@@ -294,6 +294,34 @@ def test_prove_batch_from_secrets(ctx, orc):
         assert zk.verify_fibsq(log_n, info.a_last, otr, ost) == (True, 0)
 
 
+@pytest.mark.parametrize("log_n", [5, 10, 14])
+def test_open_more_queries(ctx, orc, log_n):
+    """openings of further positions of the resident proof.  The proof's own position reproduces the
+    transcript's records byte for byte; any other position, spliced in place of the original query, passes the
+    reference's own checks (proof.rs:63-148: every Merkle path, the CP constraint, every fold step)."""
+    import struct
+    tr, st = ctx.prove_fibsq(log_n, 4242)
+    otr, ost, info = orc.prove_fibsq(log_n, 4242)
+    assert tr == otr
+    N = 8 << log_n
+    off_q = 80 + 36 * log_n
+    own = struct.unpack_from("<I", tr, off_q)[0] % (N - 16)
+    rnd = np.random.default_rng(log_n)
+    xs = [own, 0, 1, N - 17, N // 2 - 8, N // 2] + [int(v) for v in rnd.integers(0, N - 16, 10)]
+    recs = ctx.open_queries(log_n, xs)
+    assert recs[0] == tr[off_q + 4:]
+    for x, rec in zip(xs, recs):
+        spliced = tr[:off_q] + struct.pack("<I", x) + rec
+        assert len(spliced) == len(tr)
+        ok, line = zk.verify_fibsq(log_n, info.a_last, spliced, st, rederive=False)
+        assert ok, (x, line)
+    bad = bytearray(recs[3]); bad[40] ^= 1
+    ok, _ = zk.verify_fibsq(log_n, info.a_last, tr[:off_q] + struct.pack("<I", xs[3]) + bytes(bad), st, rederive=False)
+    assert not ok
+    with pytest.raises(zk.ZkError):
+        ctx.open_queries(log_n, [N - 16])
+
+
 def test_gpu_proof_passes_product_verifier(ctx, kats):
     proof = zk.generate_proof(zk.Channel.new(), ctx=ctx)
     proof.verify()  # proof.rs:15-149 with a[1022] = 2338775057 (proof.rs:70)

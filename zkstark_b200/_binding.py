@@ -83,6 +83,8 @@ def lib():
         "zk_shard_cp_dev": ([vp, vp, vp, u64, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fold_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fri_tail_dev": ([vp, u32, u32, vp, vp, vp, vp], i32),
+        "zk_decommit_len": ([u32], C.c_size_t),
+        "zk_open_queries": ([vp, u32, vp, u32, vp], i32),
         "zk_shard_fold_blocks_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp, vp], i32),
         "zk_shard_cp_blocks_dev": ([vp, vp, vp, u64, u32, u32, u32, u32, vp, vp, vp], i32),
         "zk_shard_decommit_dev": ([vp, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp], i32),
@@ -278,6 +280,15 @@ class Context:
 
     def merkle_build_dev(self, leaves_ptr, size, heap_ptr):
         self._ck(lib().zk_merkle_build_dev(self._h, C.c_void_p(leaves_ptr), size, C.c_void_p(heap_ptr)))
+
+    def open_queries(self, log_n, xs, proof_index=0):
+        """Further openings of a proof of the LAST prove call (zk_open_queries): one bytes object per position, each the
+        4 + log_n records of prover.rs:266-289 for that position."""
+        xs = np.ascontiguousarray(xs, dtype=np.uint32)
+        dl = lib().zk_decommit_len(log_n)
+        out = np.zeros(dl * len(xs), dtype=np.uint8)
+        self._ck(lib().zk_open_queries(self._h, proof_index, xs.ctypes.data_as(C.c_void_p), len(xs), out.ctypes.data_as(C.c_void_p)))
+        return [out[dl * i: dl * (i + 1)].tobytes() for i in range(len(xs))]
 
     # ---- building blocks of a proof sharded over GPUs (zkstark_b200/sharded.py)
     def shard_state_init(self, state_ptr, a_first, a_last):

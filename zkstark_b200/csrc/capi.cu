@@ -92,6 +92,7 @@ struct zk_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // prove work space
     uint32_t w_log_n = 0, w_batch = 0;
+    uint32_t last_log_n = 0, last_nb = 0;  // the sub-batch whose arrays and heaps are still resident (zk_open_queries)
     DevBuf traces, coeffs, work, f_eval, layers, f_heap, layer_heaps, states, transcripts;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -448,6 +449,8 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
     CK(cudaMemcpyAsync(pin_st, states, sizeof(ProofState) * (size_t)nb, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     ctx->launches += nl;
+    ctx->last_log_n = log_n;
+    ctx->last_nb = nb;
     if (ctx->stage_timing) {
         for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
         cudaEventElapsedTime(&ctx->stage_ms[6], ctx->ev[0], ctx->ev[6]);
@@ -907,6 +910,37 @@ int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transc
     if (log_n == 10 && secret == 3141592u && a[1022] != 2338775057u)  // prover.rs:42
         return fail(ctx, ZK_ERR_ASSERT, "a[1022] != 2338775057 (prover.rs:42)");
     return zk_prove_fibsq_from_trace(ctx, log_n, a.data(), transcript_out, cap, len_out, state_out);
+}
+
+// more query positions than the single one the reference draws.  The evaluation arrays and Merkle heaps
+// of the last prove call are still resident, so further openings are one more gather.
+size_t zk_decommit_len(uint32_t log_n) { return transcript_len(log_n) - tr_off_decommit(log_n); }
+
+int zk_open_queries(zk_ctx* ctx, uint32_t proof_index, const uint32_t* xs, uint32_t n_queries, uint8_t* out)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!xs || !out || n_queries == 0 || n_queries > 65535) return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    if (ctx->last_nb == 0 || proof_index >= ctx->last_nb) return fail(ctx, ZK_ERR_INVALID, "no resident proof with that index");
+    const uint32_t log_n = ctx->last_log_n;
+    const size_t n = (size_t)1 << log_n, N = n << LOG_BLOWUP, dl = zk_decommit_len(log_n);
+    for (uint32_t q = 0; q < n_queries; q++)
+        if (xs[q] >= N - 16) return fail(ctx, ZK_ERR_INVALID, "query position must be < 8n - 16 (prover.rs:263)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t stride = (dl + 63) & ~(size_t)63;
+    CK(ctx->s0.ensure(4 * (size_t)n_queries));
+    CK(ctx->s1.ensure(stride * n_queries));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->s0.p, xs, 4 * (size_t)n_queries, cudaMemcpyHostToDevice, s));
+    const size_t p = proof_index;
+    CK(launch_open_queries(s, log_n, (const uint32_t*)ctx->f_eval.p + p * N, (const uint8_t*)ctx->f_heap.p + p * 64 * N,
+                           (const uint32_t*)ctx->layers.p + p * 2 * N, (const uint8_t*)ctx->layer_heaps.p + p * 128 * N,
+                           (ProofState*)ctx->states.p + p, (const uint32_t*)ctx->s0.p, n_queries, (uint8_t*)ctx->s1.p, stride));
+    ctx->launches += 1;
+    std::vector<uint8_t> host(stride * n_queries);
+    CK(cudaMemcpyAsync(host.data(), ctx->s1.p, stride * n_queries, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t q = 0; q < n_queries; q++) memcpy(out + dl * q, host.data() + stride * q, dl);
+    return ZK_OK;
 }
 
 // ------------------------------------------------------------------ one proof sharded over several GPUs

@@ -845,6 +845,11 @@ struct DecommitArgs {
     const uint8_t* layer_heaps; uint64_t layer_heaps_stride;
     ProofState* state;
     uint8_t* transcript; uint64_t transcript_stride;
+    // Extra openings (zk_open_queries): when xs != null the kernel serves query positions xs[blockIdx.y] of ONE proof
+    // (the base pointers already point at it) and writes each record set to out + blockIdx.y * out_stride instead of
+    // the transcript.
+    const uint32_t* xs;
+    uint8_t* out; uint64_t out_stride;
 };
 
 // `step` levels above leaf `leaf` of a 2^log_size-leaf heap, the sibling (merkle.rs:58-66)
@@ -860,18 +865,19 @@ __device__ __forceinline__ size_t sibling_node(uint32_t log_size, uint32_t leaf,
 __global__ void __launch_bounds__(256) decommit_kernel(const DecommitArgs a)
 {
     pdl_enter();
-    const uint32_t b = blockIdx.y;                               // proof; blockIdx.x: slice of the gather items
+    const bool extra = a.xs != nullptr;                          // openings of further positions of one proof
+    const uint32_t b = extra ? 0u : blockIdx.y;                  // proof; blockIdx.x: slice of the gather items
     const uint32_t k = a.log_n, L = k, log_N = k + LOG_BLOWUP, N = 1u << log_N, B = 1u << LOG_BLOWUP;
     ProofState* ps = a.state + b;
-    uint8_t* tr = a.transcript + (size_t)b * a.transcript_stride;
+    const size_t off0 = 84 + 36 * (size_t)L;
+    uint8_t* tr = extra ? a.out + (size_t)blockIdx.y * a.out_stride - off0 : a.transcript + (size_t)b * a.transcript_stride;
     const uint32_t* f = a.f_eval + (size_t)b * a.f_stride;
     const uint8_t* fh = a.f_heap + (size_t)b * a.f_heap_stride;
     const uint32_t* lay = a.layers + (size_t)b * a.layers_stride;
     const uint8_t* lh = a.layer_heaps + (size_t)b * a.layer_heaps_stride;
-    const uint32_t x = (uint32_t)((size_t)ps->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
-    const size_t off0 = 84 + 36 * (size_t)L;
+    const uint32_t x = extra ? a.xs[blockIdx.y] : (uint32_t)((size_t)ps->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
     const size_t rec0 = 12 + 32 * (size_t)log_N;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!extra && blockIdx.x == 0 && threadIdx.x == 0) {
         // prover.rs:238: the last FRI polynomial has degree 0, i.e. its 8 evaluations are equal
         const size_t voff = layer_vals_off_dev(log_N, L);
         uint32_t bad = 0;
@@ -1446,12 +1452,24 @@ cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_ev
                             ProofState* state, uint8_t* transcript, uint64_t transcript_stride, uint32_t batch)
 {
     DecommitArgs a{log_n, f_eval, f_stride, f_heap, f_heap_stride, layers, layers_stride,
-                   layer_heaps, layer_heaps_stride, state, transcript, transcript_stride};
+                   layer_heaps, layer_heaps_stride, state, transcript, transcript_stride, nullptr, nullptr, 0};
     // 32 digests per CTA pass: enough CTAs that every sibling load of a proof is in flight at once
     const uint32_t log_N = log_n + LOG_BLOWUP, n_items = 4 * log_N + 2 * (log_n * log_N - log_n * (log_n - 1) / 2);
     uint32_t slices = (n_items + 31) / 32;
     if (batch > 16) slices = 1 + (slices - 1) / (batch / 16);        // large batches fill the machine on their own
     return zk_launch(decommit_kernel, dim3(slices, batch), dim3(256), 0, s, a);
+}
+
+// further openings of ONE proof (pointers already offset to it): n_q positions xs_dev, records to out_dev
+cudaError_t launch_open_queries(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, const uint8_t* f_heap,
+                                const uint32_t* layers, const uint8_t* layer_heaps, ProofState* state,
+                                const uint32_t* xs_dev, uint32_t n_q, uint8_t* out_dev, uint64_t out_stride)
+{
+    DecommitArgs a{log_n, f_eval, 0, f_heap, 0, layers, 0, layer_heaps, 0, state, nullptr, 0, xs_dev, out_dev, out_stride};
+    const uint32_t log_N = log_n + LOG_BLOWUP, n_items = 4 * log_N + 2 * (log_n * log_N - log_n * (log_n - 1) / 2);
+    uint32_t slices = (n_items + 31) / 32;
+    if (n_q > 16) slices = 1 + (slices - 1) / (n_q / 16);
+    return zk_launch(decommit_kernel, dim3(slices, n_q), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
