@@ -43,6 +43,9 @@ constexpr uint32_t PASS_THREADS = ZK_PASS_THREADS;
 #define ZK_PASS_MINBLOCKS 5       // 256 x 5: <= 51 registers, no spills in any source variant; 1354 -> 1333 us per 2^23 leaves (swept 32..1024 x 1..16)
 #endif
 constexpr uint32_t MAX_PASS_K = 6;
+#ifndef ZK_EPILOGUE_LEVELS
+#define ZK_EPILOGUE_LEVELS 8
+#endif
 #ifndef ZK_PASS_MAX_K
 #define ZK_PASS_MAX_K 6
 #endif
@@ -142,6 +145,7 @@ struct TreeArgs {
     uint32_t log_size;      // tree has 2^log_size leaves
     uint32_t in_level;      // level the kernel consumes (== log_size for leaf passes)
     uint32_t k;             // levels produced by one thread of a pass kernel
+    uint32_t ep_levels;     // pass kernel: further levels reduced per CTA through shared memory (0..log2 PASS_THREADS; set by the launcher)
     uint32_t log_tile;      // tile kernel: inputs per CTA (set by the launcher)
     uint32_t coop_cnt;      // tile kernel: levels of at most this many nodes use two warps per node (set by the launcher)
     ProofState* state;      // per proof (may be null for POST_NONE)

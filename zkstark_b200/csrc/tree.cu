@@ -299,6 +299,73 @@ __device__ __forceinline__ void produce_values(const TreeArgs& a, uint32_t b, ui
     }
 }
 
+// ---------------------------------------------------------------- one out-of-line SHA-256 for latency-bound code
+// The tile kernel and the channel hash a handful of messages one after the other; with every call site inlined
+// the kernel carried ~6 copies of the 17 KB compression body and each copy was fetched cold exactly once
+// (measured: ~2.7 us per copy on a 45 us kernel).  One out-of-line copy stays hot in the instruction cache.
+// Message = 16 words (one block, already padded) or 64 bytes + the constant padding block (`two_blocks`).
+struct Dig8 { uint32_t v[8]; };
+template <int V>
+__device__ __noinline__ Dig8 sha_msg(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
+                                     uint32_t w6, uint32_t w7, uint32_t w8, uint32_t w9, uint32_t w10, uint32_t w11,
+                                     uint32_t w12, uint32_t w13, uint32_t w14, uint32_t w15, uint32_t two_blocks)
+{
+    uint32_t w[16] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11, w12, w13, w14, w15};
+    Dig8 d;
+    sha::init_iv(d.v);
+    sha::compress<V>(d.v, w);
+    if (two_blocks) sha::compress_pad64<V>(d.v);
+    return d;
+}
+template <int V>
+__device__ __forceinline__ void msg_node(const uint32_t l[8], const uint32_t r[8], uint32_t out[8])   // merkle.rs:40-46
+{
+    Dig8 d = sha_msg<V>(l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7], r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], 1u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = d.v[i];
+}
+template <int V>
+__device__ __forceinline__ void msg_leaf(uint32_t v, uint32_t out[8])                                 // merkle.rs:30-34
+{
+    Dig8 d = sha_msg<V>(v, 0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 32u, 0u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = d.v[i];
+}
+
+// CTA epilogue of the pass kernel: the PASS_THREADS subtree roots of a CTA (level `level`, indices first .. first + 255)
+// are reduced `levels` more levels through shared memory, every node stored at its heap position.  The hashes of
+// these narrow levels are latency bound, but unlike in a separate kernel the other resident CTAs of the SM keep the
+// ALU pipe busy meanwhile, so the upper-tree kernel that follows starts from 2^-8 as many digests (1,024 instead of
+// 262,144 at 2^23 leaves): 80 -> ~30 us per large tree.
+template <int V>
+__device__ __forceinline__ void pass_epilogue(uint8_t* heap, uint32_t level, uint32_t first, uint32_t levels, uint32_t d[8])
+{
+    __shared__ __align__(16) uint32_t epA[8][PASS_THREADS];
+    __shared__ __align__(16) uint32_t epB[8][PASS_THREADS / 2];
+    const uint32_t t = threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < 8; w++) epA[w][t] = d[w];
+    __syncthreads();
+    uint32_t cnt = PASS_THREADS / 2, lvl = level - 1, base = first >> 1;
+    bool inA = true;
+    for (uint32_t e = 0; e < levels; e++) {
+        if (t < cnt) {
+            uint32_t l[8], r[8], o[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint2 pr = inA ? *reinterpret_cast<const uint2*>(&epA[w][2 * t]) : *reinterpret_cast<const uint2*>(&epB[w][2 * t]);
+                l[w] = pr.x; r[w] = pr.y;
+            }
+            msg_node<V>(l, r, o);                                           // merkle.rs:40-46
+            sha::store_digest(heap + 32 * ((((size_t)1 << lvl) - 1) + base + t), o);
+#pragma unroll
+            for (int w = 0; w < 8; w++) { if (inA) epB[w][t] = o[w]; else epA[w][t] = o[w]; }
+        }
+        __syncthreads();
+        inA = !inA; cnt >>= 1; lvl--; base >>= 1;
+    }
+}
+
 // ---------------------------------------------------------------- pass kernel
 // Thread t of proof b owns inputs [t*2^k, (t+1)*2^k) at heap level `in_level` and writes
 // every node of the subtree above them (levels in_level-1 .. in_level-k); for value
@@ -382,6 +449,8 @@ __global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_ker
                 for (int j = 0; j < 8; j++) stack[lvl][j] = d[j];
             }
         }
+        // d: root of this thread's 2^k-leaf subtree (heap level in_level - k, index t)
+        if (a.ep_levels) pass_epilogue<V>(heap, a.in_level - a.k, blockIdx.x * PASS_THREADS, a.ep_levels, d);
         return;
     }
     for (uint32_t i = 0; i < cnt; i++) {
@@ -405,39 +474,7 @@ __global__ void __launch_bounds__(PASS_THREADS, ZK_PASS_MINBLOCKS) tree_pass_ker
             for (int w = 0; w < 8; w++) stack[lvl][w] = d[w];
         }
     }
-}
-
-// ---------------------------------------------------------------- one out-of-line SHA-256 for latency-bound code
-// The tile kernel and the channel hash a handful of messages one after the other; with every call site inlined
-// the kernel carried ~6 copies of the 17 KB compression body and each copy was fetched cold exactly once
-// (measured: ~2.7 us per copy on a 45 us kernel).  One out-of-line copy stays hot in the instruction cache.
-// Message = 16 words (one block, already padded) or 64 bytes + the constant padding block (`two_blocks`).
-struct Dig8 { uint32_t v[8]; };
-template <int V>
-__device__ __noinline__ Dig8 sha_msg(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5,
-                                     uint32_t w6, uint32_t w7, uint32_t w8, uint32_t w9, uint32_t w10, uint32_t w11,
-                                     uint32_t w12, uint32_t w13, uint32_t w14, uint32_t w15, uint32_t two_blocks)
-{
-    uint32_t w[16] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11, w12, w13, w14, w15};
-    Dig8 d;
-    sha::init_iv(d.v);
-    sha::compress<V>(d.v, w);
-    if (two_blocks) sha::compress_pad64<V>(d.v);
-    return d;
-}
-template <int V>
-__device__ __forceinline__ void msg_node(const uint32_t l[8], const uint32_t r[8], uint32_t out[8])   // merkle.rs:40-46
-{
-    Dig8 d = sha_msg<V>(l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7], r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], 1u);
-#pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = d.v[i];
-}
-template <int V>
-__device__ __forceinline__ void msg_leaf(uint32_t v, uint32_t out[8])                                 // merkle.rs:30-34
-{
-    Dig8 d = sha_msg<V>(v, 0x80000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 32u, 0u);
-#pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = d.v[i];
+    if (a.ep_levels) pass_epilogue<V>(heap, a.in_level - a.k, blockIdx.x * PASS_THREADS, a.ep_levels, d);
 }
 
 // ---------------------------------------------------------------- device channel
@@ -1180,6 +1217,7 @@ extern uint32_t g_tile_log_override;
 extern uint32_t g_tile_shift;
 extern uint32_t g_pass_log_threads;
 extern uint32_t g_coop_cnt;
+extern uint32_t g_pass_epilogue;
 static uint32_t pass_max_k();
 template <int SRC>
 static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch)
@@ -1243,6 +1281,22 @@ static cudaError_t launch_tile_src(cudaStream_t s, int src, const TreeArgs& a, u
         default: return cudaErrorInvalidValue;
     }
 }
+// CTA epilogue levels of a pass over 2^in_level inputs with 2^k per thread, never going above heap level `floor`
+// (needs full CTAs: at least PASS_THREADS threads)
+static uint32_t pick_ep(uint32_t in_level, uint32_t k, uint32_t floor, uint32_t batch)
+{
+    uint32_t log_pt = 0;
+    while ((1u << (log_pt + 1)) <= PASS_THREADS) log_pt++;
+    if (!g_pass_epilogue || in_level < k + log_pt) return 0;
+    const uint32_t room = in_level - k - floor;
+    uint32_t ep = room < log_pt ? room : log_pt;
+    // A CTA in its epilogue holds its registers and thread slots while one warp works: with a single proof that
+    // costs more bulk throughput than the shorter upper-tree kernel wins back beyond one level (measured, 2^20:
+    // 5.111 / 5.092 / 5.100 / 5.142 / 5.258 ms at 0 / 1 / 2 / 4 / 8 levels); in a batch the other proofs' CTAs fill the
+    // gap and the deep epilogue wins (238.9 / 240.2 / 240.6 / 241.1 proofs/s at 0 / 2 / 4 / 8).
+    const uint32_t cap = batch >= 4 ? g_pass_epilogue : (g_pass_epilogue < 1 ? g_pass_epilogue : 1u);
+    return ep < cap ? ep : cap;
+}
 // digest passes until the tile kernel can take over, then the tile kernel
 static cudaError_t finish_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int* launches)
 {
@@ -1250,10 +1304,12 @@ static cudaError_t finish_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int*
     while (a.in_level > 2 * TILE_LOG) {
         uint32_t rem = a.in_level - 2 * TILE_LOG;
         a.k = rem >= 4 ? 4 : rem;
+        a.ep_levels = pick_ep(a.in_level, a.k, 0, batch);
         e = launch_pass<SRC_DIGESTS>(s, a, batch);
         (*launches)++;
         if (e != cudaSuccess) return e;
-        a.in_level -= a.k;
+        a.in_level -= a.k + a.ep_levels;
+        a.ep_levels = 0;
     }
     e = launch_tile<SRC_DIGESTS>(s, a, batch);
     (*launches)++;
@@ -1284,6 +1340,7 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
         if (k > (int)pass_max_k()) k = pass_max_k();
         if (k > (int)(a.log_size - TILE_LOG)) k = a.log_size - TILE_LOG;
         a.k = k;
+        a.ep_levels = pick_ep(a.in_level, k, 0, batch);
         switch (src) {
             case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
             case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
@@ -1292,7 +1349,8 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
         }
         launches++;
         if (e != cudaSuccess) return e;
-        a.in_level -= k;
+        a.in_level -= k + a.ep_levels;
+        a.ep_levels = 0;
         e = finish_upper(s, a, batch, &launches);
     }
     if (n_launches) *n_launches += launches;
@@ -1312,6 +1370,7 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src, TreeArgs a, uint32_t 
     if (k > 5) k = 5;
     if (k > (int)(a.log_size - stop_level)) k = a.log_size - stop_level;
     a.k = k;
+    a.ep_levels = pick_ep(a.in_level, k, stop_level, batch);
     switch (src) {
         case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
         case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
@@ -1319,16 +1378,17 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src, TreeArgs a, uint32_t 
         default: return cudaErrorInvalidValue;
     }
     launches++;
-    a.in_level -= k;
+    a.in_level -= k + a.ep_levels;
     while (e == cudaSuccess && a.in_level > stop_level) {
         uint32_t rem = a.in_level - stop_level;
         int kk = (int)a.in_level + (int)lb - 18;   // still plenty of subtrees: keep several levels per thread
         if (kk < 1) kk = 1;
         if (kk > 5) kk = 5;
         a.k = rem < (uint32_t)kk ? rem : (uint32_t)kk;
+        a.ep_levels = pick_ep(a.in_level, a.k, stop_level, batch);
         e = launch_pass<SRC_DIGESTS>(s, a, batch);
         launches++;
-        a.in_level -= a.k;
+        a.in_level -= a.k + a.ep_levels;
     }
     if (n_launches) *n_launches += launches;
     return e;
@@ -1363,6 +1423,8 @@ bool pdl_enabled()
 uint32_t g_tile_shift = ZK_TILE_SHIFT;              // the tile kernel runs 2^g_tile_shift tiles per tree
 uint32_t g_pass_log_threads = ZK_PASS_LOG_THREADS;  // the leaf pass runs ~2^g_pass_log_threads threads (summed over the batch)
 uint32_t g_coop_cnt = ZK_COOP_CNT;                  // tile kernel: widest level hashed by warp pairs
+// CTA epilogue of the pass kernel: at most this many levels (ZK_EPILOGUE_LEVELS overrides; 0 = off)
+uint32_t g_pass_epilogue = [] { const char* e = getenv("ZK_EPILOGUE_LEVELS"); return e ? (uint32_t)atoi(e) : (uint32_t)ZK_EPILOGUE_LEVELS; }();
 void set_coop_cnt(uint32_t v) { g_coop_cnt = v; }
 // bench knob: bits 0-7 direct threshold, 8-15 forced tile size (0 = adaptive), 16-23 tile shift, 24-31 leaf-pass
 // log-threads (0 = keep the default)
