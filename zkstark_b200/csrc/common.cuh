@@ -15,7 +15,7 @@ constexpr uint32_t TILE_LOG = 11;   // the tile kernel reduces up to 2^TILE_LOG 
 constexpr uint32_t TILE_PAIRS = 1u << (TILE_LOG - 1);
 constexpr uint32_t TILE_MIN_LOG = 7;
 #ifndef ZK_TILE_SHA_V
-#define ZK_TILE_SHA_V 3  // SHA-256 variant of the (latency-bound) tile kernel
+#define ZK_TILE_SHA_V 515  // SHA-256 variant of the wide (one warp per 32 nodes) levels of the tile kernel
 #endif
 #ifndef ZK_TILE_DIRECT_LOG
 #define ZK_TILE_DIRECT_LOG 17  // trees up to this many leaves (x batch) go leaves -> root in one tile-kernel launch
@@ -53,7 +53,7 @@ constexpr uint32_t MAX_PASS_K = 6;
 #define ZK_SHA_UNI 2  // 1: leaf and node hashes share one copy of the data-block compression; 2: + leaf-specialised prologue and schedule
 #endif
 #ifndef ZK_SHA_V
-#define ZK_SHA_V 3  // SHA-256 pipe-balancing variant used by the production kernels (sha256.cuh)
+#define ZK_SHA_V 515  // SHA-256 variant of the throughput-bound kernels (sha256.cuh): adds on the FMA pipe, six-add round
 #endif
 
 // Two-level table of powers of h (generator of the order-N LDE subgroup, prover.rs:49):
