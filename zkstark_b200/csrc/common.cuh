@@ -53,7 +53,7 @@ constexpr uint32_t MAX_PASS_K = 6;
 #define ZK_SHA_UNI 2  // 1: leaf and node hashes share one copy of the data-block compression; 2: + leaf-specialised prologue and schedule
 #endif
 #ifndef ZK_SHA_V
-#define ZK_SHA_V 515  // SHA-256 variant of the throughput-bound kernels (sha256.cuh): adds on the FMA pipe, six-add round
+#define ZK_SHA_V 4611  // SHA-256 variant of the throughput-bound kernels (sha256.cuh): adds on the FMA pipe, six-add round
 #endif
 
 // Two-level table of powers of h (generator of the order-N LDE subgroup, prover.rs:49):

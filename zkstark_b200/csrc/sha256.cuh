@@ -71,7 +71,7 @@ constexpr Consts make_consts()
 // `V` is a bit mask choosing which groups of operations move (tuned on the GPU):
 //   1 round adds   2 schedule adds   4 Sigma1 rotations   8 Sigma0 rotations   16 sigma0/1 shifts   32 K+W adds
 //   64 latency form of the round (see ZK_SHA_ROUND): for code that runs one warp per sub-partition
-//   512 six-add form of the round (throughput kernels)
+//   512 six-add form of the round (throughput kernels); 4096 its faster statement order
 //   128 / 256: give two of the round's sums back to the ALU pipe as 3-input adds (IADD3): IMAD issues at about one warp
 //   instruction per 3.6 cycles per sub-partition, not per 2, so a kernel with 7 IMAD per round is FMA-pipe bound
 enum ShaConst { SC_ONE = 0, SC_R6, SC_R11, SC_R2, SC_R13, SC_S3, SC_S10, SC_R18, SC_R19, SC_COUNT };
@@ -143,12 +143,23 @@ __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { re
     } else if ((V) & 512) {                                              \
         /* throughput form: six adds instead of seven (T1 is formed once and reused); the longer dependency chain  \
            is irrelevant when many warps are resident */                                                          \
-        uint32_t hk = addv<V, 1>(h, (kw));                               \
-        uint32_t y = addv<V, 1>(ch(e, f, g), bsig1<V>(e));               \
-        uint32_t t1 = addv<V, 1>(hk, y);                                 \
-        uint32_t s0m = addv<V, 1>(bsig0<V>(a), maj(a, b, c));            \
-        d = addv<V, 1>(d, t1);                                           \
-        h = addv<V, 1>(t1, s0m);                                         \
+        /* The order of the six statements matters to ptxas (2^23-leaf pass: 1306 us as first written, 1290 us with      \
+           bit 4096 = Ch + Sigma1 first and d before Sigma0 + Maj; other orders 1308 .. 1342 us; nested expressions 1331) */ \
+        if ((V) & 4096) {                                                \
+            uint32_t y = addv<V, 1>(ch(e, f, g), bsig1<V>(e));           \
+            uint32_t hk = addv<V, 1>(h, (kw));                           \
+            uint32_t t1 = addv<V, 1>(hk, y);                             \
+            d = addv<V, 1>(d, t1);                                       \
+            uint32_t s0m = addv<V, 1>(bsig0<V>(a), maj(a, b, c));        \
+            h = addv<V, 1>(t1, s0m);                                     \
+        } else {                                                         \
+            uint32_t hk = addv<V, 1>(h, (kw));                           \
+            uint32_t y = addv<V, 1>(ch(e, f, g), bsig1<V>(e));           \
+            uint32_t t1 = addv<V, 1>(hk, y);                             \
+            uint32_t s0m = addv<V, 1>(bsig0<V>(a), maj(a, b, c));        \
+            d = addv<V, 1>(d, t1);                                       \
+            h = addv<V, 1>(t1, s0m);                                     \
+        }                                                                \
     } else {                                                             \
         /* bit 128: h + K + W as one 3-input add on the ALU pipe; bit 256: the sum that produces the new a likewise */ \
         uint32_t hk = ((V) & 128) ? h + (kw) : addv<V, 1>(h, (kw));      \

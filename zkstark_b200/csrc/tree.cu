@@ -1459,7 +1459,7 @@ cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, in
         case v: tree_pass_kernel<SRC_VALUES, v, 0><<<grid, PASS_THREADS, 0, s>>>(a); break; \
         case 100 + v: tree_pass_kernel<SRC_VALUES, v, 1><<<grid, PASS_THREADS, 0, s>>>(a); break; \
         case 200 + v: tree_pass_kernel<SRC_VALUES, v, 2><<<grid, PASS_THREADS, 0, s>>>(a); break;
-        ZK_VCASE(0) ZK_VCASE(1) ZK_VCASE(2) ZK_VCASE(3) ZK_VCASE(35) ZK_VCASE(131) ZK_VCASE(259) ZK_VCASE(387) ZK_VCASE(385) ZK_VCASE(129) ZK_VCASE(515) ZK_VCASE(547)
+        ZK_VCASE(0) ZK_VCASE(1) ZK_VCASE(2) ZK_VCASE(3) ZK_VCASE(35) ZK_VCASE(131) ZK_VCASE(259) ZK_VCASE(387) ZK_VCASE(385) ZK_VCASE(129) ZK_VCASE(515) ZK_VCASE(4611)
 #endif
         default: tree_pass_kernel<SRC_VALUES><<<grid, PASS_THREADS, 0, s>>>(a); break;
     }
