@@ -124,6 +124,20 @@ __device__ __forceinline__ uint32_t ssig1(uint32_t x)
     if (V & 16) return rotr(x, 17) ^ rotr(x, 19) ^ __umulhi(x, c_sha[SC_S10]);
     return rotr(x, 17) ^ rotr(x, 19) ^ (x >> 10);
 }
+// One message-schedule update W[t] = W[t-16] + sigma0(W[t-15]) + W[t-7] + sigma1(W[t-2]); ZK_SCHED_ORDER picks the order
+// of the three adds (ptxas schedules them differently; see profiles/README).
+#ifndef ZK_SCHED_ORDER
+#define ZK_SCHED_ORDER 0
+#endif
+template <int V>
+__device__ __forceinline__ uint32_t sched_word(uint32_t w16, uint32_t w15, uint32_t w7, uint32_t w2)
+{
+    if (ZK_SCHED_ORDER == 1) return addv<V, 2>(addv<V, 2>(addv<V, 2>(w16, w7), ssig0<V>(w15)), ssig1<V>(w2));
+    if (ZK_SCHED_ORDER == 2) return addv<V, 2>(addv<V, 2>(w16, w7), addv<V, 2>(ssig0<V>(w15), ssig1<V>(w2)));
+    if (ZK_SCHED_ORDER == 3) return addv<V, 2>(addv<V, 2>(addv<V, 2>(w16, ssig0<V>(w15)), w7), ssig1<V>(w2));
+    return addv<V, 2>(addv<V, 2>(addv<V, 2>(w16, ssig1<V>(w2)), w7), ssig0<V>(w15));
+}
+
 __device__ __forceinline__ uint32_t ch(uint32_t e, uint32_t f, uint32_t g) { return (e & f) ^ (~e & g); }
 __device__ __forceinline__ uint32_t maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) ^ (a & c) ^ (b & c); }
 
@@ -217,8 +231,7 @@ __device__ __forceinline__ void compress(uint32_t st[8], uint32_t w[16])
     for (int i = 16; i < 64; i += 16) {
 #pragma unroll
         for (int j = 0; j < 16; j++)
-            w[j] = addv<V, 2>(addv<V, 2>(addv<V, 2>(w[j], ssig1<V>(w[(j + 14) & 15])), w[(j + 9) & 15]),
-                              ssig0<V>(w[(j + 1) & 15]));
+            w[j] = sched_word<V>(w[j], w[(j + 1) & 15], w[(j + 9) & 15], w[(j + 14) & 15]);
         // fetch the 16 round constants of this trip up front (4 x 128-bit constant loads): loaded one per
         // round right before use, their latency is exposed 48 times per compression when a single warp runs
         uint32_t kk[16];
@@ -338,8 +351,7 @@ __device__ __forceinline__ void compress_leaf_or_node(uint32_t st[8], uint32_t w
         if (i == 64) break;
 #pragma unroll
         for (int j = 0; j < 16; j++)
-            w[j] = addv<V, 2>(addv<V, 2>(addv<V, 2>(w[j], ssig1<V>(w[(j + 14) & 15])), w[(j + 9) & 15]),
-                              ssig0<V>(w[(j + 1) & 15]));
+            w[j] = sched_word<V>(w[j], w[(j + 1) & 15], w[(j + 9) & 15], w[(j + 14) & 15]);
     }
     st[0] = a + ZK_SHA_IV0; st[1] = b + ZK_SHA_IV1; st[2] = c + ZK_SHA_IV2; st[3] = d + ZK_SHA_IV3;
     st[4] = e + ZK_SHA_IV4; st[5] = f + ZK_SHA_IV5; st[6] = g + ZK_SHA_IV6; st[7] = h + ZK_SHA_IV7;
