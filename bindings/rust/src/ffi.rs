@@ -22,6 +22,12 @@ extern "C" {
                           len_out: *mut usize, state_out: *mut u8) -> c_int;
     pub fn zk_prove_fibsq_batch(ctx: *mut zk_ctx, log_n: u32, n_proofs: u32, traces: *const u32,
                                 transcripts_out: *mut u8, states_out: *mut u8) -> c_int;
+    pub fn zk_prove_fibsq_batch_secrets(ctx: *mut zk_ctx, log_n: u32, n_proofs: u32, secrets: *const u32,
+                                        transcripts_out: *mut u8, states_out: *mut u8) -> c_int;
+    pub fn zk_verify_fibsq(log_n: u32, a_last: u32, transcript: *const u8, len: usize, state: *const u8,
+                           rederive_challenges: c_int, failed_check: *mut c_int) -> c_int;
+    pub fn zk_decommit_len(log_n: u32) -> usize;
+    pub fn zk_open_queries(ctx: *mut zk_ctx, proof_index: u32, xs: *const u32, n_queries: u32, out: *mut u8) -> c_int;
 }
 
 /// One context per thread (zk_ctx is not thread-safe), created on first use.
