@@ -216,6 +216,21 @@ def test_prove_cp_forms_and_plain_hashing_agree(ctx, orc, log_n):
         ctx.bench_set(-1, (128 + 1) << 8)
 
 
+@pytest.mark.parametrize("log_n", [18, 22, 24])
+def test_prove_large_sizes_match_golden_digests(ctx, log_n):
+    """BASELINE configs up to the 2^24 trace (2^27-point LDE, 28 GB of work space): transcript and final channel state
+    against tests/golden/large_digests.json (made by tests/golden/make_large_digests.py from the oracle; 2^24 takes the
+    oracle 35 s, too slow to redo per run)."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "large_digests.json")))[str(log_n)]
+    tr, st = ctx.prove_fibsq(log_n, 3141592)
+    assert len(tr) == g["len"] == zk.transcript_len(log_n)
+    assert hashlib.sha256(tr).hexdigest() == g["sha256"]
+    assert st.hex() == g["state"]
+    ok, line = zk.verify_fibsq(log_n, g["a_last"], tr, st)
+    assert ok, line
+
+
 def test_prove_batch(ctx, orc):
     """BASELINE config 4 in miniature: independent proofs, secret_j = 3141592 + j."""
     log_n, nb = 10, 5
