@@ -40,7 +40,8 @@ typedef enum zk_status {
     ZK_ERR_NOMEM = -3,   /* device or host allocation failed */
     ZK_ERR_BUFFER = -4,  /* caller buffer too small */
     ZK_ERR_ASSERT = -5,  /* an inline assert of the reference failed (e.g. prover.rs:42) */
-    ZK_ERR_VERIFY = -6   /* zk_verify_fibsq: the proof was rejected */
+    ZK_ERR_VERIFY = -6,  /* zk_verify_fibsq: the proof was rejected */
+    ZK_ERR_COMM = -7     /* NCCL is unavailable or a collective failed (sharded proofs only) */
 } zk_status;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -141,11 +142,13 @@ int zk_prove_fibsq_resident(zk_ctx *ctx, uint32_t log_n, uint32_t n_proofs, cons
  * The arrays and heaps of the last prove call on this context are still resident: for every position xs[q] < 8n - 16
  * of its proof `proof_index`, writes the same 4 + log_n records the prover commits for its own query
  * (f at x, x+8, x+16 and cp at x with their paths; every FRI layer at x_i and x_i + len/2 with theirs), in the same
- * bincode layout, zk_decommit_len(log_n) bytes per position (out: n_queries * zk_decommit_len bytes, host memory).
+ * bincode layout, zk_decommit_len(log_n) bytes per position (out: n_queries * zk_decommit_len bytes, host memory;
+ * log_n must be the resident proof's size and out_cap the capacity of `out`: ZK_ERR_INVALID / ZK_ERR_BUFFER otherwise).
  * Spliced behind the head of the transcript with the query word replaced, each opening passes the reference's own
  * checks (proof.rs:63-148). */
 size_t zk_decommit_len(uint32_t log_n);
-int zk_open_queries(zk_ctx *ctx, uint32_t proof_index, const uint32_t *xs, uint32_t n_queries, uint8_t *out);
+int zk_open_queries(zk_ctx *ctx, uint32_t log_n, uint32_t proof_index, const uint32_t *xs, uint32_t n_queries, uint8_t *out,
+                    size_t out_cap);
 
 /* ---- one proof sharded over several GPUs (BASELINE configs[4]; driver: zkstark_b200/sharded.py) ------------
  * Ownership of every evaluation array is blocked-cyclic: global index i lives on rank (i >> log_block) % n_ranks
@@ -195,6 +198,38 @@ int zk_shard_fri_tail_dev(zk_ctx *ctx, uint32_t log_n, uint32_t first_layer, uin
 int zk_shard_decommit_dev(zk_ctx *ctx, uint32_t log_n, uint32_t n_ranks, uint32_t rank, uint32_t log_block,
                           uint32_t first_tail, const void *const *tree_ptrs, const uint32_t *tail_vals,
                           const uint8_t *tail_heaps, const void *state_dev, uint8_t *transcript_dev);
+
+/* ---- the sharded prover as ONE call (csrc/sharded.cu): the host side of the scheme above -- ownership, the all-to-all,
+ * the root all-gathers, the halo ring, the replicated tail, the decommitment all-reduce and the channel tail -- in C++
+ * over NCCL, everything enqueued on the ctx stream with one synchronisation at the end.  One process per GPU:
+ *   rank 0: zk_shard_unique_id(id), hand `id` to the other processes by any means (file, socket, MPI, torch.distributed)
+ *   every rank: zk_shard_comm_init(ctx, id, n_ranks, rank, &comm)            -- ncclCommInitRank; collective
+ *   every rank: zk_prove_fibsq_sharded(comm, log_n, trace, ...)              -- collective; every rank gets the proof
+ * NCCL is bound at run time (libnccl.so.2; ZK_NCCL_LIB overrides the path): single-GPU users do not need it.
+ * zk_shard_comm_init_local runs G VIRTUAL ranks on the context's own device (collectives become device copies): the
+ * same driver and kernels on one GPU, used by the single-GPU test tier.  n_ranks: 1, 2, 4 or 8 (the LDE has 8 cosets).
+ * A comm borrows its ctx: destroy the comm first.  Generalises generate_proof (prover.rs:9) like zk_prove_fibsq. */
+#define ZK_SHARD_ID_BYTES 128
+typedef struct zk_shard_comm zk_shard_comm;
+int zk_shard_unique_id(uint8_t id_out[ZK_SHARD_ID_BYTES]);
+int zk_shard_comm_init(zk_ctx *ctx, const uint8_t id[ZK_SHARD_ID_BYTES], uint32_t n_ranks, uint32_t rank, zk_shard_comm **out);
+int zk_shard_comm_init_local(zk_ctx *ctx, uint32_t n_virtual_ranks, zk_shard_comm **out);
+void zk_shard_comm_destroy(zk_shard_comm *comm);
+/* tuning: log_block (0 keeps it; default 10), log2 of the largest layer that finishes in the replicated tail
+ * (0xffffffff keeps it; default 18; 0 shards every layer that can be sharded) */
+int zk_shard_comm_set(zk_shard_comm *comm, uint32_t log_block, uint32_t log_tail_len);
+/* trace: HOST memory, 2^log_n - 1 values, identical on every rank (each rank uploads only its 1/n_ranks slice).
+ * transcript_out / state_out: as zk_prove_fibsq, on every rank. */
+int zk_prove_fibsq_sharded(zk_shard_comm *comm, uint32_t log_n, const uint32_t *trace, uint8_t *transcript_out, size_t cap,
+                           size_t *len_out, uint8_t state_out[32]);
+/* device time of the last sharded proof by phase, ms: [0] upload + trace all-gather + interpolation, [1] this rank's LDE
+ * cosets, [2] all-to-all, [3] unpack, [4] f tree, [5] halo ring, [6] cp + tree, [7] sharded FRI layers, [8] gather +
+ * replicated FRI tail, [9] decommit + all-reduce, [10] download, [11] total */
+int zk_shard_last_phase_ms(const zk_shard_comm *comm, float out_ms[12]);
+/* bytes this rank received from other ranks during the last sharded proof */
+uint64_t zk_shard_last_comm_bytes(const zk_shard_comm *comm);
+/* index of the first FRI layer that ran in the replicated tail */
+uint32_t zk_shard_last_first_tail(const zk_shard_comm *comm);
 
 /* ---- measurement support (bench.py): runs ONE hot-path kernel (or kernel group) `iters` times on
  * the ctx stream, each launch bracketed by CUDA events (optionally after an L2 flush that is not

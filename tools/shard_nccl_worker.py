@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""One real rank of the native sharded prover (zk_prove_fibsq_sharded over NCCL), one process per GPU.
+Launched N times by tests/test_gpu_sharded_native.py; the ncclUniqueId travels through a file (no torch.distributed).
+
+  python tools/shard_nccl_worker.py --rank R --world N --log-n K --id-file PATH --out PATH.json
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rank", type=int, required=True)
+    ap.add_argument("--world", type=int, required=True)
+    ap.add_argument("--log-n", type=int, default=18)
+    ap.add_argument("--id-file", required=True)
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--reps", type=int, default=2)
+    a = ap.parse_args()
+    import zkstark_b200 as zk
+    ctx = zk.Context(a.rank)
+    if a.rank == 0:
+        uid = zk.shard_unique_id()
+        tmp = a.id_file + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(uid)
+        os.replace(tmp, a.id_file)
+    else:
+        t0 = time.time()
+        while not os.path.exists(a.id_file):
+            if time.time() - t0 > 120:
+                raise SystemExit("no unique id from rank 0")
+            time.sleep(0.05)
+        uid = open(a.id_file, "rb").read()
+    comm = zk.ShardComm(ctx, a.world, a.rank, uid)
+    trace = zk.trace_fibsq(a.log_n, 3141592)
+    for _ in range(a.reps):
+        tr, st = comm.prove(a.log_n, trace)
+    out = {"rank": a.rank, "transcript_sha256": hashlib.sha256(tr).hexdigest(), "state": st.hex(),
+           "phase_ms": comm.last_phase_ms(), "comm_bytes": comm.last_comm_bytes(), "first_tail": comm.last_first_tail()}
+    with open(a.out, "w") as f:
+        json.dump(out, f)
+    comm.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,8 @@ but creating a `Context` without a CUDA device raises.
 from ._binding import (  # noqa: F401
     LIB_PATH,
     Context,
+    ShardComm,
+    shard_unique_id,
     ZkError,
     build_library,
     exported_symbols,

@@ -84,10 +84,19 @@ def lib():
         "zk_shard_fold_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp], i32),
         "zk_shard_fri_tail_dev": ([vp, u32, u32, vp, vp, vp, vp], i32),
         "zk_decommit_len": ([u32], C.c_size_t),
-        "zk_open_queries": ([vp, u32, vp, u32, vp], i32),
+        "zk_open_queries": ([vp, u32, u32, vp, u32, vp, sz], i32),
         "zk_shard_fold_blocks_dev": ([vp, vp, u64, u32, u32, u32, u32, u32, vp, vp, vp], i32),
         "zk_shard_cp_blocks_dev": ([vp, vp, vp, u64, u32, u32, u32, u32, vp, vp, vp], i32),
         "zk_shard_decommit_dev": ([vp, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp], i32),
+        "zk_shard_unique_id": ([vp], i32),
+        "zk_shard_comm_init": ([vp, vp, u32, u32, C.POINTER(vp)], i32),
+        "zk_shard_comm_init_local": ([vp, u32, C.POINTER(vp)], i32),
+        "zk_shard_comm_destroy": ([vp], None),
+        "zk_shard_comm_set": ([vp, u32, u32], i32),
+        "zk_prove_fibsq_sharded": ([vp, u32, vp, vp, sz, C.POINTER(sz), vp], i32),
+        "zk_shard_last_phase_ms": ([vp, vp], i32),
+        "zk_shard_last_comm_bytes": ([vp], u64),
+        "zk_shard_last_first_tail": ([vp], u32),
         "zk_bench_set": ([vp, i32, u32], i32),
         "zk_bench_set_tile_direct_log": ([vp, u32], i32),
     }
@@ -150,6 +159,83 @@ def merkle_trace_host(heap, index):
     if n < 0:
         raise ZkError(n, "zk_merkle_trace")
     return out[:n].copy()
+
+
+SHARD_ID_BYTES = 128
+SHARD_PHASES = ["upload+gather+interpolate", "lde_cosets", "all_to_all", "unpack", "f_tree", "halo", "cp_tree", "fri_sharded",
+                "fri_tail", "decommit+allreduce", "download", "total"]
+
+
+def shard_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls this and hands the 128 bytes to the other ranks)."""
+    buf = (C.c_uint8 * SHARD_ID_BYTES)()
+    rc = lib().zk_shard_unique_id(buf)
+    if rc:
+        raise ZkError(rc, "zk_shard_unique_id: NCCL (libnccl.so.2) is not available")
+    return bytes(buf)
+
+
+class ShardComm:
+    """zk_shard_comm: the group of ranks that prove ONE FibonacciSq trace together (BASELINE configs[4]).
+    ShardComm(ctx, n_ranks, rank, unique_id) -- one process per GPU over NCCL;
+    ShardComm.local(ctx, n_virtual_ranks)    -- the same driver with G virtual ranks on the context's device."""
+
+    def __init__(self, ctx, n_ranks, rank, unique_id):
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        idb = (C.c_uint8 * SHARD_ID_BYTES)(*unique_id)
+        ctx._ck(lib().zk_shard_comm_init(ctx._h, idb, n_ranks, rank, C.byref(self._h)))
+        self.n_ranks, self.rank = n_ranks, rank
+
+    @classmethod
+    def local(cls, ctx, n_virtual_ranks):
+        self = cls.__new__(cls)
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        ctx._ck(lib().zk_shard_comm_init_local(ctx._h, n_virtual_ranks, C.byref(self._h)))
+        self.n_ranks, self.rank = n_virtual_ranks, 0
+        return self
+
+    def close(self):
+        if self._h:
+            lib().zk_shard_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, log_block=0, log_tail_len=0xFFFFFFFF):
+        self._ctx._ck(lib().zk_shard_comm_set(self._h, log_block, log_tail_len))
+
+    def prove_ptr(self, log_n, trace_host_ptr, transcript_ptr, cap, state_ptr):
+        n = C.c_size_t(0)
+        self._ctx._ck(lib().zk_prove_fibsq_sharded(self._h, log_n, C.c_void_p(trace_host_ptr), C.c_void_p(transcript_ptr), cap,
+                                                   C.byref(n), C.c_void_p(state_ptr)))
+        return n.value
+
+    def prove(self, log_n, trace):
+        """trace: 2^log_n - 1 host values, identical on every rank -> (transcript bytes, state bytes)."""
+        trace = _u32(trace)
+        assert len(trace) == (1 << log_n) - 1
+        cap = transcript_len(log_n)
+        tr = np.empty(cap, dtype=np.uint8)
+        st = np.empty(32, dtype=np.uint8)
+        n = self.prove_ptr(log_n, trace.ctypes.data, tr.ctypes.data, cap, st.ctypes.data)
+        return tr[:n].tobytes(), st.tobytes()
+
+    def last_phase_ms(self):
+        arr = (C.c_float * 12)()
+        self._ctx._ck(lib().zk_shard_last_phase_ms(self._h, arr))
+        return dict(zip(SHARD_PHASES, [float(x) for x in arr]))
+
+    def last_comm_bytes(self):
+        return int(lib().zk_shard_last_comm_bytes(self._h))
+
+    def last_first_tail(self):
+        return int(lib().zk_shard_last_first_tail(self._h))
 
 
 class Context:
@@ -287,7 +373,8 @@ class Context:
         xs = np.ascontiguousarray(xs, dtype=np.uint32)
         dl = lib().zk_decommit_len(log_n)
         out = np.zeros(dl * len(xs), dtype=np.uint8)
-        self._ck(lib().zk_open_queries(self._h, proof_index, xs.ctypes.data_as(C.c_void_p), len(xs), out.ctypes.data_as(C.c_void_p)))
+        self._ck(lib().zk_open_queries(self._h, log_n, proof_index, xs.ctypes.data_as(C.c_void_p), len(xs),
+                                       out.ctypes.data_as(C.c_void_p), out.nbytes))
         return [out[dl * i: dl * (i + 1)].tobytes() for i in range(len(xs))]
 
     # ---- building blocks of a proof sharded over GPUs (zkstark_b200/sharded.py)

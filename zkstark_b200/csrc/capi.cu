@@ -10,99 +10,14 @@
 #include <string>
 #include <vector>
 
-#include "../../include/zkstark_b200.h"
-#include "common.cuh"
+#include "ctx.hpp"
 #include "sha256.cuh"
 
-namespace zk {
-cudaError_t launch_interpolate(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow,
-                               PowTab wpow, uint32_t log_n, bool phantom, uint32_t* y, uint64_t y_stride,
-                               uint32_t* coeffs, uint64_t coeffs_stride, uint32_t batch, int* n_launches,
-                               unsigned long long* acc);
-cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
-                       uint32_t log_n, const uint32_t* coeffs, uint64_t coeffs_stride, uint32_t* work,
-                       uint64_t work_stride, uint32_t* evals, uint64_t evals_stride, uint32_t batch,
-                       int* n_launches);
-cudaError_t launch_lde_one_coset(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
-                                 uint32_t log_n, uint32_t r, const uint32_t* coeffs, uint32_t* work, uint32_t* out,
-                                 int* n_launches);
-cudaError_t launch_trace_batch(cudaStream_t s, const uint32_t* secrets_dev, uint32_t* traces, uint64_t stride,
-                               uint32_t log_n, uint32_t batch);
-cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
-cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
-double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
-}  // namespace zk
 
 using namespace zk;
+using namespace zkh;
 
-namespace {
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    cudaError_t ensure(size_t need)
-    {
-        if (need <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&p, need);
-        if (e == cudaSuccess) bytes = need;
-        return e;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-
-struct PowTabOwned {
-    uint32_t* lo = nullptr;
-    uint32_t* hi = nullptr;
-    PowTab tab{};
-};
-
-struct SizeTables {
-    PowTabOwned h;  // powers of h = 5^((p-1)/N)
-    PowTabOwned w;  // powers of 5
-    DevBuf cp_tab;  // CpArgs::tab of the size log_N - 3 (built on first use by the prove pipeline)
-};
-
-}  // namespace
-
-struct zk_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    std::string err;
-    uint64_t launches = 0;
-    uint32_t* tw_fwd = nullptr;
-    uint32_t* tw_inv = nullptr;
-    std::map<uint32_t, SizeTables> tabs;  // by log_N
-    DevBuf s0, s1, s2;                    // scratch for the host-buffer stage calls
-    DevBuf flushbuf;
-    DevBuf counters;                      // tile-arrival counters of the tree kernels (one per proof of a batch)
-    int bench_variant = -1;
-    uint32_t bench_k = 0;
-    bool use_cp_tab = true;               // composition polynomial from per-size constant tables (bench knob)
-    bool lanes = true;                    // batches run as two lanes on two streams (bench knob)
-    cudaStream_t lane_stream = nullptr;   // side stream of the second lane
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // prove work space
-    uint32_t w_log_n = 0, w_batch = 0;
-    uint32_t last_log_n = 0, last_nb = 0;  // the sub-batch whose arrays and heaps are still resident (zk_open_queries)
-    DevBuf traces, coeffs, work, f_eval, layers, f_heap, layer_heaps, states, transcripts;
-    void* pinned = nullptr;
-    size_t pinned_bytes = 0;
-    size_t mem_budget = 0;
-    bool stage_timing = false;
-    float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-};
-
-namespace {
+namespace zkh {
 
 int fail(zk_ctx* c, int code, const std::string& msg)
 {
@@ -115,12 +30,12 @@ int fail_cuda(zk_ctx* c, cudaError_t e, const char* what)
     return fail(c, e == cudaErrorMemoryAllocation ? ZK_ERR_NOMEM : ZK_ERR_CUDA,
                 std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define CK(call)                                                     \
-    do {                                                             \
-        cudaError_t e__ = (call);                                    \
-        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);   \
-    } while (0)
-
+void free_powtab(PowTabOwned& t)
+{
+    if (t.lo) cudaFree(t.lo);
+    if (t.hi) cudaFree(t.hi);
+    t = PowTabOwned{};
+}
 cudaError_t build_powtab(PowTabOwned& t, uint32_t base, uint32_t log_E /* exponents < 2^log_E */, uint32_t log_N_tag)
 {
     uint32_t lo_bits = (log_E + 1) / 2, hi_bits = log_E - lo_bits;
@@ -131,26 +46,23 @@ cudaError_t build_powtab(PowTabOwned& t, uint32_t base, uint32_t log_E /* expone
     c = 1;
     for (size_t i = 0; i < hi.size(); i++) { hi[i] = h_to_mont(c); c = h_mul(c, step); }
     cudaError_t e;
-    if ((e = cudaMalloc(&t.lo, lo.size() * 4)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&t.hi, hi.size() * 4)) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t.lo, lo.size() * 4)) != cudaSuccess) { t.lo = nullptr; return e; }
+    if ((e = cudaMalloc(&t.hi, hi.size() * 4)) != cudaSuccess) { t.hi = nullptr; free_powtab(t); return e; }
+    if ((e = cudaMemcpy(t.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(t.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        free_powtab(t);
+        return e;
+    }
     t.tab.lo = t.lo;
     t.tab.hi = t.hi;
     t.tab.lo_bits = lo_bits;
     t.tab.log_N = log_N_tag;
     return cudaSuccess;
 }
-void free_powtab(PowTabOwned& t)
-{
-    if (t.lo) cudaFree(t.lo);
-    if (t.hi) cudaFree(t.hi);
-    t = PowTabOwned{};
-}
 
 unsigned long long* phantom_acc(zk_ctx* ctx)
 {
-    return (unsigned long long*)((char*)ctx->counters.p + 4 * 256 /* MAX_BATCH */);
+    return (unsigned long long*)((char*)ctx->counters.p + 4 * MAX_BATCH);
 }
 
 int get_tables(zk_ctx* ctx, uint32_t log_N, SizeTables** out)
@@ -159,7 +71,8 @@ int get_tables(zk_ctx* ctx, uint32_t log_N, SizeTables** out)
     if (it == ctx->tabs.end()) {
         SizeTables st;
         CK(build_powtab(st.h, h_root(log_N), log_N, log_N));
-        CK(build_powtab(st.w, GEN, log_N, log_N));
+        cudaError_t ew = build_powtab(st.w, GEN, log_N, log_N);
+        if (ew != cudaSuccess) { free_powtab(st.h); return fail_cuda(ctx, ew, "build_powtab"); }
         it = ctx->tabs.emplace(log_N, st).first;
     }
     *out = &it->second;
@@ -187,10 +100,8 @@ int init_tw(zk_ctx* ctx)
     return ZK_OK;
 }
 
-constexpr uint32_t MAX_BATCH = 256;  // proofs per sub-batch (one tile counter each)
-
 bool is_pow2(uint64_t v) { return v && !(v & (v - 1)); }
-uint32_t ilog2(uint64_t v)
+uint32_t ilog2_u64(uint64_t v)
 {
     uint32_t l = 0;
     while (((uint64_t)1 << (l + 1)) <= v) l++;
@@ -217,6 +128,7 @@ CpArgs make_cp_args(uint32_t log_n)
     c.g1 = h_pow(g, n - 1);
     c.g2 = h_pow(g, n - 2);
     c.g3 = h_pow(g, n - 3);
+    c.halo_mask = 0xffffffffu;   // halo rows in local block order unless a caller rolls them (csrc/sharded.cu)
     const uint32_t wn = h_pow(GEN, n), hn = h_pow(h, n);
     uint32_t xn = wn;
     for (int i = 0; i < 8; i++) {
@@ -270,6 +182,7 @@ int ensure_workspace(zk_ctx* ctx, uint32_t log_n, uint32_t batch)
 {
     const size_t n = (size_t)1 << log_n, N = n << LOG_BLOWUP;
     const size_t trs = (transcript_len(log_n) + 63) & ~(size_t)63;
+    ctx->last_nb = 0;   // buffers may move: the previous proof is no longer addressable by zk_open_queries
     CK(ctx->traces.ensure(4 * n * batch));
     CK(ctx->coeffs.ensure(4 * n * batch));
     CK(ctx->work.ensure(4 * N * batch));
@@ -340,6 +253,7 @@ int enqueue_prove(zk_ctx* ctx, cudaStream_t s, uint32_t log_n, uint32_t p0, uint
     CK(launch_lde(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, coeffs, n, work, N, f_eval, N, nb, &nl));
     if (tm) tm->mark();
     TreeArgs a{};
+    a.tune = &ctx->tune;
     a.counters = (uint32_t*)ctx->counters.p + p0;
     a.state = states;
     a.transcript = trd;
@@ -400,8 +314,8 @@ int enqueue_prove(zk_ctx* ctx, cudaStream_t s, uint32_t log_n, uint32_t p0, uint
 // machine (measured with two contexts: +2.4 % proofs/s at 16 proofs per step).
 // host_rows (optional): nb rows of n-1 trace values in (pinned) host memory, uploaded here -- the second lane's rows on
 // its own stream, so that their copy overlaps the first lane's kernels.
-int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcripts_out, uint8_t* states_out,
-                   const uint32_t* host_rows = nullptr)
+static int prove_subbatch_body(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcripts_out, uint8_t* states_out,
+                               const uint32_t* host_rows)
 {
     const uint32_t log_N = log_n + LOG_BLOWUP;
     const size_t n_row = (size_t)1 << log_n;
@@ -473,6 +387,26 @@ int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcript
     return ZK_OK;
 }
 
+int prove_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t* transcripts_out, uint8_t* states_out,
+                   const uint32_t* host_rows = nullptr)
+{
+    ctx->last_nb = 0;   // nothing is resident for zk_open_queries until this sub-batch has completed
+    const int rc = prove_subbatch_body(ctx, log_n, nb, transcripts_out, states_out, host_rows);
+    if (rc != ZK_OK) {
+        // A failed launch may leave the second lane forked and the per-proof tile-arrival counters / phantom accumulators
+        // non-zero (only a kernel that completes re-arms them): drain both streams and zero them, so that the next
+        // prove on this context starts clean.  Best effort: the original error is what the caller sees.
+        const std::string keep = ctx->err;
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->lane_stream) cudaStreamSynchronize(ctx->lane_stream);
+        cudaMemset(ctx->counters.p, 0, 12 * MAX_BATCH);
+        cudaGetLastError();
+        ctx->err = keep;
+        ctx->last_nb = 0;
+    }
+    return rc;
+}
+
 uint32_t pick_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs)
 {
     // fast path: the work space already fits this request (cudaMemGetInfo costs ~1 ms)
@@ -500,7 +434,7 @@ int check_log_n(zk_ctx* ctx, uint32_t log_n)
     return ZK_OK;
 }
 
-}  // namespace
+}  // namespace zkh
 
 // =============================================================================== C ABI
 extern "C" {
@@ -550,6 +484,7 @@ void zk_ctx_destroy(zk_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->tabs) { free_powtab(kv.second.h); free_powtab(kv.second.w); kv.second.cp_tab.release(); }
+    for (auto& kv : ctx->shift_tabs) free_powtab(kv.second);
     DevBuf* bufs[] = {&ctx->counters, &ctx->flushbuf, &ctx->s0, &ctx->s1, &ctx->s2, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval,
                       &ctx->layers, &ctx->f_heap, &ctx->layer_heaps, &ctx->states, &ctx->transcripts};
     for (DevBuf* b : bufs) b->release();
@@ -622,19 +557,22 @@ int zk_lde_coset_dev(zk_ctx* ctx, const uint32_t* coeffs, uint32_t log_n, uint32
     if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
     CK(ctx->s2.ensure(4 * N));
     PowTab wtab = T->w.tab;
-    PowTabOwned tmp;
     shift %= P;
+    if (shift == 0) return fail(ctx, ZK_ERR_INVALID, "shift must be non-zero mod p");
     if (shift != GEN) {
-        CK(build_powtab(tmp, shift, log_n, log_n + LOG_BLOWUP));
-        wtab = tmp.tab;
+        // powers of another coset shift: built once per (shift, size) and kept with the context (no stream synchronisation)
+        const uint64_t key = ((uint64_t)shift << 8) | (log_n + LOG_BLOWUP);
+        auto it = ctx->shift_tabs.find(key);
+        if (it == ctx->shift_tabs.end()) {
+            PowTabOwned tmp;
+            CK(build_powtab(tmp, shift, log_n, log_n + LOG_BLOWUP));
+            it = ctx->shift_tabs.emplace(key, tmp).first;
+        }
+        wtab = it->second.tab;
     }
     int nl = 0;
     cudaError_t e = launch_lde(ctx->stream, ctx->tw_fwd, ctx->tw_inv, T->h.tab, wtab, log_n, coeffs, 0,
                                (uint32_t*)ctx->s2.p, N, evals_out, N, 1, &nl);
-    if (shift != GEN) {
-        cudaStreamSynchronize(ctx->stream);
-        free_powtab(tmp);
-    }
     if (e != cudaSuccess) return fail_cuda(ctx, e, "launch_lde");
     ctx->launches += nl;
     return ZK_OK;
@@ -644,7 +582,7 @@ int zk_fri_fold_dev(zk_ctx* ctx, const uint32_t* cur, uint64_t len, uint32_t lay
 {
     if (!ctx) return ZK_ERR_INVALID;
     if (!cur || !next_out || !is_pow2(len) || len < 2) return fail(ctx, ZK_ERR_INVALID, "len must be a power of two >= 2");
-    const uint32_t log_len = ilog2(len);
+    const uint32_t log_len = ilog2_u64(len);
     if (log_len + layer_k > 30) return fail(ctx, ZK_ERR_INVALID, "len << layer_k exceeds 2^30");
     CK(cudaSetDevice(ctx->device));
     SizeTables* T;
@@ -689,10 +627,11 @@ int zk_merkle_build_dev(zk_ctx* ctx, const uint32_t* leaves, uint64_t size, uint
     if (!is_pow2(size) || size > ((uint64_t)1 << 30)) return fail(ctx, ZK_ERR_INVALID, "size must be a power of two (merkle.rs:17-21)");
     CK(cudaSetDevice(ctx->device));
     TreeArgs a{};
+    a.tune = &ctx->tune;
     a.counters = (uint32_t*)ctx->counters.p;
     a.vals = const_cast<uint32_t*>(leaves);
     a.heap = heap_out;
-    a.log_size = ilog2(size);
+    a.log_size = ilog2_u64(size);
     a.post = POST_NONE;
     int nl = 0;
     CK(launch_merkle_tree(ctx->stream, SRC_VALUES, a, 1, &nl));
@@ -916,13 +855,15 @@ int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transc
 // of the last prove call are still resident, so further openings are one more gather.
 size_t zk_decommit_len(uint32_t log_n) { return transcript_len(log_n) - tr_off_decommit(log_n); }
 
-int zk_open_queries(zk_ctx* ctx, uint32_t proof_index, const uint32_t* xs, uint32_t n_queries, uint8_t* out)
+int zk_open_queries(zk_ctx* ctx, uint32_t log_n, uint32_t proof_index, const uint32_t* xs, uint32_t n_queries, uint8_t* out,
+                    size_t out_cap)
 {
     if (!ctx) return ZK_ERR_INVALID;
     if (!xs || !out || n_queries == 0 || n_queries > 65535) return fail(ctx, ZK_ERR_INVALID, "bad argument");
     if (ctx->last_nb == 0 || proof_index >= ctx->last_nb) return fail(ctx, ZK_ERR_INVALID, "no resident proof with that index");
-    const uint32_t log_n = ctx->last_log_n;
+    if (log_n != ctx->last_log_n) return fail(ctx, ZK_ERR_INVALID, "log_n differs from the resident proof's");
     const size_t n = (size_t)1 << log_n, N = n << LOG_BLOWUP, dl = zk_decommit_len(log_n);
+    if (out_cap < dl * (size_t)n_queries) return fail(ctx, ZK_ERR_BUFFER, "out buffer smaller than n_queries * zk_decommit_len(log_n)");
     for (uint32_t q = 0; q < n_queries; q++)
         if (xs[q] >= N - 16) return fail(ctx, ZK_ERR_INVALID, "query position must be < 8n - 16 (prover.rs:263)");
     CK(cudaSetDevice(ctx->device));
@@ -963,7 +904,7 @@ int zk_shard_lde_coset_dev(zk_ctx* ctx, const uint32_t* coeffs, uint32_t log_n, 
     SizeTables* T;
     if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
     int nl = 0;
-    CK(launch_lde_one_coset(ctx->stream, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, coset, coeffs, work, out, &nl));
+    CK(launch_lde_one_coset(ctx->stream, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, coset, coeffs, work, out, &nl, nullptr));
     ctx->launches += nl;
     return ZK_OK;
 }
@@ -972,10 +913,11 @@ int zk_shard_merkle_blocks_dev(zk_ctx* ctx, const uint32_t* vals_local, uint64_t
 {
     if (!ctx) return ZK_ERR_INVALID;
     if (!vals_local || !heap_local || !is_pow2(local_len)) return fail(ctx, ZK_ERR_INVALID, "local_len must be a power of two");
-    const uint32_t lg = ilog2(local_len);
+    const uint32_t lg = ilog2_u64(local_len);
     if (lg < log_block || log_block < 1) return fail(ctx, ZK_ERR_INVALID, "local_len smaller than a block");
     CK(cudaSetDevice(ctx->device));
     TreeArgs a{};
+    a.tune = &ctx->tune;
     a.counters = (uint32_t*)ctx->counters.p;
     a.vals = const_cast<uint32_t*>(vals_local);
     a.heap = heap_local;
@@ -995,6 +937,7 @@ int zk_shard_upper_tree_dev(zk_ctx* ctx, uint8_t* upper_heap, uint32_t log_count
     if (post_op == POST_FRI && fri_layer >= n_layers) return fail(ctx, ZK_ERR_INVALID, "the last layer belongs to the replicated tail");
     CK(cudaSetDevice(ctx->device));
     TreeArgs a{};
+    a.tune = &ctx->tune;
     a.counters = (uint32_t*)ctx->counters.p;
     a.heap = upper_heap;
     a.log_size = log_count;
@@ -1025,7 +968,7 @@ int zk_shard_cp_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, 
     CpArgs c = make_cp_args(log_n);
     c.f = f_local;
     c.halo = halo;
-    c.log_len = ilog2(local_len);
+    c.log_len = ilog2_u64(local_len);
     c.shard = ShardMap{n_ranks, rank, log_block, 0};
     c.alpha_from_state = 1;
     CK(launch_cp(ctx->stream, cp_local, c, T->h.tab, 1, 0, (const ProofState*)state_dev));
@@ -1049,7 +992,7 @@ int zk_shard_fold_dev(zk_ctx* ctx, const uint32_t* cur_local, uint64_t local_len
     f.cur = cur_local;
     f.beta_from_state = 1;
     f.shard = ShardMap{n_ranks, rank, log_block, 0};
-    CK(launch_fold(ctx->stream, cur_local, next_local, ilog2(local_len) - 1, f, T->h.tab, 1, 0, (const ProofState*)state_dev));
+    CK(launch_fold(ctx->stream, cur_local, next_local, ilog2_u64(local_len) - 1, f, T->h.tab, 1, 0, (const ProofState*)state_dev));
     ctx->launches += 1;
     return ZK_OK;
 }
@@ -1058,6 +1001,16 @@ int zk_shard_fold_dev(zk_ctx* ctx, const uint32_t* cur_local, uint64_t local_len
 int zk_shard_cp_blocks_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, uint64_t local_len, uint32_t log_n,
                            uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev, uint32_t* cp_local,
                            uint8_t* heap_local)
+{
+    return zkh::shard_cp_blocks(ctx, f_local, halo, 0, local_len, log_n, n_ranks, rank, log_block, state_dev, cp_local, heap_local);
+}
+}  // extern "C"
+
+// halo_roll != 0: the halo rows are the heads of rank + 1's local blocks as they are (no re-ordering): on the last rank the
+// block that follows local block bl is rank 0's block bl + 1 (wrapping around the whole domain)
+int zkh::shard_cp_blocks(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, uint32_t halo_roll, uint64_t local_len,
+                         uint32_t log_n, uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev,
+                         uint32_t* cp_local, uint8_t* heap_local)
 {
     int rc = check_log_n(ctx, log_n);
     if (rc) return rc;
@@ -1068,14 +1021,19 @@ int zk_shard_cp_blocks_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t*
     CK(cudaSetDevice(ctx->device));
     SizeTables* T;
     if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
-    const uint32_t lg = ilog2(local_len);
+    const uint32_t lg = ilog2_u64(local_len);
     TreeArgs a{};
+    a.tune = &ctx->tune;
     a.counters = (uint32_t*)ctx->counters.p;
     a.state = (ProofState*)const_cast<void*>(state_dev);
     a.pow = T->h.tab;
     a.cp = make_cp_args(log_n);
     a.cp.f = f_local;
     a.cp.halo = halo;
+    if (halo_roll) {
+        a.cp.halo_roll = halo_roll;
+        a.cp.halo_mask = (uint32_t)(local_len >> log_block) - 1u;
+    }
     a.cp.log_len = lg;
     a.cp.shard = ShardMap{n_ranks, rank, log_block, 0};
     a.cp.alpha_from_state = 1;
@@ -1087,6 +1045,7 @@ int zk_shard_cp_blocks_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t*
     ctx->launches += nl;
     return ZK_OK;
 }
+extern "C" {
 
 // zk_shard_fold_dev + zk_shard_merkle_blocks_dev in one pass: the leaf pass of the block subtrees folds the previous
 // layer first (north_star item 4: fold, beta-mix and next-layer leaf hashing fused), so the new layer is written once
@@ -1099,7 +1058,7 @@ int zk_shard_fold_blocks_dev(zk_ctx* ctx, const uint32_t* cur_local, uint64_t lo
     if (!cur_local || !next_local || !heap_local || !state_dev || !is_pow2(local_len) || local_len < 2 || n_ranks == 0 ||
         rank >= n_ranks || log_N0 > 30)
         return fail(ctx, ZK_ERR_INVALID, "bad argument");
-    const uint32_t lg_next = ilog2(local_len) - 1;
+    const uint32_t lg_next = ilog2_u64(local_len) - 1;
     if (log_block < 5 || lg_next < log_block)
         return fail(ctx, ZK_ERR_INVALID, "the folded layer must hold at least one block of >= 32 values per rank");
     CK(cudaSetDevice(ctx->device));
@@ -1107,6 +1066,7 @@ int zk_shard_fold_blocks_dev(zk_ctx* ctx, const uint32_t* cur_local, uint64_t lo
     int rc = get_tables(ctx, log_N0, &T);
     if (rc) return rc;
     TreeArgs a{};
+    a.tune = &ctx->tune;
     a.counters = (uint32_t*)ctx->counters.p;
     a.state = (ProofState*)const_cast<void*>(state_dev);
     a.pow = T->h.tab;
@@ -1137,6 +1097,7 @@ int zk_shard_fri_tail_dev(zk_ctx* ctx, uint32_t log_n, uint32_t first_layer, uin
     SizeTables* T;
     if ((rc = get_tables(ctx, log_N, &T))) return rc;
     TreeArgs a{};
+    a.tune = &ctx->tune;
     a.counters = (uint32_t*)ctx->counters.p;
     a.state = (ProofState*)state_dev;
     a.transcript = transcript_dev;
@@ -1185,6 +1146,7 @@ int zk_shard_decommit_dev(zk_ctx* ctx, uint32_t log_n, uint32_t n_ranks, uint32_
     }
     a.tail_vals = tail_vals; a.tail_heaps = tail_heaps;
     a.state = (const ProofState*)state_dev; a.out = transcript_dev;
+    a.flag_off = (uint32_t)((transcript_len(log_n) + 3) & ~(size_t)3);
     CK(launch_shard_decommit(ctx->stream, a));
     ctx->launches += 1;
     return ZK_OK;
@@ -1204,14 +1166,14 @@ int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
     }
     ctx->bench_variant = sha_variant;
     ctx->bench_k = leaf_pass_k & 0xffu;
-    if (leaf_pass_k >> 8) set_coop_cnt((leaf_pass_k >> 8) - 1);   // bits 8..: 1 + widest cooperative tile level (0: keep)
+    if (leaf_pass_k >> 8) ctx->tune.coop_cnt = (leaf_pass_k >> 8) - 1;   // bits 8..: 1 + widest cooperative tile level (0: keep)
     return ZK_OK;
 }
 
 int zk_bench_set_tile_direct_log(zk_ctx* ctx, uint32_t log_leaves)
 {
     if (!ctx || (log_leaves & 0xffu) > 2 * TILE_LOG || ((log_leaves >> 8) & 0xffu) > TILE_LOG) return ZK_ERR_INVALID;
-    set_tile_direct_log(log_leaves);
+    set_tile_direct_log(ctx->tune, log_leaves);
     return ZK_OK;
 }
 
@@ -1244,6 +1206,7 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
     SizeTables* T = nullptr;
     size_t n_in = (size_t)1 << log_size, N8 = n_in << LOG_BLOWUP;
     TreeArgs ta{};
+    ta.tune = &ctx->tune;
     ta.counters = (uint32_t*)ctx->counters.p;
     FoldArgs fa{};
     CpArgs ca{};

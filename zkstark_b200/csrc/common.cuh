@@ -107,6 +107,23 @@ __host__ __device__ inline uint32_t shard_global(const ShardMap& m, uint32_t loc
     return ((((local >> m.log_block) * m.n_ranks) + m.rank) << m.log_block) | (local & ((1u << m.log_block) - 1u));
 }
 
+// Store layout of the last pass of a ONE-coset LDE transform when the evaluations go straight into the all-to-all send
+// buffer of the sharded prover (csrc/sharded.cu): point j of the transform (j < n) belongs to global block j / jb,
+// which lives on rank d = (j / jb) % G as its local block bl = j / jb / G; the send buffer is [d][slot][bl][tt].
+struct NttPack {
+    uint32_t log_jb;     // log2 of the points of ONE coset per block (= log_block - 3); 0: plain natural-order store
+    uint32_t log_G;      // log2 of the number of ranks
+    uint32_t log_nbl;    // log2 of the blocks per rank
+    uint32_t slot;       // which of this rank's n_slots coset transforms this is
+    uint32_t n_slots;    // 8 / G
+};
+__host__ __device__ inline size_t pack_index(const NttPack& p, uint32_t j)
+{
+    const uint32_t tt = j & ((1u << p.log_jb) - 1u), b = j >> p.log_jb;
+    const uint32_t d = b & ((1u << p.log_G) - 1u), bl = b >> p.log_G;
+    return ((((size_t)d * p.n_slots + p.slot) << p.log_nbl) + bl) << p.log_jb | tt;
+}
+
 // Fused leaf sources.  `vals` is where leaf values live (or are produced into).
 struct FoldArgs {           // polynomial.rs:385-400 + prover.rs:204-211 in evaluation form
     const uint32_t* cur;    // layer k, len = 2*half (batch stride cur_stride)
@@ -130,6 +147,8 @@ struct CpArgs {             // prover.rs:101-173 pointwise
     uint32_t a_first, a_last;  // used when !alpha_from_state (stand-alone API)
     ShardMap shard;            // sharded: f is the rank-local array, x comes from the global index
     const uint32_t* halo;      // sharded: first 16 values of the block that follows each local block
+    uint32_t halo_roll;        // halo row of local block bl is (bl + halo_roll) % n_blocks: the heads arrive from rank + 1 as
+    uint32_t halo_mask;        //   ITS local blocks; on the last rank the following block is rank 0's NEXT one (halo_mask = n_blocks - 1)
     uint32_t log_len;          // log2 of the number of local points (== log_N when not sharded)
     // Optional per-size constant tables (built once per context and size by launch_cp_tables; they depend on the
     // domain only, like twiddles): tab[i] = 1/(x_i - 1) R, tab[N + i] = 1/(x_i - g^(n-2)) R,
@@ -137,7 +156,21 @@ struct CpArgs {             // prover.rs:101-173 pointwise
     const uint32_t* tab;
 };
 
+// Launch-shape knobs of the tree kernels.  One copy per context (zk_ctx::tune; zk_bench_set* edit it), so contexts of
+// different threads / GPUs in one process never see each other's experiments.
+struct TreeTune {
+    uint32_t tile_direct_log = ZK_TILE_DIRECT_LOG;   // trees up to 2^this leaves (x batch) skip the per-thread-subtree leaf pass
+    uint32_t tile_log_override = 0;                  // forced tile size of the tile kernel (0 = adaptive)
+    uint32_t tile_shift = ZK_TILE_SHIFT;             // the tile kernel runs 2^this tiles per tree
+    uint32_t pass_log_threads = ZK_PASS_LOG_THREADS; // the leaf pass runs ~2^this threads (summed over the batch)
+    uint32_t coop_cnt = ZK_COOP_CNT;                 // tile kernel: widest level hashed by warp pairs
+    uint32_t pass_epilogue = ZK_EPILOGUE_LEVELS;     // CTA epilogue of the pass kernel: at most this many levels (0 = off)
+    uint32_t pass_max_k = ZK_PASS_MAX_K;             // deepest per-thread subtree of the leaf pass
+};
+TreeTune default_tree_tune();   // compile-time defaults overridden by ZK_EPILOGUE_LEVELS / ZK_PASS_MAX_K in the environment
+
 struct TreeArgs {
+    const TreeTune* tune;   // host side only (null: defaults)
     uint32_t* vals;         // leaf values of this tree (read, or written by a fused source)
     uint64_t vals_stride;   // elements between consecutive proofs of the batch
     uint8_t* heap;          // 32*(2*size-1) bytes per proof, root first (merkle.rs:14-51)
@@ -204,8 +237,7 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src_kind, TreeArgs a, uint
 cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int* n_launches);
 // the leaf pass alone (bench support): a.in_level / a.k preset by the caller
 cudaError_t launch_tree_leaf_pass(cudaStream_t s, TreeArgs a, uint32_t batch, int variant);
-void set_tile_direct_log(uint32_t v);
-void set_coop_cnt(uint32_t v);
+void set_tile_direct_log(TreeTune& t, uint32_t v);
 cudaError_t sha_init_constants();
 cudaError_t launch_node_latency(cudaStream_t s, uint32_t* out, uint32_t reps, uint32_t warps, int variant, long long* cycles);
 cudaError_t launch_decommit(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, uint64_t f_stride,
@@ -226,6 +258,8 @@ struct ShardDecommitArgs {
     const uint8_t* tail_heaps;
     const ProofState* state;
     uint8_t* out;                            // transcript buffer; only the records this rank owns are written
+    uint32_t flag_off;                       // byte offset in `out` (inside its 64-byte slack behind the transcript) of a u32 that
+                                             // is set non-zero when the last FRI layer is not constant (prover.rs:238)
 };
 cudaError_t launch_shard_decommit(cudaStream_t s, const ShardDecommitArgs& a);
 cudaError_t launch_open_queries(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, const uint8_t* f_heap,

@@ -33,6 +33,7 @@ struct NttPassArgs {
     uint32_t log_R1;     // final pass: first-pass radix (0 when single pass)
     uint32_t log_Q2;     // final pass: second-pass radix (0 unless three passes)
     uint32_t coset_base; // index of the first coset of this launch (sharded LDE: one coset per launch)
+    NttPack pack;        // final pass of a one-coset launch: store straight into the all-to-all send layout
 };
 
 constexpr int TP = 33;  // padded tile pitch
@@ -251,12 +252,14 @@ __global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_final_kernel(const
         const size_t rho = (size_t)(c1_0 + u) + ((size_t)c2 << a.log_R1);
         const uint32_t log_rows = a.log_M - LOG_R;
         uint32_t* q = dstb + (rho << LOG_CS) + r;
+        const bool packed = LOG_CS == 0 && a.pack.log_jb != 0;
 #pragma unroll
         for (int i = 0; i < RW; i++) {
             const uint32_t c = warp + i * C::NW;
             uint32_t x = sm[brev_c<LOG_R>(c) * TP + lane];
             if (a.use_scale) x = mont_mul(x, a.scale_m);
-            q[((size_t)c << log_rows) << LOG_CS] = x;
+            if (packed) dstb[pack_index(a.pack, (uint32_t)(rho + ((size_t)c << log_rows)))] = x;   // 32 lanes: 32 consecutive j, one block
+            else q[((size_t)c << log_rows) << LOG_CS] = x;
         }
     }
 }
@@ -404,7 +407,8 @@ static cudaError_t launch_final(bool coset, uint32_t n_cosets, dim3 grid, cudaSt
 static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint32_t n_cosets, bool coset_scale,
                            bool inverse, const uint32_t* coeffs, uint64_t coeffs_stride, uint32_t* work,
                            uint64_t work_stride, uint32_t* dst, uint64_t dst_stride, bool use_scale,
-                           uint32_t scale_m, uint32_t batch, int* n_launches, uint32_t coset_base = 0)
+                           uint32_t scale_m, uint32_t batch, int* n_launches, uint32_t coset_base = 0,
+                           const NttPack* pack = nullptr)
 {
     if (n_cosets != 1 && n_cosets != 8) return cudaErrorInvalidValue;
     uint32_t log_arrays = 0;
@@ -416,6 +420,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     a.hpow = T.hpow;
     a.wpow = T.wpow;
     a.coset_base = coset_base;
+    if (pack) a.pack = *pack;
     const uint32_t* twb = inverse ? T.tw_inv : T.tw_fwd;
     uint32_t log_S = mu;
     cudaError_t e;
@@ -535,10 +540,10 @@ cudaError_t launch_lde(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* t
 // One coset of the LDE on its own: out[j] = f(5 h^(8 j + r)), j < n (sharded LDE: ranks split the cosets).
 cudaError_t launch_lde_one_coset(cudaStream_t s, const uint32_t* tw_fwd, const uint32_t* tw_inv, PowTab hpow, PowTab wpow,
                                  uint32_t log_n, uint32_t r, const uint32_t* coeffs, uint32_t* work, uint32_t* out,
-                                 int* n_launches)
+                                 int* n_launches, const NttPack* pack)
 {
     NttTables T{tw_fwd, tw_inv, hpow, wpow};
-    return run_ntt(s, T, log_n, 1, true, false, coeffs, 0, work, 0, out, 0, false, 0, 1, n_launches, r);
+    return run_ntt(s, T, log_n, 1, true, false, coeffs, 0, work, 0, out, 0, false, 0, 1, n_launches, r, pack);
 }
 
 }  // namespace zk

@@ -16,6 +16,7 @@
 // layer (polynomial.rs:385-400 in evaluation form, proof.rs:110-112) or the composition
 // polynomial (prover.rs:101-173); the produced layer is written once and hashed from L1.
 #include <cstdlib>
+#include <mutex>
 #include "common.cuh"
 #define ZK_SHA_DEVICE
 #include "sha256.cuh"
@@ -23,6 +24,20 @@
 namespace zk {
 
 // ---------------------------------------------------------------- helpers
+// cudaFuncSetAttribute once per (kernel instantiation, device); contexts of several threads may race here
+static std::mutex g_attr_mutex;
+template <typename K>
+static cudaError_t set_max_smem_once(bool (&done)[64], K kernel, int bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    std::lock_guard<std::mutex> lk(g_attr_mutex);
+    if (done[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
 __device__ __forceinline__ uint32_t pow_h_m(const PowTab& t, uint32_t e)
 {
     return mont_mul(__ldg(t.lo + (e & ((1u << t.lo_bits) - 1u))), __ldg(t.hi + (e >> t.lo_bits)));
@@ -162,7 +177,7 @@ __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, cons
             fggx = f[(i + 2 * B) & len_mask];
         } else {
             // inside the local block, else in the 16-value head of the block that follows it globally
-            const uint32_t t = i & blk_mask, bl = i >> c.shard.log_block;
+            const uint32_t t = i & blk_mask, bl = ((i >> c.shard.log_block) + c.halo_roll) & c.halo_mask;
             fgx = (t + B <= blk_mask) ? f[i + B] : c.halo[bl * 16 + (t + B - blk_mask - 1)];
             fggx = (t + 2 * B <= blk_mask) ? f[i + 2 * B] : c.halo[bl * 16 + (t + 2 * B - blk_mask - 1)];
         }
@@ -1009,6 +1024,13 @@ __global__ void __launch_bounds__(256) shard_decommit_kernel(const ShardDecommit
     const uint32_t x = (uint32_t)((size_t)a.state->query_raw % (size_t)(N - 2 * B));  // prover.rs:263
     const size_t off0 = 84 + 36 * (size_t)L;
     const size_t rec0 = 12 + 32 * (size_t)log_N;
+    if (threadIdx.x == 0 && a.flag_off && a.tail_vals) {
+        // prover.rs:238: the last FRI polynomial has degree 0, i.e. its 8 evaluations are equal (the tail is replicated)
+        const uint32_t* last = a.tail_vals + (layer_vals_off_dev(log_N, L) - layer_vals_off_dev(log_N, a.first_tail));
+        uint32_t bad = 0;
+        for (uint32_t j = 1; j < (N >> L); j++) bad |= (last[j] != last[0]);
+        *reinterpret_cast<uint32_t*>(tr + a.flag_off) = bad;
+    }
     for (uint32_t r = threadIdx.x; r < 4 + L; r += blockDim.x) {
         ShardSrc sp;
         if (r < 4) {                                             // prover.rs:266-277
@@ -1183,15 +1205,12 @@ cudaError_t launch_chan_tail(cudaStream_t s, ProofState* states, const uint8_t* 
         blocks += (nw + 3 + 15) / 16 - 1;
     }
     const size_t smem = 4 * (((words + 3) & ~(size_t)3) + 64 * blocks);
-    static bool attr_done[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(chan_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done[dev] = true;
-    }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    {
+        static bool attr_done[64] = {};
+        cudaError_t e = set_max_smem_once(attr_done, chan_tail_kernel, 200 * 1024);
+        if (e != cudaSuccess) return e;
+    }
     return zk_launch(chan_tail_kernel, dim3(batch), dim3(256), smem, s, states, transcripts, stride, log_n);
 }
 
@@ -1212,13 +1231,11 @@ __global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64
 }
 
 // ---------------------------------------------------------------- launchers
-extern uint32_t g_tile_direct_log;
-extern uint32_t g_tile_log_override;
-extern uint32_t g_tile_shift;
-extern uint32_t g_pass_log_threads;
-extern uint32_t g_coop_cnt;
-extern uint32_t g_pass_epilogue;
-static uint32_t pass_max_k();
+static const TreeTune& tune_of(const TreeArgs& a)
+{
+    static const TreeTune dflt = default_tree_tune();
+    return a.tune ? *a.tune : dflt;
+}
 template <int SRC>
 static cudaError_t launch_pass(cudaStream_t s, const TreeArgs& a, uint32_t batch)
 {
@@ -1233,13 +1250,14 @@ static cudaError_t launch_tile(cudaStream_t s, const TreeArgs& a, uint32_t batch
     if (a.in_level > 2 * TILE_LOG) return cudaErrorInvalidValue;
     // Tile size: a lone warp hashes a node in ~2.7 us and already keeps its sub-partition's ALU pipe ~75 % busy
     // (one warp instruction per 2 cycles), so the latency-bound levels want FEW warps on MANY SMs and no two CTAs
-    // on one SM (their surviving warps would share sub-partition 0): 2^g_tile_shift = 128 tiles <= 148 SMs,
+    // on one SM (their surviving warps would share sub-partition 0): 2^tile_shift = 128 tiles <= 148 SMs,
     // tiles of 128 inputs (2 warps) for small trees, up to 2^TILE_LOG inputs above that.
     TreeArgs b = a;
-    int lt = (int)a.in_level - (int)g_tile_shift;
+    const TreeTune& T = tune_of(a);
+    int lt = (int)a.in_level - (int)T.tile_shift;
     if (lt < (int)TILE_MIN_LOG) lt = TILE_MIN_LOG;
     if (lt > (int)TILE_LOG) lt = TILE_LOG;
-    if (g_tile_log_override) lt = g_tile_log_override;
+    if (T.tile_log_override) lt = T.tile_log_override;
     if (lt > (int)a.in_level) lt = a.in_level;
     if (a.in_level - lt > TILE_LOG) return cudaErrorInvalidValue;
     b.log_tile = lt;
@@ -1249,7 +1267,7 @@ static cudaError_t launch_tile(cudaStream_t s, const TreeArgs& a, uint32_t batch
     if (n_tiles > 2 * threads) threads = n_tiles / 2;                        // ... or of the tile roots, in the closing CTA
     if (threads < 32) threads = 32;
     // cooperative levels need two warps per 32 nodes
-    uint32_t coop = g_coop_cnt > 32 * COOP_PAIRS ? 32 * COOP_PAIRS : g_coop_cnt;
+    uint32_t coop = T.coop_cnt > 32 * COOP_PAIRS ? 32 * COOP_PAIRS : T.coop_cnt;
     if (coop) {
         uint32_t need = 2 * (threads < coop ? threads : coop);
         need = (need + 63) & ~63u;
@@ -1260,14 +1278,8 @@ static cudaError_t launch_tile(cudaStream_t s, const TreeArgs& a, uint32_t batch
     const size_t smem = 4 * ((size_t)12 * threads + (size_t)COOP_WORDS * npair);
     {
         static bool attr_done[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(tree_tile_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(4 * (12 * TILE_PAIRS + COOP_WORDS * COOP_PAIRS)));
-            if (e != cudaSuccess) return e;
-            attr_done[dev] = true;
-        }
+        cudaError_t e = set_max_smem_once(attr_done, tree_tile_kernel<SRC>, (int)(4 * (12 * TILE_PAIRS + COOP_WORDS * COOP_PAIRS)));
+        if (e != cudaSuccess) return e;
     }
     return zk_launch(tree_tile_kernel<SRC>, dim3(n_tiles, batch), dim3(threads), smem, s, b);
 }
@@ -1283,18 +1295,18 @@ static cudaError_t launch_tile_src(cudaStream_t s, int src, const TreeArgs& a, u
 }
 // CTA epilogue levels of a pass over 2^in_level inputs with 2^k per thread, never going above heap level `floor`
 // (needs full CTAs: at least PASS_THREADS threads)
-static uint32_t pick_ep(uint32_t in_level, uint32_t k, uint32_t floor, uint32_t batch)
+static uint32_t pick_ep(const TreeTune& T, uint32_t in_level, uint32_t k, uint32_t floor, uint32_t batch)
 {
     uint32_t log_pt = 0;
     while ((1u << (log_pt + 1)) <= PASS_THREADS) log_pt++;
-    if (!g_pass_epilogue || in_level < k + log_pt) return 0;
+    if (!T.pass_epilogue || in_level < k + log_pt) return 0;
     const uint32_t room = in_level - k - floor;
     uint32_t ep = room < log_pt ? room : log_pt;
     // A CTA in its epilogue holds its registers and thread slots while one warp works: with a single proof that
     // costs more bulk throughput than the shorter upper-tree kernel wins back beyond one level (measured, 2^20:
     // 5.111 / 5.092 / 5.100 / 5.142 / 5.258 ms at 0 / 1 / 2 / 4 / 8 levels); in a batch the other proofs' CTAs fill the
     // gap and the deep epilogue wins (238.9 / 240.2 / 240.6 / 241.1 proofs/s at 0 / 2 / 4 / 8).
-    const uint32_t cap = batch >= 4 ? g_pass_epilogue : (g_pass_epilogue < 1 ? g_pass_epilogue : 1u);
+    const uint32_t cap = batch >= 4 ? T.pass_epilogue : (T.pass_epilogue < 1 ? T.pass_epilogue : 1u);
     return ep < cap ? ep : cap;
 }
 // digest passes until the tile kernel can take over, then the tile kernel
@@ -1304,7 +1316,7 @@ static cudaError_t finish_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int*
     while (a.in_level > 2 * TILE_LOG) {
         uint32_t rem = a.in_level - 2 * TILE_LOG;
         a.k = rem >= 4 ? 4 : rem;
-        a.ep_levels = pick_ep(a.in_level, a.k, 0, batch);
+        a.ep_levels = pick_ep(tune_of(a), a.in_level, a.k, 0, batch);
         e = launch_pass<SRC_DIGESTS>(s, a, batch);
         (*launches)++;
         if (e != cudaSuccess) return e;
@@ -1329,18 +1341,19 @@ cudaError_t launch_merkle_tree(cudaStream_t s, int src, TreeArgs a, uint32_t bat
     int launches = 0;
     a.in_level = a.log_size;
     const uint32_t lb = ilog2(batch);
-    if (a.log_size + lb <= g_tile_direct_log || a.log_size <= TILE_LOG) {
+    const TreeTune& T = tune_of(a);
+    if (a.log_size + lb <= T.tile_direct_log || a.log_size <= TILE_LOG) {
         // small and mid-size trees: leaves -> root in one launch
         e = launch_tile_src(s, src, a, batch);
         launches++;
     } else {
         // leaf pass: enough threads to fill 148 SMs several times over, else fewer levels per thread
-        int k = (int)a.log_size + (int)lb - (int)g_pass_log_threads;
+        int k = (int)a.log_size + (int)lb - (int)T.pass_log_threads;
         if (k < 1) k = 1;
-        if (k > (int)pass_max_k()) k = pass_max_k();
+        if (k > (int)T.pass_max_k) k = T.pass_max_k;
         if (k > (int)(a.log_size - TILE_LOG)) k = a.log_size - TILE_LOG;
         a.k = k;
-        a.ep_levels = pick_ep(a.in_level, k, 0, batch);
+        a.ep_levels = pick_ep(tune_of(a), a.in_level, k, 0, batch);
         switch (src) {
             case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
             case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
@@ -1370,7 +1383,7 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src, TreeArgs a, uint32_t 
     if (k > 5) k = 5;
     if (k > (int)(a.log_size - stop_level)) k = a.log_size - stop_level;
     a.k = k;
-    a.ep_levels = pick_ep(a.in_level, k, stop_level, batch);
+    a.ep_levels = pick_ep(tune_of(a), a.in_level, k, stop_level, batch);
     switch (src) {
         case SRC_VALUES: e = launch_pass<SRC_VALUES>(s, a, batch); break;
         case SRC_FOLD: e = launch_pass<SRC_FOLD>(s, a, batch); break;
@@ -1385,7 +1398,7 @@ cudaError_t launch_merkle_partial(cudaStream_t s, int src, TreeArgs a, uint32_t 
         if (kk < 1) kk = 1;
         if (kk > 5) kk = 5;
         a.k = rem < (uint32_t)kk ? rem : (uint32_t)kk;
-        a.ep_levels = pick_ep(a.in_level, a.k, stop_level, batch);
+        a.ep_levels = pick_ep(tune_of(a), a.in_level, a.k, stop_level, batch);
         e = launch_pass<SRC_DIGESTS>(s, a, batch);
         launches++;
         a.in_level -= a.k + a.ep_levels;
@@ -1402,38 +1415,29 @@ cudaError_t launch_merkle_upper(cudaStream_t s, TreeArgs a, uint32_t batch, int*
     return e;
 }
 
-// trees of up to 2^g_tile_direct_log leaves (summed over the batch) skip the per-thread-subtree leaf pass
-uint32_t g_tile_direct_log = ZK_TILE_DIRECT_LOG;
-uint32_t g_tile_log_override = 0;
-// deepest per-thread subtree of the leaf pass (ZK_PASS_MAX_K overrides the default for experiments)
-static uint32_t pass_max_k()
+TreeTune default_tree_tune()
 {
-    static const uint32_t v = [] {
-        const char* e = getenv("ZK_PASS_MAX_K");
-        uint32_t k = e ? (uint32_t)atoi(e) : (uint32_t)ZK_PASS_MAX_K;
-        return k < 1 ? 1u : (k > MAX_PASS_K ? MAX_PASS_K : k);
-    }();
-    return v;
+    TreeTune t;
+    if (const char* e = getenv("ZK_EPILOGUE_LEVELS")) t.pass_epilogue = (uint32_t)atoi(e);
+    if (const char* e = getenv("ZK_PASS_MAX_K")) {
+        const uint32_t k = (uint32_t)atoi(e);
+        t.pass_max_k = k < 1 ? 1u : (k > MAX_PASS_K ? MAX_PASS_K : k);
+    }
+    return t;
 }
 bool pdl_enabled()
 {
     static const bool on = [] { const char* e = getenv("ZK_NO_PDL"); return !(e && e[0] == '1'); }();
     return on;
 }
-uint32_t g_tile_shift = ZK_TILE_SHIFT;              // the tile kernel runs 2^g_tile_shift tiles per tree
-uint32_t g_pass_log_threads = ZK_PASS_LOG_THREADS;  // the leaf pass runs ~2^g_pass_log_threads threads (summed over the batch)
-uint32_t g_coop_cnt = ZK_COOP_CNT;                  // tile kernel: widest level hashed by warp pairs
-// CTA epilogue of the pass kernel: at most this many levels (ZK_EPILOGUE_LEVELS overrides; 0 = off)
-uint32_t g_pass_epilogue = [] { const char* e = getenv("ZK_EPILOGUE_LEVELS"); return e ? (uint32_t)atoi(e) : (uint32_t)ZK_EPILOGUE_LEVELS; }();
-void set_coop_cnt(uint32_t v) { g_coop_cnt = v; }
 // bench knob: bits 0-7 direct threshold, 8-15 forced tile size (0 = adaptive), 16-23 tile shift, 24-31 leaf-pass
 // log-threads (0 = keep the default)
-void set_tile_direct_log(uint32_t v)
+void set_tile_direct_log(TreeTune& t, uint32_t v)
 {
-    g_tile_direct_log = v & 0xffu;
-    g_tile_log_override = (v >> 8) & 0xffu;
-    g_tile_shift = ((v >> 16) & 0xffu) ? ((v >> 16) & 0xffu) : ZK_TILE_SHIFT;
-    g_pass_log_threads = (v >> 24) ? (v >> 24) : ZK_PASS_LOG_THREADS;
+    t.tile_direct_log = v & 0xffu;
+    t.tile_log_override = (v >> 8) & 0xffu;
+    t.tile_shift = ((v >> 16) & 0xffu) ? ((v >> 16) & 0xffu) : ZK_TILE_SHIFT;
+    t.pass_log_threads = (v >> 24) ? (v >> 24) : ZK_PASS_LOG_THREADS;
 }
 
 __global__ void state_set_kernel(ProofState* st, uint32_t a_first, uint32_t a_last)
