@@ -8,6 +8,13 @@ as one batched launch sequence (the latency-bound upper Merkle levels and Fiat-S
 overlap the others); single-proof latency is reported beside it as prove_ms_single.  Independent proofs
 shard across ranks with no data-path collective (weak scaling): value = proofs/s summed over all ranks.
 
+After the headline the same line carries the other BASELINE configs, each with parity against a committed golden:
+  sharded_2p24      configs[4]: ONE 2^24 proof over all N ranks (zk_prove_fibsq_sharded, NCCL inside the library), beside
+                    the single-GPU time measured on rank 0 in the same run;
+  batch_2p16x1024   configs[3]: 1024 independent 2^16 proofs split over the N ranks (strong scaling);
+  configs           single-GPU latency of one proof at 2^10 (the reference's own configuration), 2^16 and 2^24 with the
+                    CPU baselines of the small ones (2^10: the LITERAL single-thread restatement of the reference).
+
   python bench.py                          # 1 GPU
   torchrun --nproc-per-node N bench.py --gpus N
   python bench.py --impl reference         # the CPU arm: the oracle's NTT route on all host threads
@@ -40,16 +47,25 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="independent proofs per rank per step (proofs of one step run as one batched launch sequence)")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / cpu_baseline / stage breakdown")
     ap.add_argument("--workload", default="batch", choices=["batch", "sharded"],
-                    help="batch: independent proofs per rank (headline, weak scaling); sharded: ONE proof of 2^log-n "
-                         "split over all ranks (BASELINE configs[4], strong scaling; use --log-n 24)")
+                    help="batch: independent proofs per rank (headline, weak scaling) followed by the other configs; sharded: "
+                         "only ONE proof of 2^log-n split over all ranks through the Python driver (zkstark_b200/sharded.py)")
+    ap.add_argument("--no-configs", action="store_true", help="skip sharded_2p24 / batch_2p16x1024 / configs")
+    ap.add_argument("--sharded-log-n", type=int, default=24)
+    ap.add_argument("--cpu-2p24", action="store_true", help="also time the oracle at 2^24 (35 s per proof)")
     return ap.parse_args()
 
 
 def workload_name(log_n, batch):
-    w = f"FibonacciSq synthetic trace 2^{log_n}, blowup 8 (LDE 2^{log_n + 3}), secret 3141592+rank"
+    w = f"FibonacciSq synthetic trace 2^{log_n}, blowup 8 (LDE 2^{log_n + 3}), secret 3141592+index"
     if batch > 1:
         w += f", {batch} independent proofs per step per GPU"
     return w
+
+
+def make_config(log_n, batch):
+    """The `config` object of BOTH arms (the driver compares them)."""
+    return {"workload": workload_name(log_n, batch), "log_n": log_n, "proofs_per_step_per_gpu": batch,
+            "scope": "secret in -> proof out: trace generation (prover.rs:32-39) + prove() (prover.rs:60-292)"}
 
 
 class ClockSampler:
@@ -116,8 +132,9 @@ def run_reference(args):
     oracle.build()
     threads = oracle.default_threads()
     k = args.log_n
-    for _ in range(min(args.warmup, 1)):
-        oracle.prove_fibsq(k, 3141592, oracle.ROUTE_FAST, threads)
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        oracle.prove_fibsq(k, 3141592 + i, oracle.ROUTE_FAST, threads)
     t0 = time.perf_counter()
     lde_s = 0.0
     for i in range(args.steps):
@@ -125,14 +142,17 @@ def run_reference(args):
         lde_s += info.t_interp + info.t_lde
     dt = time.perf_counter() - t0
     v = args.steps / dt
+    cfg = make_config(k, args.batch)
+    cfg["timing"] = "host wall clock around every step"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 (F_p, p=3*2^30+1) + SHA-256", "data": "synthetic",
-        "config": {"workload": workload_name(k, 1), "log_n": k, "timing": "host wall clock, whole prove() incl. trace generation"},
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} full prove() calls at 2^{k} (oracle NTT route, OpenMP x{threads}, "
-                                   f"sha_ni={bool(oracle.lib().orc_sha256_uses_shani())})"},
+                         "sample": f"each step = ONE proof of the workload's {args.batch} (secret in -> proof out, trace generation "
+                                   f"included): {args.steps} prove() calls at 2^{k}, oracle NTT route, OpenMP x{threads}, "
+                                   f"sha_ni={bool(oracle.lib().orc_sha256_uses_shani())}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "lde_elems_per_s": args.steps * (8 << k) / lde_s if lde_s > 0 else None,
         "gpu_launches": 0,
@@ -198,17 +218,19 @@ def main():
     def step_resident():
         ctx.prove_fibsq_resident_ptr(k, nb, traces_dev.data_ptr(), tr_out.data_ptr(), st_out.data_ptr())
 
-    def step_e2e():
+    def step_from_trace():
         ctx.prove_fibsq_batch_ptr(k, nb, traces_host.data_ptr(), tr_out.data_ptr(), st_out.data_ptr())
+
+    secrets_np = np.array([(3141592 + rank * nb + j) & 0xFFFFFFFF for j in range(nb)], dtype=np.uint32)
 
     def timed(fn, steps):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         w0 = time.perf_counter()
-        for a, b in evs:
+        for i, (a, b) in enumerate(evs):
             flush.fill_(1)            # L2 flush between timed iterations (not inside the event pair)
             a.record(stream)
-            fn()
+            fn(i, steps)
             b.record(stream)
         barrier()
         wall = time.perf_counter() - w0
@@ -218,13 +240,23 @@ def main():
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         return float(tot.item()), ms, wall
 
-    for _ in range(max(args.warmup, 3)):
+    def step_e2e(i, steps):
+        # secrets in -> transcripts out through the pipelined API: the traces of step i + 1 are generated (host threads) and
+        # uploaded (side stream) while step i is proved; the first step's trace generation is exposed and inside its events
+        if i == 0:
+            ctx.prove_stream_submit(k, secrets_np)
+        if i + 1 < steps:
+            ctx.prove_stream_submit(k, secrets_np)
+        ctx.prove_stream_collect_ptr(tr_out.data_ptr(), st_out.data_ptr())
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
-    tot_ms, ms_list, wall = timed(step_resident, args.steps)
+    tot_ms, ms_list, wall = timed(lambda i, steps: step_resident(), args.steps)
     # parity of the N>1 path: every rank's transcripts, hashed, gathered in global order
     from zkstark_b200 import dist as zd
     digests = zd.gather_transcript_digests([tr_out[j].numpy().tobytes() for j in range(nb)], device="cuda")
@@ -232,23 +264,46 @@ def main():
     clocks = sampler.stop() if rank == 0 else {}
     first_hash = __import__("hashlib").sha256(tr_out[0].numpy().tobytes()).hexdigest()
 
+    timed(step_e2e, warm)     # warm-up of the pipelined path (allocates its two trace slots)
+    tr_out.zero_()
+    e2e_ms, e2e_list, _ = timed(step_e2e, args.steps)
+    e2e_digests = zd.gather_transcript_digests([tr_out[j].numpy().tobytes() for j in range(nb)], device="cuda")
     for _ in range(2):
-        step_e2e()
-    e2e_ms, _, _ = timed(step_e2e, args.steps)
+        step_from_trace()
+    ft_ms, _, _ = timed(lambda i, steps: step_from_trace(), args.steps)
+    # one un-pipelined call, secrets in -> transcripts out (trace generation exposed)
+    t_single = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        ctx.prove_fibsq_batch_secrets_ptr(k, nb, secrets_np.ctypes.data, tr_out.data_ptr(), st_out.data_ptr())
+        t_single.append(1e3 * (time.perf_counter() - t0))
 
     value = world * nb * args.steps / (tot_ms * 1e-3)
     e2e_value = world * nb * args.steps / (e2e_ms * 1e-3)
+    cfg = make_config(k, nb)
+    cfg.update({"l2": "256 MiB buffer rewritten between timed iterations (L2 flush); per-proof working set 1.75 GB >> L2",
+                "timing": "CUDA events per step on the ctx stream (torch current stream), sum over steps, max over ranks"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 (F_p, p=3*2^30+1) + SHA-256", "data": "synthetic",
-        "config": {"workload": workload_name(k, nb), "log_n": k, "proofs_per_step_per_gpu": nb,
-                   "l2": "512 MiB-free: 256 MiB buffer rewritten between timed iterations (L2 flush); per-proof working set 1.75 GB >> L2",
-                   "timing": "CUDA events per step on the ctx stream (torch current stream), sum over steps, max over ranks"},
+        "config": cfg,
+        "value_scope": "traces resident in HBM -> transcripts on the host (zk_prove_fibsq_resident)",
         "prove_ms": tot_ms / args.steps / nb,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * (n - 1) * nb),
                 "d2h_bytes_per_step": int((((tl + 63) // 64) * 64 + 256) * nb), "ms_per_step": e2e_ms / args.steps,
-                "api": "zk_prove_fibsq_batch: pinned host trace in, transcript + state out (H2D/D2H inside)"},
+                "first_step_ms": e2e_list[0],
+                "api": "zk_prove_stream_submit / zk_prove_stream_collect: host secrets in, traces generated by host threads one "
+                       "step ahead and uploaded from pinned memory on a side stream (H2D), transcripts + states out (D2H); the "
+                       "first step's trace generation is not overlapped and is inside the timed region",
+                "h2d_note": "the library uploads the traces it generates: 4 (n - 1) bytes per proof, counted here",
+                "parity": bool(e2e_digests == digests)},
+        "e2e_from_trace": {"value": world * nb * args.steps / (ft_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * (n - 1) * nb),
+                           "api": "zk_prove_fibsq_batch: pinned host traces in (H2D inside), transcripts out"},
+        "e2e_single_call_ms": min(t_single),
+        "e2e_single_call_note": "zk_prove_fibsq_batch_secrets, one call, host wall clock: the trace generation of the (only) "
+                                "sub-batch is exposed in front of the proving",
         "trace_gen_ms": trace_gen_ms,
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -259,11 +314,173 @@ def main():
 
     if rank == 0 and not args.no_extras:
         extras(args, ctx, zk, line, clocks, world, step_resident)
+    if not args.no_configs:
+        del traces_dev, flush
+        torch.cuda.empty_cache()
+        other_configs(args, ctx, zk, torch, dist, world, rank, local, stream, barrier, line)
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(args, ctx, zk, torch, dist, world, rank, local, stream, barrier, line):
+    """BASELINE configs[3], configs[4] and the single-GPU latencies, each checked against a committed golden."""
+    import hashlib
+
+    import numpy as np
+    from zkstark_b200 import dist as zd
+
+    def dev_max(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    gold_large = json.load(open(os.path.join(ROOT, "tests", "golden", "large_digests.json")))
+    ctx.trim()
+
+    # ---- configs[3]: 1024 independent 2^16 proofs split over the ranks (strong scaling, no collective)
+    k16, total = 16, 1024
+    lo, hi = zd.shard_range(total, world, rank)
+    secrets = np.array([zd.proof_secret(j) for j in range(lo, hi)], dtype=np.uint32)
+    tl16 = zk.transcript_len(k16)
+    tr16 = torch.empty((hi - lo, tl16), dtype=torch.uint8).pin_memory()
+    st16 = torch.empty((hi - lo, 32), dtype=torch.uint8).pin_memory()
+
+    def batch16():
+        ctx.prove_fibsq_batch_secrets_ptr(k16, hi - lo, secrets.ctypes.data, tr16.data_ptr(), st16.data_ptr())
+
+    for _ in range(2):
+        batch16()
+    reps = 5
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    barrier()
+    for a, b in evs:
+        a.record(stream)
+        batch16()
+        b.record(stream)
+    barrier()
+    ms16 = dev_max(sum(a.elapsed_time(b) for a, b in evs)) / reps
+    d16 = zd.gather_transcript_digests([tr16[j].numpy().tobytes() for j in range(hi - lo)], device="cuda")
+    try:
+        gold16 = json.load(open(os.path.join(ROOT, "tests", "golden", "batch_2p16_digest.json")))
+        parity16 = bool(hashlib.sha256("".join(d16).encode()).hexdigest() == gold16["checksum_of_checksums"][str(total)])
+    except Exception:
+        parity16 = None
+    line["batch_2p16x1024"] = {
+        "workload": "BASELINE configs[3]: 1024 independent 2^16-trace proofs (secret 3141592 + j) split over the ranks, "
+                    "secrets in -> transcripts out (zk_prove_fibsq_batch_secrets)",
+        "proofs_per_s": total / (ms16 * 1e-3), "ms": ms16, "n_gpus": world, "scaling": "strong",
+        "parity_vs_golden": parity16, "golden": "tests/golden/batch_2p16_digest.json (oracle, checksum of checksums)"}
+    del tr16, st16
+    ctx.trim()
+
+    # ---- configs[4]: ONE 2^24 proof over all ranks (native driver: NCCL inside the library)
+    ks = args.sharded_log_n
+    trace_np = zk.trace_fibsq(ks, 3141592)
+    trace = torch.from_numpy(trace_np.view(np.int32)).pin_memory()
+    tls = zk.transcript_len(ks)
+    trs = torch.empty(tls, dtype=torch.uint8).pin_memory()
+    sts = torch.empty(32, dtype=torch.uint8).pin_memory()
+    ms_1gpu = None
+    if rank == 0:
+        # the single-GPU time of the same proof, same run, same GPU model: the monolithic pipeline on rank 0 alone
+        for _ in range(2):
+            ctx.prove_fibsq_from_trace_ptr(ks, trace.data_ptr(), trs.data_ptr(), tls, sts.data_ptr())
+        e = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for a, b in e:
+            a.record(stream)
+            ctx.prove_fibsq_from_trace_ptr(ks, trace.data_ptr(), trs.data_ptr(), tls, sts.data_ptr())
+            b.record(stream)
+        torch.cuda.synchronize()
+        ms_1gpu = min(a.elapsed_time(b) for a, b in e)
+        mono_hash = hashlib.sha256(trs.numpy().tobytes()).hexdigest()
+        ctx.trim()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(zk.shard_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = zk.ShardComm(ctx, world, rank, bytes(uid.cpu().numpy()))
+    else:
+        comm = zk.ShardComm.local(ctx, 1)
+    for _ in range(2):
+        comm.prove_ptr(ks, trace.data_ptr(), trs.data_ptr(), tls, sts.data_ptr())
+    reps = 5
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    barrier()
+    phases = []
+    for a, b in evs:
+        a.record(stream)
+        comm.prove_ptr(ks, trace.data_ptr(), trs.data_ptr(), tls, sts.data_ptr())
+        b.record(stream)
+        phases.append(comm.last_phase_ms())
+    barrier()
+    ms_sh = dev_max(sum(a.elapsed_time(b) for a, b in evs)) / reps
+    sh_hash = hashlib.sha256(trs.numpy().tobytes()).hexdigest()
+    all_hash = zd.gather_transcript_digests([trs.numpy().tobytes()], device="cuda")
+    gold = gold_large.get(str(ks), {})
+    best = min(phases, key=lambda p: p["total"])
+    line["sharded_2p%d" % ks] = {
+        "workload": f"BASELINE configs[4]: ONE FibonacciSq proof, trace 2^{ks} (LDE 2^{ks + 3}), sharded over {world} GPU(s): "
+                    "coset-split LDE + one NCCL all-to-all, blocked-cyclic ownership (zk_prove_fibsq_sharded); pinned host "
+                    "trace in, transcript out",
+        "ms": ms_sh, "ms_1gpu": ms_1gpu, "efficiency": (ms_1gpu / (world * ms_sh)) if ms_1gpu else None, "n_gpus": world,
+        "scaling": "strong", "nvlink_bytes_per_rank": comm.last_comm_bytes(), "first_tail_layer": comm.last_first_tail(),
+        "phase_ms": {a: round(b, 4) for a, b in best.items()},
+        "parity": bool(gold and sh_hash == gold.get("sha256") and sts.numpy().tobytes().hex() == gold.get("state")
+                       and len(set(all_hash)) == 1),
+        "parity_1gpu": bool(gold and ms_1gpu is not None and mono_hash == gold.get("sha256")) if rank == 0 else None,
+        "golden": "tests/golden/large_digests.json (oracle)"}
+    comm.close()
+    ctx.trim()
+
+    # ---- single-GPU latency of ONE proof per config (rank 0), beside its CPU baseline
+    if rank == 0:
+        cfgs = {}
+        ctx.set_stage_timing(True)
+        tdata = json.load(open(os.path.join(ROOT, "tests", "golden", "transcripts.json")))
+        for kk in (10, 16):
+            tr = zk.trace_fibsq(kk, 3141592)
+            best_dev, best_call, out = None, None, None
+            for _ in range(8):
+                t0 = time.perf_counter()
+                out = ctx.prove_fibsq_from_trace(kk, tr)
+                dt = 1e3 * (time.perf_counter() - t0)
+                best_call = dt if best_call is None else min(best_call, dt)
+                sm = ctx.last_stage_ms()["total"]
+                best_dev = sm if best_dev is None else min(best_dev, sm)
+            ent = {"prove_ms_device": best_dev, "prove_call_ms_host_wall": best_call}
+            g = tdata.get(str(kk)) if isinstance(tdata, dict) else None
+            if g and "sha256" in g:
+                ent["parity"] = bool(hashlib.sha256(out[0]).hexdigest() == g["sha256"])
+            cfgs["2^%d" % kk] = ent
+        ctx.set_stage_timing(False)
+        cfgs["2^%d" % ks] = {"prove_ms_device": ms_1gpu, "parity": line["sharded_2p%d" % ks]["parity_1gpu"]}
+        try:
+            import oracle
+            oracle.build()
+            th = oracle.default_threads()
+            t0 = time.perf_counter()
+            otr, _, _ = oracle.prove_fibsq(10, 3141592, oracle.ROUTE_LITERAL, 1)
+            cfgs["2^10"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+            cfgs["2^10"]["cpu_kind"] = ("port: LITERAL restatement of the reference's own O(n^3) algorithm (oracle/prover.c), 1 thread, "
+                                        "1 sample -- what `cargo run --release` does on a single core")
+            oracle.prove_fibsq(16, 1, oracle.ROUTE_FAST, th)
+            t0 = time.perf_counter()
+            for i in range(5):
+                oracle.prove_fibsq(16, 3141592 + i, oracle.ROUTE_FAST, th)
+            cfgs["2^16"]["cpu_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+            cfgs["2^16"]["cpu_kind"] = f"port: oracle NTT route, OpenMP x{th}, 5 samples"
+            if args.cpu_2p24:
+                t0 = time.perf_counter()
+                oracle.prove_fibsq(ks, 3141592, oracle.ROUTE_FAST, th)
+                cfgs["2^%d" % ks]["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+        except Exception as ex:      # the CPU legs are a reported baseline, never a reason to lose the line
+            cfgs["cpu_error"] = repr(ex)
+        line["configs"] = cfgs
 
 
 def run_sharded(args, ctx, zk, torch, dist, world, rank, local, stream, barrier):
@@ -412,15 +629,15 @@ def extras(args, ctx, zk, line, clocks, world, step_resident):
         import oracle
         oracle.build()
         threads = oracle.default_threads()
-        reps = 2
-        oracle.prove_fibsq(max(k - 4, 3), 1, oracle.ROUTE_FAST, threads)  # thread-pool warm-up
+        reps = 5
+        oracle.prove_fibsq(k, 1, oracle.ROUTE_FAST, threads)  # warm-up (thread pool, page faults)
         t0 = time.perf_counter()
         for i in range(reps):
             otr, ost, info = oracle.prove_fibsq(k, 3141592 + i, oracle.ROUTE_FAST, threads)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {
             "value": reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{reps} full prove() calls at 2^{k} with the oracle's NTT route (OpenMP x{threads}, "
+            "sample": f"{reps} proofs of the workload (secret in -> proof out, trace generation included) at 2^{k} with the oracle's NTT route (OpenMP x{threads}, "
                       f"sha_ni={bool(oracle.lib().orc_sha256_uses_shani())}); the reference's own O(n^3) algorithm "
                       "only exists for n = 1024",
             "ms_per_proof": 1e3 * dt / reps,

@@ -343,3 +343,57 @@ def test_gpu_proof_passes_product_verifier(ctx, kats):
     tampered = zk.Proof(proof.state, proof.data[:100] + bytes([proof.data[100] ^ 1]) + proof.data[101:])
     with pytest.raises(zk.ZkError):
         tampered.verify()
+
+
+def test_prove_stream_pipeline(ctx, orc):
+    """zk_prove_stream_submit / _collect: secrets in, proofs out, two batches in flight, FIFO order."""
+    k = 12
+    sa = np.array([3141592 + j for j in range(5)], dtype=np.uint32)
+    sb = np.array([17 + j for j in range(3)], dtype=np.uint32)
+    with pytest.raises(zk.ZkError):
+        ctx.prove_stream_collect(k, 1)                  # nothing submitted
+    ctx.prove_stream_submit(k, sa)
+    ctx.prove_stream_submit(k, sb)
+    with pytest.raises(zk.ZkError):
+        ctx.prove_stream_submit(k, sb)                  # two batches already in flight
+    with pytest.raises(zk.ZkError):
+        ctx.trim()                                      # batches in flight
+    tra, sta = ctx.prove_stream_collect(k, len(sa))
+    ctx.prove_stream_submit(k, sa[:2])                  # refill while one is pending
+    trb, stb = ctx.prove_stream_collect(k, len(sb))
+    trc, stc = ctx.prove_stream_collect(k, 2)
+    for secrets, tr, st in ((sa, tra, sta), (sb, trb, stb), (sa[:2], trc, stc)):
+        for j, s in enumerate(secrets):
+            otr, ost, _ = orc.prove_fibsq(k, int(s))
+            assert tr[j].tobytes() == otr and st[j].tobytes() == ost
+
+
+def test_trim_then_prove_again(ctx, orc):
+    """zk_ctx_trim releases the work space and the per-size tables; the next call rebuilds them."""
+    a = ctx.prove_fibsq(11, 77)
+    ctx.trim()
+    b = ctx.prove_fibsq(11, 77)
+    ctx.trim(tables_too=True)
+    c = ctx.prove_fibsq(11, 77)
+    otr, ost, _ = orc.prove_fibsq(11, 77)
+    assert a == b == c == (otr, ost)
+    with pytest.raises(zk.ZkError):
+        ctx.open_queries(12, [5])                       # log_n differs from the resident proof's
+    assert len(ctx.open_queries(11, [5, 9])) == 2
+
+
+def test_lde_other_coset_shift(ctx, orc):
+    """zk_lde_coset with shift != 5 (tables of the shift are cached per context; no stream synchronisation)."""
+    k = 9
+    rng = np.random.default_rng(5)
+    coeffs = rng.integers(0, zk.P, size=1 << k, dtype=np.uint64).astype(np.uint32)
+    for shift in (7, 5, 7, 3221225472):
+        got = ctx.lde_coset(coeffs, k, shift=shift)
+        h = pow(5, (zk.P - 1) >> (k + 3), zk.P)
+        idx = [0, 1, 2, 77, (8 << k) - 1]
+        for i in idx:
+            x = shift % zk.P * pow(h, i, zk.P) % zk.P
+            want = 0
+            for c in reversed(coeffs.tolist()):
+                want = (want * x + c) % zk.P
+            assert int(got[i]) == want

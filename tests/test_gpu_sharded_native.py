@@ -91,5 +91,5 @@ def test_native_nccl_two_processes(tmp_path):
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "large_digests.json")))
     for r in range(2):
         o = json.load(open(tmp_path / f"out{r}.json"))
-        assert o["sha256"] == gold[str(log_n)]["sha256"]
+        assert o["transcript_sha256"] == gold[str(log_n)]["sha256"]
         assert o["state"] == gold[str(log_n)]["state"]

@@ -55,6 +55,7 @@ def lib():
         "zk_ctx_last_stage_ms": ([vp, vp], i32),
         "zk_ctx_set_stage_timing": ([vp, i32], i32),
         "zk_ctx_set_memory_budget": ([vp, sz], i32),
+        "zk_ctx_trim": ([vp, i32], i32),
         "zk_interpolate_subgroup": ([vp, vp, u32, u32, vp], i32),
         "zk_lde_coset": ([vp, vp, u32, u32, u32, vp], i32),
         "zk_fri_fold": ([vp, vp, u64, u32, u32, vp], i32),
@@ -68,6 +69,8 @@ def lib():
         "zk_prove_fibsq_batch": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_trace_fibsq": ([u32, u32, vp], i32),
         "zk_prove_fibsq_batch_secrets": ([vp, u32, u32, vp, vp, vp], i32),
+        "zk_prove_stream_submit": ([vp, u32, u32, vp], i32),
+        "zk_prove_stream_collect": ([vp, vp, vp], i32),
         "zk_verify_fibsq": ([u32, u32, vp, sz, vp, i32, C.POINTER(i32)], i32),
         "zk_interpolate_subgroup_dev": ([vp, vp, u32, u32, vp], i32),
         "zk_lde_coset_dev": ([vp, vp, u32, u32, u32, vp], i32),
@@ -341,10 +344,34 @@ class Context:
         self._ck(lib().zk_prove_fibsq_batch_secrets(self._h, log_n, nb, _p(secrets), _p(tr), _p(st)))
         return tr, st
 
+    def prove_stream_submit(self, log_n, secrets):
+        secrets = _u32(secrets)
+        self._ck(lib().zk_prove_stream_submit(self._h, log_n, len(secrets), _p(secrets)))
+
+    def prove_stream_collect_ptr(self, transcripts_ptr, states_ptr):
+        self._ck(lib().zk_prove_stream_collect(self._h, C.c_void_p(transcripts_ptr), C.c_void_p(states_ptr)))
+
+    def prove_stream_collect(self, log_n, n_proofs):
+        tl = transcript_len(log_n)
+        tr = np.empty((n_proofs, tl), dtype=np.uint8)
+        st = np.empty((n_proofs, 32), dtype=np.uint8)
+        self.prove_stream_collect_ptr(tr.ctypes.data, st.ctypes.data)
+        return tr, st
+
     # ---- raw-pointer entry points (device memory owned by the caller, e.g. torch tensors)
     def prove_fibsq_batch_ptr(self, log_n, n_proofs, traces_host_ptr, transcripts_ptr, states_ptr):
         self._ck(lib().zk_prove_fibsq_batch(self._h, log_n, n_proofs, C.c_void_p(traces_host_ptr),
                                             C.c_void_p(transcripts_ptr), C.c_void_p(states_ptr)))
+
+    def prove_fibsq_batch_secrets_ptr(self, log_n, n_proofs, secrets_host_ptr, transcripts_ptr, states_ptr):
+        self._ck(lib().zk_prove_fibsq_batch_secrets(self._h, log_n, n_proofs, C.c_void_p(secrets_host_ptr),
+                                                    C.c_void_p(transcripts_ptr), C.c_void_p(states_ptr)))
+
+    def prove_fibsq_from_trace_ptr(self, log_n, trace_host_ptr, transcript_ptr, cap, state_ptr):
+        n = C.c_size_t(0)
+        self._ck(lib().zk_prove_fibsq_from_trace(self._h, log_n, C.c_void_p(trace_host_ptr), C.c_void_p(transcript_ptr), cap,
+                                                 C.byref(n), C.c_void_p(state_ptr)))
+        return n.value
 
     def prove_fibsq_resident_ptr(self, log_n, n_proofs, traces_dev_ptr, transcripts_ptr, states_ptr):
         self._ck(lib().zk_prove_fibsq_resident(self._h, log_n, n_proofs, C.c_void_p(traces_dev_ptr),
@@ -445,6 +472,9 @@ class Context:
 
     def bench_set(self, sha_variant=-1, leaf_pass_k=0):
         self._ck(lib().zk_bench_set(self._h, sha_variant, leaf_pass_k))
+
+    def trim(self, tables_too=False):
+        self._ck(lib().zk_ctx_trim(self._h, int(tables_too)))
 
     def set_memory_budget(self, nbytes):
         self._ck(lib().zk_ctx_set_memory_budget(self._h, nbytes))

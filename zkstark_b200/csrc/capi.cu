@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <cstdlib>
+#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -419,6 +420,14 @@ uint32_t pick_subbatch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs)
                       ctx->f_heap.bytes + ctx->layer_heaps.bytes + ctx->states.bytes + ctx->transcripts.bytes;
         budget = (size_t)((fr + held) * 0.7);
     }
+    // the per-size constant tables of the composition polynomial (12 N bytes, once per size) come out of the same budget
+    // when they are not built yet
+    {
+        auto it = ctx->tabs.find(log_n + LOG_BLOWUP);
+        const bool have = it != ctx->tabs.end() && it->second.cp_tab.p;
+        const size_t tab = ctx->use_cp_tab && !have ? (size_t)12 << (log_n + LOG_BLOWUP) : 0;
+        budget = budget > tab ? budget - tab : 0;
+    }
     size_t per = per_proof_bytes(log_n);
     size_t nb = budget / per;
     if (nb < 1) nb = 1;
@@ -463,6 +472,8 @@ int zk_ctx_create_on_stream(int device, void* cuda_stream, zk_ctx** out)
     for (int i = 0; i < 8; i++)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
     { const char* e = getenv("ZK_NO_LANES"); if (e && e[0] == '1') ctx->lanes = false; }
+    { const char* e = getenv("ZK_TRACE_DEVICE"); if (e && e[0] == '1') ctx->trace_on_device = true; }
+    { const char* e = getenv("ZK_HOST_THREADS"); if (e) ctx->host_threads = (uint32_t)atoi(e); }
     if (cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
@@ -493,6 +504,14 @@ void zk_ctx_destroy(zk_ctx* ctx)
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->lane_stream) { cudaStreamSynchronize(ctx->lane_stream); cudaStreamDestroy(ctx->lane_stream); }
+    if (ctx->trace_stream) { cudaStreamSynchronize(ctx->trace_stream); cudaStreamDestroy(ctx->trace_stream); }
+    for (auto& sl : ctx->slot) {
+        if (sl.worker.joinable()) sl.worker.join();
+        sl.traces.release();
+        sl.secrets.release();
+        if (sl.pinned) cudaFreeHost(sl.pinned);
+        if (sl.ready) cudaEventDestroy(sl.ready);
+    }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -519,6 +538,35 @@ int zk_ctx_last_stage_ms(zk_ctx* ctx, float out_ms[7])
     for (int i = 0; i < 7; i++) out_ms[i] = ctx->stage_ms[i];
     return ZK_OK;
 }
+int zk_ctx_trim(zk_ctx* ctx, int tables_too)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->lane_stream) CK(cudaStreamSynchronize(ctx->lane_stream));
+    if (ctx->trace_stream) CK(cudaStreamSynchronize(ctx->trace_stream));
+    if (ctx->slot_count) return fail(ctx, ZK_ERR_INVALID, "batches are still in flight (zk_prove_stream_collect them first)");
+    DevBuf* bufs[] = {&ctx->s0, &ctx->s1, &ctx->s2, &ctx->flushbuf, &ctx->traces, &ctx->coeffs, &ctx->work, &ctx->f_eval, &ctx->layers,
+                      &ctx->f_heap, &ctx->layer_heaps, &ctx->states, &ctx->transcripts, &ctx->slot[0].traces, &ctx->slot[1].traces};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& sl : ctx->slot) {
+        if (sl.pinned) cudaFreeHost(sl.pinned);
+        sl.pinned = nullptr;
+        sl.pinned_bytes = 0;
+    }
+    ctx->w_log_n = ctx->w_batch = 0;
+    ctx->last_nb = 0;
+    if (tables_too) {
+        for (auto& kv : ctx->tabs) { free_powtab(kv.second.h); free_powtab(kv.second.w); kv.second.cp_tab.release(); }
+        ctx->tabs.clear();
+        for (auto& kv : ctx->shift_tabs) free_powtab(kv.second);
+        ctx->shift_tabs.clear();
+    } else {
+        for (auto& kv : ctx->tabs) kv.second.cp_tab.release();   // 12 N bytes each: rebuilt on the next prove of that size
+    }
+    return ZK_OK;
+}
+
 int zk_ctx_set_memory_budget(zk_ctx* ctx, size_t bytes)
 {
     if (!ctx) return ZK_ERR_INVALID;
@@ -806,25 +854,127 @@ int zk_prove_fibsq_batch(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const u
     return ZK_OK;
 }
 
+int zk_prove_stream_submit(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t* secrets);
+int zk_prove_stream_collect(zk_ctx* ctx, uint8_t* transcripts_out, uint8_t* states_out);
 int zk_prove_fibsq_batch_secrets(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t* secrets,
                                  uint8_t* transcripts_out, uint8_t* states_out)
 {
     int rc = check_log_n(ctx, log_n);
     if (rc) return rc;
     if (!secrets || !transcripts_out || !states_out || n_proofs == 0) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (ctx->slot_count) return fail(ctx, ZK_ERR_INVALID, "batches of zk_prove_stream_submit are in flight: collect them first");
     CK(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)1 << log_n, trl = transcript_len(log_n);
+    const size_t trl = transcript_len(log_n);
+    // sub-batches go through the submit / collect pipeline: the traces of sub-batch j + 1 are produced while j is proved
     const uint32_t nbmax = pick_subbatch(ctx, log_n, n_proofs);
-    if ((rc = ensure_workspace(ctx, log_n, nbmax))) return rc;
-    CK(ctx->s0.ensure(4 * (size_t)nbmax));
+    auto count = [&](uint32_t done) { return n_proofs - done < nbmax ? n_proofs - done : nbmax; };
+    if ((rc = zk_prove_stream_submit(ctx, log_n, count(0), secrets))) return rc;
     for (uint32_t done = 0; done < n_proofs; done += nbmax) {
-        uint32_t nb = n_proofs - done < nbmax ? n_proofs - done : nbmax;
-        CK(cudaMemcpyAsync(ctx->s0.p, secrets + done, 4 * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
-        CK(launch_trace_batch(ctx->stream, (const uint32_t*)ctx->s0.p, (uint32_t*)ctx->traces.p, n, log_n, nb));
-        ctx->launches += 1;
-        if ((rc = prove_subbatch(ctx, log_n, nb, transcripts_out + trl * done, states_out + 32 * (size_t)done))) return rc;
+        const uint32_t next = done + nbmax;
+        if (next < n_proofs && (rc = zk_prove_stream_submit(ctx, log_n, count(next), secrets + next))) break;
+        if ((rc = zk_prove_stream_collect(ctx, transcripts_out + trl * done, states_out + 32 * (size_t)done))) break;
     }
+    if (rc) {   // drain what is still in flight (results are discarded; the caller sees the first error)
+        const std::string keep = ctx->err;
+        while (ctx->slot_count) {
+            zk_ctx::StreamSlot& sl = ctx->slot[ctx->slot_head];
+            if (sl.worker.joinable()) sl.worker.join();
+            ctx->slot_head ^= 1;
+            ctx->slot_count--;
+        }
+        if (ctx->trace_stream) cudaStreamSynchronize(ctx->trace_stream);
+        ctx->err = keep;
+    }
+    return rc;
+}
+
+// ---- pipelined secrets -> proofs.  The FibonacciSq recurrence (prover.rs:32-39) is one dependent squaring per step: a 2^20
+// trace costs ~7.5 ms on a host core and ~95 ms as a lone GPU thread, whatever the batch size -- against ~4 ms of proving
+// per proof.  It is therefore produced on the HOST, one trace per thread over all cores, one batch AHEAD of the proving:
+// submit() starts the worker threads of a batch (each writes its rows into pinned memory and enqueues their upload on a
+// side stream), collect() proves the oldest submitted batch.  With one batch submitted ahead, trace generation and upload
+// disappear behind the previous batch's hashing.  (ZK_TRACE_DEVICE=1: the traces are generated by trace_batch_kernel on
+// the side stream instead -- one GPU thread per proof; pays only for very many short traces.)
+static void stream_worker(zk_ctx* ctx, zk_ctx::StreamSlot* sl)
+{
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)1 << sl->log_n;
+    uint32_t T = ctx->host_threads ? ctx->host_threads : std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > sl->n) T = sl->n;
+    std::vector<cudaError_t> errs(T, cudaSuccess);
+    auto body = [&](uint32_t t) {
+        cudaSetDevice(ctx->device);
+        for (uint32_t b = t; b < sl->n; b += T) {
+            uint32_t* row = (uint32_t*)sl->pinned + n * b;
+            zk_trace_fibsq(sl->log_n, sl->host_secrets[b], row);
+            cudaError_t e = cudaMemcpyAsync((uint32_t*)sl->traces.p + n * b, row, 4 * (n - 1), cudaMemcpyHostToDevice, ctx->trace_stream);
+            if (e != cudaSuccess) errs[t] = e;
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < T; t++) th.emplace_back(body, t);
+    body(0);
+    for (auto& x : th) x.join();
+    sl->err = cudaSuccess;
+    for (cudaError_t e : errs) if (e != cudaSuccess) sl->err = e;
+    cudaError_t e = cudaEventRecord(sl->ready, ctx->trace_stream);
+    if (e != cudaSuccess) sl->err = e;
+}
+
+int zk_prove_stream_submit(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t* secrets)
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!secrets || n_proofs == 0) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (ctx->slot_count >= 2) return fail(ctx, ZK_ERR_INVALID, "two batches are already in flight: collect one first");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->trace_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CK(cudaStreamCreateWithPriority(&ctx->trace_stream, cudaStreamNonBlocking, hi));
+    }
+    zk_ctx::StreamSlot& sl = ctx->slot[(ctx->slot_head + ctx->slot_count) & 1];
+    const size_t n = (size_t)1 << log_n;
+    if (!sl.ready) CK(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+    CK(sl.traces.ensure(4 * n * n_proofs));
+    sl.host_secrets.assign(secrets, secrets + n_proofs);   // the caller's array may go away before the workers read it
+    sl.log_n = log_n;
+    sl.n = n_proofs;
+    sl.err = cudaSuccess;
+    if (ctx->trace_on_device) {
+        CK(sl.secrets.ensure(4 * (size_t)n_proofs));
+        CK(cudaMemcpyAsync(sl.secrets.p, sl.host_secrets.data(), 4 * (size_t)n_proofs, cudaMemcpyHostToDevice, ctx->trace_stream));
+        CK(launch_trace_batch(ctx->trace_stream, (const uint32_t*)sl.secrets.p, (uint32_t*)sl.traces.p, n, log_n, n_proofs));
+        CK(cudaEventRecord(sl.ready, ctx->trace_stream));
+        ctx->launches += 1;
+    } else {
+        if (sl.pinned_bytes < 4 * n * n_proofs) {
+            if (sl.pinned) cudaFreeHost(sl.pinned);
+            sl.pinned = nullptr;
+            sl.pinned_bytes = 0;
+            CK(cudaMallocHost(&sl.pinned, 4 * n * n_proofs));
+            sl.pinned_bytes = 4 * n * n_proofs;
+        }
+        sl.worker = std::thread(stream_worker, ctx, &sl);
+    }
+    ctx->slot_count++;
     return ZK_OK;
+}
+
+int zk_prove_stream_collect(zk_ctx* ctx, uint8_t* transcripts_out, uint8_t* states_out)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!transcripts_out || !states_out) return fail(ctx, ZK_ERR_INVALID, "null buffer");
+    if (ctx->slot_count == 0) return fail(ctx, ZK_ERR_INVALID, "nothing submitted");
+    CK(cudaSetDevice(ctx->device));
+    zk_ctx::StreamSlot& sl = ctx->slot[ctx->slot_head];
+    ctx->slot_head ^= 1;
+    ctx->slot_count--;
+    if (sl.worker.joinable()) sl.worker.join();        // usually long finished: its batch was submitted one collect ago
+    if (sl.err != cudaSuccess) return fail_cuda(ctx, sl.err, "trace upload");
+    CK(cudaStreamWaitEvent(ctx->stream, sl.ready, 0));
+    return zk_prove_fibsq_resident(ctx, sl.log_n, sl.n, (const uint32_t*)sl.traces.p, transcripts_out, states_out);
 }
 
 int zk_prove_fibsq_from_trace(zk_ctx* ctx, uint32_t log_n, const uint32_t* trace, uint8_t* transcript_out, size_t cap,
@@ -1002,7 +1152,7 @@ int zk_shard_cp_blocks_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t*
                            uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev, uint32_t* cp_local,
                            uint8_t* heap_local)
 {
-    return zkh::shard_cp_blocks(ctx, f_local, halo, 0, local_len, log_n, n_ranks, rank, log_block, state_dev, cp_local, heap_local);
+    return zkh::shard_cp_blocks(ctx, f_local, halo, 0, local_len, log_n, n_ranks, rank, log_block, state_dev, cp_local, heap_local, nullptr);
 }
 }  // extern "C"
 
@@ -1010,7 +1160,7 @@ int zk_shard_cp_blocks_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t*
 // block that follows local block bl is rank 0's block bl + 1 (wrapping around the whole domain)
 int zkh::shard_cp_blocks(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, uint32_t halo_roll, uint64_t local_len,
                          uint32_t log_n, uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev,
-                         uint32_t* cp_local, uint8_t* heap_local)
+                         uint32_t* cp_local, uint8_t* heap_local, DevBuf* tab_cache)
 {
     int rc = check_log_n(ctx, log_n);
     if (rc) return rc;
@@ -1041,6 +1191,16 @@ int zkh::shard_cp_blocks(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* h
     a.heap = heap_local;
     a.log_size = lg;
     int nl = 0;
+    if (tab_cache && ctx->use_cp_tab) {
+        // rank-local slice of the per-size constant tables (CpArgs::tab), in local order: 12 bytes per local point, built
+        // once per (communicator, size) -- the caller keeps tab_cache for exactly one geometry
+        if (!tab_cache->p && tab_cache->ensure(12 * local_len) == cudaSuccess) {
+            CK(launch_cp_tables(ctx->stream, (uint32_t*)tab_cache->p, a.cp, T->h.tab));
+            nl++;
+        }
+        cudaGetLastError();
+        a.cp.tab = (const uint32_t*)tab_cache->p;   // null when the allocation failed: the per-point form is used
+    }
     CK(launch_merkle_partial(ctx->stream, SRC_CP, a, 1, lg - log_block, &nl));
     ctx->launches += nl;
     return ZK_OK;

@@ -5,6 +5,7 @@
 
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zkstark_b200.h"
@@ -113,10 +114,21 @@ struct zk_ctx {
     float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // pipelined secrets -> proofs stream (zk_prove_stream_*)
-    struct StreamSlot { zkh::DevBuf traces, secrets; cudaEvent_t ready = nullptr; uint32_t log_n = 0, n = 0; bool full = false; };
+    struct StreamSlot {
+        zkh::DevBuf traces, secrets;
+        std::vector<uint32_t> host_secrets;
+        void* pinned = nullptr;            // host traces of the batch (rows of n words), written by the worker threads
+        size_t pinned_bytes = 0;
+        std::thread worker;                // produces + uploads the traces; joined by collect
+        cudaError_t err = cudaSuccess;
+        cudaEvent_t ready = nullptr;       // recorded on trace_stream behind the last upload
+        uint32_t log_n = 0, n = 0;
+    };
     StreamSlot slot[2];
     uint32_t slot_head = 0, slot_count = 0;
     cudaStream_t trace_stream = nullptr;
+    bool trace_on_device = false;          // ZK_TRACE_DEVICE=1
+    uint32_t host_threads = 0;             // ZK_HOST_THREADS (0: all hardware threads)
 };
 
 namespace zkh {
@@ -142,6 +154,6 @@ void finish_channel_host(uint32_t log_n, const zk::ProofState& ps, const uint8_t
 int check_log_n(zk_ctx* ctx, uint32_t log_n);
 int shard_cp_blocks(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, uint32_t halo_roll, uint64_t local_len,
                     uint32_t log_n, uint32_t n_ranks, uint32_t rank, uint32_t log_block, const void* state_dev,
-                    uint32_t* cp_local, uint8_t* heap_local);
+                    uint32_t* cp_local, uint8_t* heap_local, DevBuf* tab_cache);
 
 }  // namespace zkh

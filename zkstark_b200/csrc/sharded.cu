@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(256) shard_max_kernel(MaxPtrs ptrs, uint32_t G
 struct RankBufs {
     uint32_t rank = 0;
     DevBuf state, transcript, y, coeffs, work, send, recv, f_local, layers, heap_f, heap_layers, upper, stage, heads, halo,
-        tail_vals, tail_heaps;
+        tail_vals, tail_heaps, cp_tab;
+    uint32_t cp_tab_log_n = 0, cp_tab_lb = 0;   // the geometry cp_tab was built for
 };
 
 enum Phase { PH_START = 0, PH_INTERP, PH_LDE, PH_A2A, PH_UNPACK, PH_FTREE, PH_HALO, PH_CPTREE, PH_FRI, PH_TAIL, PH_DECOMMIT, PH_END, PH_COUNT };
@@ -468,8 +469,11 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
     for (RankBufs& b : cm->rk) {
         // the block after local block bl of the LAST rank is rank 0's block bl + 1 (wrapping around the domain)
         const uint32_t roll = (b.rank + 1 == g.G) ? 1u : 0u;
+        if (b.cp_tab.p && (b.cp_tab_log_n != log_n || b.cp_tab_lb != g.lb)) b.cp_tab.release();   // another geometry: rebuild
+        b.cp_tab_log_n = log_n;
+        b.cp_tab_lb = g.lb;
         if ((rc = shard_cp_blocks(ctx, (const uint32_t*)b.f_local.p, (const uint32_t*)b.halo.p, roll, g.Nloc, log_n, g.G, b.rank, g.lb,
-                                  b.state.p, (uint32_t*)b.layers.p, (uint8_t*)b.heap_layers.p)))
+                                  b.state.p, (uint32_t*)b.layers.p, (uint8_t*)b.heap_layers.p, &b.cp_tab)))
             return rc;
         heaps.push_back((uint8_t*)b.heap_layers.p);
     }
@@ -634,7 +638,7 @@ void zk_shard_comm_destroy(zk_shard_comm* cm)
     if (cm->nccl && nccl_api()) nccl_api()->CommDestroy(cm->nccl);
     for (RankBufs& b : cm->rk) {
         DevBuf* bufs[] = {&b.state, &b.transcript, &b.y, &b.coeffs, &b.work, &b.send, &b.recv, &b.f_local, &b.layers, &b.heap_f,
-                          &b.heap_layers, &b.upper, &b.stage, &b.heads, &b.halo, &b.tail_vals, &b.tail_heaps};
+                          &b.heap_layers, &b.upper, &b.stage, &b.heads, &b.halo, &b.tail_vals, &b.tail_heaps, &b.cp_tab};
         for (DevBuf* d : bufs) d->release();
     }
     for (int i = 0; i < PH_COUNT; i++) if (cm->ev[i]) cudaEventDestroy(cm->ev[i]);

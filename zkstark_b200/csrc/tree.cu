@@ -204,12 +204,31 @@ __device__ __forceinline__ void cp_coef_tab(const uint32_t alpha_raw[3], uint32_
     k.a_first = a_first;
     k.a_last = a_last;
 }
+// f at local index i + off (off = 8 or 16): inside the local block, else in the 16-value head of the block that follows it
+// globally (CpArgs::halo), else -- not sharded -- modulo the domain
+__device__ __forceinline__ uint32_t cp_neighbor(const CpArgs& c, const uint32_t* f, uint32_t i, uint32_t off)
+{
+    if (c.halo == nullptr) return f[(i + off) & ((1u << c.log_len) - 1u)];
+    const uint32_t blk_mask = (1u << c.shard.log_block) - 1u, t = i & blk_mask;
+    if (t + off <= blk_mask) return f[i + off];
+    const uint32_t bl = ((i >> c.shard.log_block) + c.halo_roll) & c.halo_mask;
+    return c.halo[bl * 16 + (t + off - blk_mask - 1)];
+}
+// the same for four consecutive points starting at a multiple of four: the four neighbours are in one place
+__device__ __forceinline__ uint4 cp_neighbor4(const CpArgs& c, const uint32_t* f, uint32_t i, uint32_t off)
+{
+    if (c.halo == nullptr) return *reinterpret_cast<const uint4*>(f + ((i + off) & ((1u << c.log_len) - 1u)));
+    const uint32_t blk_mask = (1u << c.shard.log_block) - 1u, t = i & blk_mask;
+    if (t + off <= blk_mask) return *reinterpret_cast<const uint4*>(f + i + off);
+    const uint32_t bl = ((i >> c.shard.log_block) + c.halo_roll) & c.halo_mask;
+    return *reinterpret_cast<const uint4*>(c.halo + bl * 16 + (t + off - blk_mask - 1));
+}
 template <int C>
 __device__ __forceinline__ void cp_chunk_tab(const CpArgs& c, const uint32_t* f, uint32_t* out, uint32_t base,
                                              const CpCoefTab& k)
 {
     const uint32_t B = 1u << LOG_BLOWUP;
-    const uint32_t N = 1u << c.log_len, len_mask = N - 1u;
+    const uint32_t N = 1u << c.log_len;      // local points: the tables are in local order
     uint32_t fx[C], fg[C], fgg[C], ta[C], tb[C], tc[C];
     if (C >= 4) {
 #pragma unroll
@@ -218,8 +237,8 @@ __device__ __forceinline__ void cp_chunk_tab(const CpArgs& c, const uint32_t* f,
             const uint4 a = *reinterpret_cast<const uint4*>(c.tab + base + j);
             const uint4 b = *reinterpret_cast<const uint4*>(c.tab + N + base + j);
             const uint4 q = *reinterpret_cast<const uint4*>(c.tab + 2 * (size_t)N + base + j);
-            const uint4 v1 = *reinterpret_cast<const uint4*>(f + ((base + j + B) & len_mask));
-            const uint4 v2 = *reinterpret_cast<const uint4*>(f + ((base + j + 2 * B) & len_mask));
+            const uint4 v1 = cp_neighbor4(c, f, base + j, B);
+            const uint4 v2 = cp_neighbor4(c, f, base + j, 2 * B);
             fx[j] = v.x; fx[j + 1] = v.y; fx[j + 2] = v.z; fx[j + 3] = v.w;
             ta[j] = a.x; ta[j + 1] = a.y; ta[j + 2] = a.z; ta[j + 3] = a.w;
             tb[j] = b.x; tb[j + 1] = b.y; tb[j + 2] = b.z; tb[j + 3] = b.w;
@@ -231,7 +250,7 @@ __device__ __forceinline__ void cp_chunk_tab(const CpArgs& c, const uint32_t* f,
 #pragma unroll
         for (int j = 0; j < C; j++) {
             const uint32_t i = base + j;
-            fx[j] = f[i]; fg[j] = f[(i + B) & len_mask]; fgg[j] = f[(i + 2 * B) & len_mask];
+            fx[j] = f[i]; fg[j] = cp_neighbor(c, f, i, B); fgg[j] = cp_neighbor(c, f, i, 2 * B);
             ta[j] = c.tab[i]; tb[j] = c.tab[N + i]; tc[j] = c.tab[2 * (size_t)N + i];
         }
     }
@@ -258,10 +277,10 @@ __device__ __forceinline__ void cp_chunk_tab(const CpArgs& c, const uint32_t* f,
 __global__ void __launch_bounds__(256) cp_table_kernel(uint32_t* tab, CpArgs c, PowTab pw)
 {
     pdl_enter();
-    const uint32_t N = 1u << pw.log_N;
+    const uint32_t N = 1u << c.log_len;                                  // local points (== 2^log_N when not sharded)
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
-    const uint32_t x = mont_mul(GEN, pow_h_m(pw, i));                    // canonical 5 h^i
+    const uint32_t x = mont_mul(GEN, pow_h_m(pw, shard_global(c.shard, i)));   // canonical 5 h^i, i the GLOBAL index
     const uint32_t xm = to_mont(x);
     const uint32_t d0m = to_mont(fsub(x, 1u)), d1m = to_mont(fsub(x, c.g2));
     const uint32_t xn_m = mont_pow(xm, (uint64_t)1 << c.log_n);          // x^n, one of 8 values
@@ -273,7 +292,7 @@ __global__ void __launch_bounds__(256) cp_table_kernel(uint32_t* tab, CpArgs c, 
 }
 cudaError_t launch_cp_tables(cudaStream_t s, uint32_t* tab, CpArgs c, PowTab pow)
 {
-    const uint32_t N = 1u << pow.log_N;
+    const uint32_t N = 1u << c.log_len;
     return zk_launch(cp_table_kernel, dim3((N + 255) / 256), dim3(256), 0, s, tab, c, pow);
 }
 
