@@ -124,6 +124,16 @@ int zk_prove_stream_collect(zk_ctx *ctx, uint8_t *transcripts_out, uint8_t *stat
  * checks alpha / beta / query (and `state`, when given) -- the reference trusts the values in the proof. */
 int zk_verify_fibsq(uint32_t log_n, uint32_t a_last, const uint8_t *transcript, size_t len, const uint8_t *state,
                     int rederive, int *failed_check);
+/* SHA-256 of a host buffer (FIPS 180-4; SHA-NI when the CPU has it): what the reference takes from sha2 0.10.6 for its
+ * host-side Channel (channel.rs:21-24) and compute_root_from_path (merkle.rs:82-110), for hosts without a hash crate. */
+void zk_sha256(const uint8_t *data, size_t len, uint8_t out[32]);
+/* Wire format of `Proof { state, data }` (proof.rs:5-8) as bincode 1.x writes the struct: 32 state bytes, u64 LE length,
+ * transcript.  Host code.  zk_proof_deserialize checks the length prefix and returns a pointer INTO `bytes`. */
+size_t zk_proof_serialized_len(size_t transcript_len);
+int zk_proof_serialize(const uint8_t state[32], const uint8_t *transcript, size_t transcript_len, uint8_t *out, size_t cap,
+                       size_t *len_out);
+int zk_proof_deserialize(const uint8_t *bytes, size_t len, uint8_t state_out[32], const uint8_t **transcript_out,
+                         size_t *transcript_len_out);
 /* prover.rs:32-39: a[0] = 1, a[1] = secret, a[i] = a[i-2]^2 + a[i-1]^2; 2^log_n - 1 values (host) */
 int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t *trace_out);
 /* releases the proving work space, the scratch buffers and the per-size composition-polynomial tables (tables_too != 0:
@@ -241,6 +251,12 @@ int zk_shard_last_phase_ms(const zk_shard_comm *comm, float out_ms[12]);
 uint64_t zk_shard_last_comm_bytes(const zk_shard_comm *comm);
 /* index of the first FRI layer that ran in the replicated tail */
 uint32_t zk_shard_last_first_tail(const zk_shard_comm *comm);
+
+/* ---- K1 on its own: the device field arithmetic (csrc/field.cuh, replacing Gf<P> over num-modular, field.rs:96-211)
+ * applied element-wise to host arrays a, b of n raw u32 words, each reduced first as F::from(u32) does (field.rs:20-24).
+ * out: 6 rows of n canonical residues -- a + b, a - b, a * b, -a, a^-1 (0 for a = 0), a^b (exponent: the raw word b,
+ * Pow<u32>, field.rs:26-38).  For parity tests against the scalar Rust type; not on the proving path. */
+int zk_field_ops(zk_ctx *ctx, const uint32_t *a, const uint32_t *b, size_t n, uint32_t *out);
 
 /* ---- measurement support (bench.py): runs ONE hot-path kernel (or kernel group) `iters` times on
  * the ctx stream, each launch bracketed by CUDA events (optionally after an L2 flush that is not

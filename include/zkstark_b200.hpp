@@ -6,10 +6,11 @@
 //   reference (Rust)                                         here (namespace zk)
 //   Merkle::new(size, iter) / merkle[i] / merkle.trace(i)    Merkle::create(size, data) / m[i] / m.trace(i)   merkle.rs:14,54,74
 //   compute_root_from_path(element, index, &path)            compute_root_from_path(...)                      merkle.rs:82
-//   lagrange::<F>(&points)  (x_i = g^i)                      lagrange_subgroup(ys, log_n)                     polynomial.rs:337
+//   lagrange::<F>(&points)  (x_i = g^i)                      lagrange(points) / lagrange_subgroup(ys, log_n)  polynomial.rs:337
 //   f_poly.solve(x) over f_domain                            solve_on_coset(coeffs, log_n)                    prover.rs:69-70
 //   fri::<F>(&poly, beta) + solve on the squared domain      fri_fold(cur, layer_k, beta_raw)                 polynomial.rs:385
-//   Channel::new() / generate_proof(channel) -> Proof        Channel{} / generate_proof(channel, log_n)       prover.rs:9
+//   Channel::new() / commit / get_u32 / finalize             Channel{} / commit(..) / get_u32() / finalize()  channel.rs:11-37
+//   generate_proof(channel) -> Proof                         generate_proof(channel, log_n)                   prover.rs:9
 //   proof.verify() (panics) / proof.size()                   proof.verify() (throws) / proof.size()           proof.rs:15,151
 //
 // Errors: the reference panics (assert_eq!/unwrap); every failure here throws zk::Error.
@@ -19,6 +20,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "zkstark_b200.h"
@@ -132,10 +134,83 @@ inline std::vector<uint32_t> trace_fibsq(uint32_t log_n, uint32_t secret)
     return a;
 }
 
+// lagrange::<F>(&points) with the reference's own signature (polynomial.rs:337): points (x_i, y_i).  The GPU path
+// interpolates over the trace subgroup, so the abscissae must be x_i = g^i, g = 5^((p-1)/n), n the next power of two
+// >= points.size() -- what prover.rs:56-61 builds; anything else throws (there is no CPU fallback).  Ascending
+// coefficients without trailing zeros, i.e. `Polynomial.0` (polynomial.rs:15-28,31).
+inline std::vector<uint32_t> lagrange(const std::vector<std::pair<uint32_t, uint32_t>>& points)
+{
+    size_t n = 1;
+    uint32_t log_n = 0;
+    while (n < points.size()) { n <<= 1; log_n++; }
+    if (points.size() != n && points.size() != n - 1)
+        throw Error(ZK_ERR_INVALID, "lagrange on the GPU needs n or n - 1 points of the 2^k subgroup");
+    uint64_t g = 1, b = 5, e = (uint64_t(MODULUS) - 1) >> log_n;   // g = 5^((p-1)/n)  (prover.rs:48)
+    for (; e; e >>= 1, b = b * b % MODULUS)
+        if (e & 1) g = g * b % MODULUS;
+    std::vector<uint32_t> ys(points.size());
+    uint64_t x = 1;
+    for (size_t i = 0; i < points.size(); i++, x = x * g % MODULUS) {
+        if (points[i].first != x) throw Error(ZK_ERR_INVALID, "lagrange on the GPU needs abscissae g^i (prover.rs:56-61)");
+        ys[i] = points[i].second;
+    }
+    std::vector<uint32_t> c = lagrange_subgroup(ys, log_n);
+    while (!c.empty() && c.back() == 0) c.pop_back();
+    return c;
+}
+
 // ---------------------------------------------------------------- channel.rs / proof.rs / prover.rs
-struct Channel {  // channel.rs:6-17: only Channel::new() (zero state, empty transcript) exists in the reference
-    Hash state{};
+struct Proof;
+// channel.rs:6-37 with bincode 1.x's layout of what prover.rs commits (u32: 4 bytes LE; [u8; 32]: raw; Box<[Hash]>: u64 LE
+// length + digests; tuples: concatenation).  SHA-256 is the library's host implementation (sha2 in the reference).
+struct Channel {
+    Hash state{};                 // channel.rs:12-17: Channel::new() is the zero state, empty transcript
     std::vector<uint8_t> data;
+
+    void commit_bytes(const std::vector<uint8_t>& v)   // channel.rs:19-26
+    {
+        std::vector<uint8_t> msg(state.begin(), state.end());
+        msg.insert(msg.end(), v.begin(), v.end());
+        zk_sha256(msg.data(), msg.size(), state.data());
+        data.insert(data.end(), v.begin(), v.end());
+    }
+    void commit(const Hash& h) { commit_bytes(std::vector<uint8_t>(h.begin(), h.end())); }
+    void commit(uint32_t v) { std::vector<uint8_t> b; put_u32(b, v); commit_bytes(b); }
+    void commit(uint32_t v, const AuthPath& p)         // prover.rs:274-277: (value, path)
+    {
+        std::vector<uint8_t> b;
+        put_u32(b, v);
+        put_path(b, p);
+        commit_bytes(b);
+    }
+    void commit(uint32_t a, uint32_t b2, const AuthPath& p, const AuthPath& q)   // prover.rs:288: (cp_x, cp_nx, path, path)
+    {
+        std::vector<uint8_t> b;
+        put_u32(b, a);
+        put_u32(b, b2);
+        put_path(b, p);
+        put_path(b, q);
+        commit_bytes(b);
+    }
+    uint32_t get_u32()                                 // channel.rs:28-32: big-endian read, un-reduced, committed
+    {
+        const uint32_t f = (uint32_t(state[0]) << 24) | (uint32_t(state[1]) << 16) | (uint32_t(state[2]) << 8) | state[3];
+        commit(f);
+        return f;
+    }
+    inline Proof finalize() const;                     // channel.rs:34-36
+
+private:
+    static void put_u32(std::vector<uint8_t>& b, uint32_t v)
+    {
+        for (int i = 0; i < 4; i++) b.push_back(uint8_t(v >> (8 * i)));
+    }
+    static void put_path(std::vector<uint8_t>& b, const AuthPath& p)
+    {
+        const uint64_t n = p.size();
+        for (int i = 0; i < 8; i++) b.push_back(uint8_t(n >> (8 * i)));
+        for (const Hash& h : p) b.insert(b.end(), h.begin(), h.end());
+    }
 };
 
 struct Proof {  // proof.rs:5-13
@@ -151,7 +226,36 @@ struct Proof {  // proof.rs:5-13
         if (rc != ZK_OK) throw Error(rc, "proof rejected: the assert at proof.rs:" + std::to_string(line) + " fails");
     }
     size_t size() const { return 48 + data.size(); }  // proof.rs:151-154 (size_of::<Proof>() == 48)
+    // wire format: what bincode 1.x writes for the struct (32 state bytes, u64 LE length, data)
+    std::vector<uint8_t> to_bytes() const
+    {
+        std::vector<uint8_t> out(zk_proof_serialized_len(data.size()));
+        size_t n = 0;
+        int rc = zk_proof_serialize(state.data(), data.data(), data.size(), out.data(), out.size(), &n);
+        if (rc != ZK_OK) throw Error(rc, "zk_proof_serialize");
+        out.resize(n);
+        return out;
+    }
+    static Proof from_bytes(const std::vector<uint8_t>& blob, uint32_t log_n = 10, uint32_t a_last = 2338775057u)
+    {
+        Proof p;
+        const uint8_t* tr = nullptr;
+        size_t n = 0;
+        int rc = zk_proof_deserialize(blob.data(), blob.size(), p.state.data(), &tr, &n);
+        if (rc != ZK_OK) throw Error(rc, rc == ZK_ERR_BUFFER ? "truncated proof" : "proof length prefix does not match the payload");
+        p.data.assign(tr, tr + n);
+        p.log_n = log_n;
+        p.a_last = a_last;
+        return p;
+    }
 };
+inline Proof Channel::finalize() const
+{
+    Proof p;
+    p.state = state;
+    p.data = data;
+    return p;
+}
 
 // generate_proof(channel) (prover.rs:9-293), generalised to n = 2^log_n; the reference is log_n = 10, secret 3141592.
 inline Proof generate_proof(const Channel& channel, uint32_t log_n = 10, uint32_t secret = 3141592u)

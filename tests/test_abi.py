@@ -8,6 +8,8 @@ import pytest
 
 import zkstark_b200 as zk
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_library_built_in_tree():
     assert os.path.exists(zk.LIB_PATH), "run __graft_entry__.build() first"
@@ -99,3 +101,35 @@ def test_host_sha256_matches_hashlib():
         out = ctypes.create_string_buffer(32)
         f(d, n, out)
         assert out.raw == hashlib.sha256(d).digest(), n
+
+
+def test_rust_ffi_matches_header():
+    """bindings/rust/src/ffi.rs declares every export of the header, and is what tools/gen_rust_ffi.py generates."""
+    import re
+    import subprocess
+    import sys
+    ffi = open(os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (zk_[a-z0-9_]+)\(", ffi))
+    assert declared == set(zk.header_symbols())
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py"), "--check"]) == 0
+    gpu = open(os.path.join(ROOT, "bindings", "rust", "src", "gpu.rs")).read()
+    for name in set(re.findall(r"ffi::(zk_[a-z0-9_]+)\(", gpu)):
+        assert name in declared, name
+
+
+def test_rust_patches_apply(tmp_path):
+    """The level-2 patches apply cleanly to the reference tree (only where the reference is present: not on the GPU box)."""
+    import shutil
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "src")) or shutil.which("patch") is None:
+        pytest.skip("no reference checkout / patch(1) here")
+    work = tmp_path / "ref"
+    shutil.copytree(ref, work, ignore=shutil.ignore_patterns(".git"))
+    for p in ("01_hooks.patch", "02_prover_eval_loops.patch"):
+        r = subprocess.run(["patch", "-p1", "-d", str(work), "-i", os.path.join(ROOT, "bindings", "rust", "patches", p)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    src = (work / "src" / "polynomial.rs").read_text()
+    assert "crate::gpu::lagrange_hook(points)" in src and "pub fn lagrange<T>(points: &Vec<(T, T)>) -> Polynomial<T>" in src
+    assert "pub fn new(mut size: usize, data: impl Iterator<Item = u32>) -> Self" in (work / "src" / "merkle.rs").read_text()

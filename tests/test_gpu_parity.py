@@ -397,3 +397,37 @@ def test_lde_other_coset_shift(ctx, orc):
             for c in reversed(coeffs.tolist()):
                 want = (want * x + c) % zk.P
             assert int(got[i]) == want
+
+
+def test_field_ops_direct(ctx, orc):
+    """K1 directly: device fadd / fsub / mont_mul / fneg / mont_inv / mont_pow (csrc/field.cuh) against oracle/field.c
+    (field.rs:96-211) on the full edge grid and on 2^20 random pairs."""
+    P = zk.P
+    L = orc.lib()
+    edge = [0, 1, 2, P - 2, P - 1, P, P + 1, 1 << 31, (1 << 31) + 1, 0xFFFFFFFF]   # raw words: >= p are reduced first (field.rs:20-24)
+    ga = np.array([a for a in edge for _ in edge], dtype=np.uint32)
+    gb = np.array([b for _ in edge for b in edge], dtype=np.uint32)
+    out = ctx.field_ops(ga, gb)
+    for i, (a, b) in enumerate(zip(ga.tolist(), gb.tolist())):
+        x, y = a % P, b % P
+        assert int(out[0, i]) == L.orc_add(x, y, P)
+        assert int(out[1, i]) == L.orc_sub(x, y, P)
+        assert int(out[2, i]) == L.orc_mul(x, y, P)
+        assert int(out[3, i]) == (P - x) % P
+        assert int(out[4, i]) == (L.orc_inv(x, P) if x else 0)
+        assert int(out[5, i]) == L.orc_pow(x, b, P)
+    rng = np.random.default_rng(2026)
+    n = 1 << 20
+    a = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    out = ctx.field_ops(a, b)
+    x, y = a.astype(np.uint64) % P, b.astype(np.uint64) % P
+    assert np.array_equal(out[0], ((x + y) % P).astype(np.uint32))
+    assert np.array_equal(out[1], ((x + P - y) % P).astype(np.uint32))
+    assert np.array_equal(out[2], ((x * y) % P).astype(np.uint32))             # < 2^64: exact in uint64
+    assert np.array_equal(out[3], ((P - x) % P).astype(np.uint32))
+    assert np.array_equal((out[4].astype(np.uint64) * x) % P, (x != 0).astype(np.uint64))   # a * a^-1 = 1
+    for i in range(0, n, n // 2048):                                                # oracle on a sample of inv / pow
+        xi = int(x[i])
+        assert int(out[4, i]) == (L.orc_inv(xi, P) if xi else 0)
+        assert int(out[5, i]) == L.orc_pow(xi, int(b[i]), P) == pow(xi, int(b[i]), P)

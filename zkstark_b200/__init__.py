@@ -20,6 +20,8 @@ from ._binding import (  # noqa: F401
     transcript_len,
     trace_fibsq,
     merkle_trace_host,
+    proof_serialize,
+    proof_deserialize,
     verify_fibsq,
 )
 from .api import (  # noqa: F401

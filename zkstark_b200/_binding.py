@@ -71,6 +71,11 @@ def lib():
         "zk_prove_fibsq_batch_secrets": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_prove_stream_submit": ([vp, u32, u32, vp], i32),
         "zk_prove_stream_collect": ([vp, vp, vp], i32),
+        "zk_sha256": ([vp, sz, vp], None),
+        "zk_field_ops": ([vp, vp, vp, sz, vp], i32),
+        "zk_proof_serialized_len": ([sz], sz),
+        "zk_proof_serialize": ([vp, vp, sz, vp, sz, C.POINTER(sz)], i32),
+        "zk_proof_deserialize": ([vp, sz, vp, C.POINTER(vp), C.POINTER(sz)], i32),
         "zk_verify_fibsq": ([u32, u32, vp, sz, vp, i32, C.POINTER(i32)], i32),
         "zk_interpolate_subgroup_dev": ([vp, vp, u32, u32, vp], i32),
         "zk_lde_coset_dev": ([vp, vp, u32, u32, u32, vp], i32),
@@ -151,6 +156,31 @@ def verify_fibsq(log_n, a_last, transcript, state=None, rederive=True):
     if rc not in (0, -6):
         raise ZkError(rc, "zk_verify_fibsq: invalid argument")
     return rc == 0, fc.value
+
+
+def proof_serialize(state, transcript):
+    """`Proof { state, data }` -> bytes (bincode 1.x struct layout; zk_proof_serialize)."""
+    cap = lib().zk_proof_serialized_len(len(transcript))
+    out = (C.c_uint8 * cap)()
+    n = C.c_size_t(0)
+    rc = lib().zk_proof_serialize(bytes(state), bytes(transcript), len(transcript), out, cap, C.byref(n))
+    if rc:
+        raise ZkError(rc, "zk_proof_serialize")
+    return bytes(out[: n.value])
+
+
+def proof_deserialize(blob):
+    """bytes -> (state, transcript); raises ZkError on a truncated blob or a wrong length prefix."""
+    blob = bytes(blob)
+    buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob or b"\0")
+    st = (C.c_uint8 * 32)()
+    ptr = C.c_void_p()
+    n = C.c_size_t(0)
+    rc = lib().zk_proof_deserialize(buf, len(blob), st, C.byref(ptr), C.byref(n))
+    if rc:
+        raise ZkError(rc, "truncated proof" if rc == -4 else "proof length prefix does not match the payload")
+    off = ptr.value - C.addressof(buf)
+    return bytes(st), blob[off: off + n.value]
 
 
 def merkle_trace_host(heap, index):
@@ -293,6 +323,14 @@ class Context:
         al = _u32(alpha_raw)
         out = np.empty_like(f_eval)
         self._ck(lib().zk_cp_eval_fibsq(self._h, _p(f_eval), log_n, log_blowup, _p(al), a_first, a_last, _p(out)))
+        return out
+
+    def field_ops(self, a, b):
+        """K1 on the device: rows a+b, a-b, a*b, -a, a^-1, a^b of canonical residues (zk_field_ops)."""
+        a, b = _u32(a), _u32(b)
+        assert a.shape == b.shape and a.ndim == 1
+        out = np.empty((6, len(a)), dtype=np.uint32)
+        self._ck(lib().zk_field_ops(self._h, _p(a), _p(b), len(a), _p(out)))
         return out
 
     def merkle_build(self, leaves):

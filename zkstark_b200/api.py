@@ -99,16 +99,13 @@ class Proof:
     # `data` being the channel transcript, already bincode (channel.rs:19-26), which the untouched Rust
     # `Proof::new(state, data.into_boxed_slice()).verify()` consumes as is.
     def to_bytes(self):
-        return bytes(self.state) + len(self.data).to_bytes(8, "little") + bytes(self.data)
+        from ._binding import proof_serialize
+        return proof_serialize(self.state, self.data)          # zk_proof_serialize (C ABI)
 
     @staticmethod
     def from_bytes(blob):
-        if len(blob) < 40:
-            raise ZkError(-1, "truncated proof")
-        n = int.from_bytes(blob[32:40], "little")
-        if len(blob) != 40 + n:
-            raise ZkError(-1, "proof length prefix does not match the payload")
-        return Proof(bytes(blob[:32]), bytes(blob[40:]))
+        from ._binding import proof_deserialize
+        return Proof(*proof_deserialize(blob))                  # zk_proof_deserialize (C ABI)
 
     def size(self):  # proof.rs:151-154: size_of::<Proof>() == 48 (32-byte array + Box<[u8]> fat pointer)
         return 48 + len(self.data)

@@ -26,6 +26,27 @@ __global__ void flush_kernel(uint4* p, size_t n)
     for (; i < n; i += stride) p[i] = make_uint4((uint32_t)i, 1u, 2u, 3u);
 }
 
+// K1 on its own (field.cuh): every device field operation on arbitrary u32 operands, reduced first as F::from(u32) does
+// (field.rs:20-24).  out: 6 rows of n -- a + b, a - b, a * b, -a, a^-1 (0 for a = 0), a^b  (field.rs:96-211, 26-38).
+__global__ void __launch_bounds__(256) field_ops_kernel(const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t x = reduce_u32(a[i]), y = reduce_u32(b[i]);
+    const uint32_t xm = to_mont(x);
+    out[i] = fadd(x, y);
+    out[n + i] = fsub(x, y);
+    out[2 * n + i] = mont_mul(xm, y);                       // (x R)(y) / R
+    out[3 * n + i] = fneg(x);
+    out[4 * n + i] = x ? from_mont(mont_inv(xm)) : 0u;
+    out[5 * n + i] = from_mont(mont_pow(xm, (uint64_t)b[i]));   // the exponent is the raw word (Pow<u32>, field.rs:26-38)
+}
+cudaError_t launch_field_ops(cudaStream_t s, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out)
+{
+    field_ops_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, b, n, out);
+    return cudaGetLastError();
+}
+
 // 4 independent chains of {SHF, LOP3, IADD3}: the instruction mix of SHA-256 on the ALU pipe.
 constexpr int INT_ITERS = 4096;
 __global__ void __launch_bounds__(256) intpipe_kernel(uint32_t* out, uint32_t seed)

@@ -1312,6 +1312,24 @@ int zk_shard_decommit_dev(zk_ctx* ctx, uint32_t log_n, uint32_t n_ranks, uint32_
     return ZK_OK;
 }
 
+// ------------------------------------------------------------------ K1 on its own (tests)
+int zk_field_ops(zk_ctx* ctx, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (!a || !b || !out || n == 0 || n > ((size_t)1 << 28)) return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->s0.ensure(8 * n));
+    CK(ctx->s1.ensure(24 * n));
+    uint32_t* da = (uint32_t*)ctx->s0.p;
+    CK(cudaMemcpyAsync(da, a, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(da + n, b, 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_field_ops(ctx->stream, da, da + n, n, (uint32_t*)ctx->s1.p));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(out, ctx->s1.p, 24 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
 // ------------------------------------------------------------------ measurement support
 int zk_bench_set(zk_ctx* ctx, int sha_variant, uint32_t leaf_pass_k)
 {

@@ -14,6 +14,8 @@
 // every butterfly is conflict-free and its twiddle is warp-uniform (broadcast from smem).
 // LDE = 8 size-n coset transforms  f_eval[8 j + r] = NTT_n( c_k (5 h^r)^k )[j]  (h^8 = g),
 // written interleaved so stores stay contiguous.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace zk {
@@ -351,7 +353,8 @@ struct NttPlan {
 static NttPlan make_plan(uint32_t mu, uint32_t log_arrays)
 {
     NttPlan p{};
-    int cap = (int)(mu + log_arrays) - 5 - NTT_LOG_TILES;
+    static const int log_tiles = [] { const char* e = getenv("ZK_NTT_LOG_TILES"); return e ? atoi(e) : NTT_LOG_TILES; }();
+    int cap = (int)(mu + log_arrays) - 5 - log_tiles;
     if (cap > 10) cap = 10;
     if (cap < 5) cap = 5;
     uint32_t np = mu <= 10 ? 1 : (mu + cap - 1) / cap;

@@ -195,3 +195,38 @@ extern "C" int zk_verify_fibsq(uint32_t log_n, uint32_t a_last, const uint8_t* t
 #undef FAIL
     return ZK_OK;
 }
+
+// ---------------------------------------------------------------- wire format
+// `Proof { state: [u8; 32], data: Box<[u8]> }` (proof.rs:5-8) as bincode 1.x serialises the struct: the 32 state bytes
+// (serde tuple: no length), the u64 little-endian length of `data`, the bytes of `data`.  `data` is the channel
+// transcript (channel.rs:8,34-36), already bincode, which the untouched `Proof::new(state, data).verify()` reads as is.
+extern "C" size_t zk_proof_serialized_len(size_t transcript_len) { return 32 + 8 + transcript_len; }
+
+extern "C" int zk_proof_serialize(const uint8_t state[32], const uint8_t* transcript, size_t transcript_len, uint8_t* out, size_t cap,
+                                  size_t* len_out)
+{
+    if (!state || (!transcript && transcript_len) || !out) return ZK_ERR_INVALID;
+    const size_t need = 40 + transcript_len;
+    if (cap < need) return ZK_ERR_BUFFER;
+    memcpy(out, state, 32);
+    for (int i = 0; i < 8; i++) out[32 + i] = (uint8_t)((uint64_t)transcript_len >> (8 * i));
+    if (transcript_len) memcpy(out + 40, transcript, transcript_len);
+    if (len_out) *len_out = need;
+    return ZK_OK;
+}
+
+extern "C" int zk_proof_deserialize(const uint8_t* bytes, size_t len, uint8_t state_out[32], const uint8_t** transcript_out,
+                                    size_t* transcript_len_out)
+{
+    if (!bytes || !state_out || !transcript_out || !transcript_len_out) return ZK_ERR_INVALID;
+    if (len < 40) return ZK_ERR_BUFFER;                       // truncated
+    uint64_t n = 0;
+    for (int i = 0; i < 8; i++) n |= (uint64_t)bytes[32 + i] << (8 * i);
+    if (n != (uint64_t)(len - 40)) return ZK_ERR_INVALID;     // the length prefix does not match the payload
+    memcpy(state_out, bytes, 32);
+    *transcript_out = bytes + 40;
+    *transcript_len_out = (size_t)n;
+    return ZK_OK;
+}
+
+extern "C" void zk_sha256(const uint8_t* data, size_t len, uint8_t out[32]) { sha::host_sha256(data, len, out); }
