@@ -268,6 +268,9 @@ int zk_field_ops(zk_ctx *ctx, const uint32_t *a, const uint32_t *b, size_t n, ui
  *   4 FRI fold of 2^log_size values (layer 0)            5 CP evaluation (log_size = log_n)
  *   6 integer-pipe microbenchmark: ms_out[2] = achieved Tiop/s; log_size selects the mix:
  *     0 = ALU pipe (SHF/LOP3/IADD3), 1 = FMA pipe (IMAD), 2 = 1:1 ALU/IMAD
+ *   8 butterfly microbenchmark (the instruction roofline of the transforms): radix-16 register rounds of
+ *     (u, v) -> (u + v, (u - v) w) without memory traffic; ms_out[2] = achieved tera-butterflies/s; log_size selects
+ *     0 = whole butterflies, 1 = only the Montgomery products, 2 = only the additions / subtractions
  *   7 node-hash latency probe: one CTA of `log_size` warps hashes a chain of `iters` nodes;
  *     ms_out[2] = SM cycles per node hash                                                        */
 /* tuning knobs of zk_bench_kernel(0): SHA-256 pipe-balancing variant (-1 = production) and levels per thread */

@@ -47,6 +47,51 @@ cudaError_t launch_field_ops(cudaStream_t s, const uint32_t* a, const uint32_t* 
     return cudaGetLastError();
 }
 
+// Butterfly microbenchmark (instruction roofline of the transforms): every thread runs radix-16 register rounds -- 32
+// DIF butterflies  (u, v) -> (u + v, (u - v) w)  with p = 3 * 2^30 + 1 > 2^31 -- on 16 values it keeps in registers; no
+// memory traffic.  mode 0: whole butterflies, 1: only the Montgomery products, 2: only the additions / subtractions.
+constexpr int BF_ITERS = 512;
+template <int MODE>
+__global__ void __launch_bounds__(256) bfly_kernel(uint32_t* out, uint32_t seed)
+{
+    uint32_t x[16], tw[15];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = reduce_u32(seed * (i + 1) + threadIdx.x * 7919u + blockIdx.x);
+#pragma unroll
+    for (int i = 0; i < 15; i++) tw[i] = reduce_u32(seed ^ (0x9E3779B9u * (i + 3)));
+#pragma unroll 1
+    for (int it = 0; it < BF_ITERS; it++) {
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int half = 8 >> t, off = 16 - (16 >> t);
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+#pragma unroll
+                for (int blk = 0; blk < 16 / (2 * half); blk++) {
+                    const int i0 = blk * 2 * half + j, i1 = i0 + half;
+                    const uint32_t u = x[i0], v = x[i1];
+                    if (MODE == 0) { x[i0] = fadd(u, v); x[i1] = mont_mul(fsub(u, v), tw[off + j]); }
+                    else if (MODE == 1) { x[i0] = v; x[i1] = mont_mul(u, tw[off + j]); }
+                    else { x[i0] = fadd(u, v); x[i1] = fsub(u, v); }
+                }
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= x[i];
+    if (acc == 0x12345u) out[0] = acc;
+}
+// returns butterflies per launch
+double bench_bfly(cudaStream_t s, uint32_t* out, int n_sm, int mode)
+{
+    const int blocks = n_sm * 8;
+    if (mode == 1) bfly_kernel<1><<<blocks, 256, 0, s>>>(out, 12345u);
+    else if (mode == 2) bfly_kernel<2><<<blocks, 256, 0, s>>>(out, 12345u);
+    else bfly_kernel<0><<<blocks, 256, 0, s>>>(out, 12345u);
+    return (double)blocks * 256 * BF_ITERS * 32;
+}
+
 // 4 independent chains of {SHF, LOP3, IADD3}: the instruction mix of SHA-256 on the ALU pipe.
 constexpr int INT_ITERS = 4096;
 __global__ void __launch_bounds__(256) intpipe_kernel(uint32_t* out, uint32_t seed)

@@ -1372,8 +1372,8 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
         ctx->launches += 1;
         return ZK_OK;
     }
-    if (which < 0 || which > 6) return fail(ctx, ZK_ERR_INVALID, "unknown kernel id");
-    if (which != 6 && (log_size < 3 || log_size > 30)) return fail(ctx, ZK_ERR_INVALID, "log_size out of range");
+    if (which < 0 || (which > 6 && which != 8)) return fail(ctx, ZK_ERR_INVALID, "unknown kernel id");
+    if (which != 6 && which != 8 && (log_size < 3 || log_size > 30)) return fail(ctx, ZK_ERR_INVALID, "log_size out of range");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     int rc = ZK_OK;
@@ -1451,6 +1451,7 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
                                            ctx->bench_variant == -200 ? nullptr : phantom_acc(ctx)); break;
             case 4: e = launch_fold(s, (const uint32_t*)ctx->s0.p, (uint32_t*)ctx->s1.p, log_size - 1, fa, T->h.tab, 1, 0); nl++; break;
             case 5: e = launch_cp(s, (uint32_t*)ctx->s1.p, ca, T->h.tab, 1, 0); nl++; break;
+            case 8: ops = bench_bfly(s, (uint32_t*)ctx->s0.p, n_sm, (int)log_size); e = cudaGetLastError(); nl++; break;
             default: ops = bench_intpipe(s, (uint32_t*)ctx->s0.p, n_sm, (int)log_size); e = cudaGetLastError(); nl++; break;
         }
         if (e != cudaSuccess) { rc = fail_cuda(ctx, e, "bench launch"); break; }
@@ -1458,6 +1459,15 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
     }
     if (rc == ZK_OK) {
         CK(cudaStreamSynchronize(s));
+        if (which == 2 || which == 3) {   // ZK_NTT_TIMING=1: per-pass times of the last transform on stderr
+            float pm[4];
+            const int np = ntt_pass_times(pm);
+            if (np > 0) {
+                fprintf(stderr, "[zk] %s 2^%u passes:", which == 2 ? "lde" : "interpolate", log_size);
+                for (int i = 0; i < np; i++) fprintf(stderr, " %.1f us", pm[i] * 1e3);
+                fprintf(stderr, "\n");
+            }
+        }
         double sum = 0, mn = 1e30;
         for (uint32_t it = 0; it < iters; it++) {
             float ms = 0;
@@ -1467,7 +1477,7 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
         }
         ms_out[0] = (float)(sum / iters);
         ms_out[1] = (float)mn;
-        ms_out[2] = which == 6 ? (float)(ops / (mn * 1e-3) / 1e12) : 0.f;
+        ms_out[2] = (which == 6 || which == 8) ? (float)(ops / (mn * 1e-3) / 1e12) : 0.f;   // Tiop/s, or tera-butterflies/s
     }
     for (auto& e : ev) cudaEventDestroy(e);
     ctx->launches += nl;

@@ -266,6 +266,358 @@ __global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_final_kernel(const
     }
 }
 
+// ================================================================ v2: narrow tiles (8 columns), two passes up to 2^20
+// The kernels above move tiles of 32 columns, so a radix-2^10 pass needs 135 KB of shared memory and one 1024-thread CTA
+// per SM, and a 2^20 transform is cheaper as THREE passes of 2^7.  Here a tile is R rows x 8 columns (one 32-byte sector
+// per row): 40 KB at R = 2^10, so a length-2^20 transform is TWO passes -- one global round trip and one twiddle
+// multiplication per point less -- and the shared-memory traffic, which the instruction queue of the memory pipe bounds
+// before the banks do, is cut to ~3 instructions per point and pass:
+//   * a thread owns 16 points of one column in every round; the first round takes them straight from global memory and
+//     the last one stores straight to global memory (a warp always touches 4 rows x 8 consecutive columns: full sectors);
+//   * between rounds the tile lives in shared memory as THREAD-CONTIGUOUS chunks: the 16 points a thread needs next are
+//     16 consecutive words (chunk pitch 20 words), read with four 128-bit loads; the producing round scatters its results
+//     with 32-bit stores.  Every row index is (run-time bits of the thread) | (compile-time bits of the point), so a
+//     scatter address is one run-time base plus an immediate.  The thread -> rows map of a round is a bit permutation
+//     chosen so that the 4 row slots of a warp fall on 4 different words mod 4 of their target chunks: conflict-free;
+//   * twiddles (and the per-row coset factors) are kept in shared memory in the same per-thread order: 128-bit broadcasts.
+constexpr int N2_E = 16;        // points per thread
+constexpr int N2_PITCH = 20;    // words per thread chunk (16 + 4: eight consecutive chunks start in eight different bank groups)
+
+constexpr int n2_round_lr(int rem) { return rem > 4 ? (rem == 5 ? 3 : 4) : rem; }
+struct N2Round { int S0, LR, LS, last; };
+constexpr N2Round n2_round(int LOG_R, int k)
+{
+    int s0 = 0;
+    for (int i = 0; i < k; i++) s0 += n2_round_lr(LOG_R - s0);
+    const int lr = n2_round_lr(LOG_R - s0);
+    return N2Round{s0, lr, LOG_R - s0 - lr, s0 + lr == LOG_R};
+}
+constexpr int n2_rounds(int LOG_R)
+{
+    int s0 = 0, k = 0;
+    while (s0 < LOG_R) { s0 += n2_round_lr(LOG_R - s0); k++; }
+    return k;
+}
+// Which row bit every bit of (row slot, trip) of a round stands for.  Digit bits [LS, LS+LR) belong to the butterflies.
+//   last round : rows of a thread are consecutive: trip bits [LR, 4), slot bits [4, LOG_R)
+//   otherwise  : slot bits 0,1 -> the two lowest bits of the NEXT round's position-in-chunk (its digit's low bits), so the
+//                4 row slots of a warp scatter to 4 different words mod 4; trip bits -> the highest free bits; the other
+//                slot bits -> the remaining free bits, ascending
+struct N2Map { int rs[8]; int trip[4]; int n_rs, n_trip; };
+constexpr N2Map n2_map(int LOG_R, int k)
+{
+    const N2Round r = n2_round(LOG_R, k);
+    N2Map m{};
+    m.n_rs = LOG_R - 4;
+    m.n_trip = 4 - r.LR;
+    bool used[12] = {};
+    for (int b = r.LS; b < r.LS + r.LR; b++) used[b] = true;
+    if (r.last) {
+        for (int b = 0; b < m.n_trip; b++) { m.trip[b] = r.LR + b; used[r.LR + b] = true; }
+        for (int b = 0; b < m.n_rs; b++) m.rs[b] = 4 + b;
+        return m;
+    }
+    const N2Round nx = n2_round(LOG_R, k + 1);
+    const int lo2 = nx.last ? 0 : nx.LS;          // low bits of the next round's position-in-chunk
+    int nrs = 0;
+    for (int b = 0; b < 2 && nrs < m.n_rs; b++) { m.rs[nrs++] = lo2 + b; used[lo2 + b] = true; }
+    for (int b = 0, top = LOG_R - 1; b < m.n_trip; top--) {
+        if (!used[top]) { m.trip[m.n_trip - 1 - b] = top; used[top] = true; b++; }
+    }
+    for (int b = 0; b < LOG_R && nrs < m.n_rs; b++)
+        if (!used[b]) { m.rs[nrs++] = b; used[b] = true; }
+    return m;
+}
+// rows of (slot, trip) without the digit
+template <int LOG_R, int K>
+__host__ __device__ constexpr uint32_t n2_rows(uint32_t rslot, uint32_t trip)
+{
+    constexpr N2Map m = n2_map(LOG_R, K);
+    uint32_t row = 0;
+    for (int b = 0; b < m.n_rs; b++) row |= ((rslot >> b) & 1u) << m.rs[b];
+    for (int b = 0; b < m.n_trip; b++) row |= ((trip >> b) & 1u) << m.trip[b];
+    return row;
+}
+// inverse: which thread chunk (slot) and which position in it a row has in round K
+template <int LOG_R, int K>
+__host__ __device__ constexpr uint32_t n2_slot_of(uint32_t row)
+{
+    constexpr N2Map m = n2_map(LOG_R, K);
+    uint32_t s = 0;
+    for (int b = 0; b < m.n_rs; b++) s |= ((row >> m.rs[b]) & 1u) << b;
+    return s;
+}
+template <int LOG_R, int K>
+__host__ __device__ constexpr uint32_t n2_pos_of(uint32_t row)
+{
+    constexpr N2Map m = n2_map(LOG_R, K);
+    constexpr N2Round r = n2_round(LOG_R, K);
+    uint32_t t = 0;
+    for (int b = 0; b < m.n_trip; b++) t |= ((row >> m.trip[b]) & 1u) << b;
+    return (t << r.LR) | ((row >> r.LS) & ((1u << r.LR) - 1u));
+}
+__host__ __device__ constexpr uint32_t brevc(uint32_t x, int bits)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+template <int LOG_R>
+struct Ntt2Cfg {
+    static constexpr int R = 1 << LOG_R;
+    static constexpr int THREADS = R * 8 / N2_E;       // 512 at R = 2^10 .. 32 at R = 2^6
+    static constexpr int NSLOT = THREADS / 8;          // row slots: R / 16
+    static constexpr int NR = n2_rounds(LOG_R);
+    static constexpr int TILE_WORDS = NSLOT * 8 * N2_PITCH;
+    // twiddle chunks: round k has 2^LS distinct `lo`, each with RAD - 1 twiddles stored in a chunk of RAD words
+    static constexpr int tw_off(int k)
+    {
+        int o = 0;
+        for (int i = 0; i < k; i++) { const N2Round r = n2_round(LOG_R, i); o += (1 << r.LS) << r.LR; }
+        return o;
+    }
+    static constexpr int TW_WORDS = tw_off(NR);
+    static constexpr int RF_WORDS = NSLOT * N2_PITCH;  // per-row coset factors in round-0 chunk order (strided pass with COSET)
+};
+
+// twiddle tables of all rounds in per-thread order: T_k[lo * RAD + slot(t, j)] = w_R^(((j << LS) + lo) << (S0 + t))
+template <int LOG_R>
+__device__ __forceinline__ void n2_build_twiddles(uint32_t* tw_s, const uint32_t* __restrict__ tw_g)
+{
+    using C = Ntt2Cfg<LOG_R>;
+#pragma unroll
+    for (int k = 0; k < C::NR; k++) {
+        constexpr int dummy = 0; (void)dummy;
+        const N2Round r = n2_round(LOG_R, k);
+        const int rad = 1 << r.LR, total = (1 << r.LS) << r.LR;
+        uint32_t* T = tw_s + C::tw_off(k);
+        for (int e = threadIdx.x; e < total; e += C::THREADS) {
+            const int lo = e >> r.LR, slot = e & (rad - 1);
+            if (slot == rad - 1) continue;
+            int t = 0, off = 0, h = rad >> 1;
+            while (slot >= off + h) { off += h; h >>= 1; t++; }
+            const int j = slot - off;
+            T[e] = tw_g[((j << r.LS) + lo) << (r.S0 + t)];
+        }
+    }
+}
+
+// the butterflies of one round on the 16 points of a thread (TRIPS mini-transforms of radix 2^LR); x[trip * RAD + d]
+template <int LOG_R, int K>
+__device__ __forceinline__ void n2_butterflies(uint32_t (&x)[N2_E], const uint32_t* tw_s, uint32_t row_rt)
+{
+    using C = Ntt2Cfg<LOG_R>;
+    constexpr N2Round r = n2_round(LOG_R, K);
+    constexpr int RAD = 1 << r.LR, TRIPS = N2_E / RAD;
+    constexpr N2Map m = n2_map(LOG_R, K);
+    // the trip bits never fall below the digit (they are the highest free bits, or bits [LR, 4) of the last round where
+    // LS = 0), so every trip of a thread has the same `lo` and the same twiddles
+    static_assert(m.n_trip == 0 || r.last || m.trip[0] >= r.LS + r.LR, "trip bits must lie above the digit");
+    uint32_t tw[RAD];
+    if (RAD >= 4) {
+        const uint32_t lo = row_rt & ((1u << r.LS) - 1u);
+        const uint4* tp = reinterpret_cast<const uint4*>(tw_s + C::tw_off(K) + (lo << r.LR));
+#pragma unroll
+        for (int q = 0; q < RAD / 4; q++) {
+            const uint4 t4 = tp[q];
+            tw[4 * q] = t4.x; tw[4 * q + 1] = t4.y; tw[4 * q + 2] = t4.z; tw[4 * q + 3] = t4.w;
+        }
+    } else {
+        tw[0] = tw_s[C::tw_off(K)];
+        tw[1] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < TRIPS; i++) {
+#pragma unroll
+        for (int t = 0; t < r.LR; t++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int half = RAD >> (t + 1), off = RAD - (RAD >> t);
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+                const bool trivial = (r.LS == 0 && j == 0);           // w^0
+#pragma unroll
+                for (int blk = 0; blk < RAD / (2 * half); blk++) {
+                    const int i0 = i * RAD + blk * 2 * half + j, i1 = i0 + half;
+                    const uint32_t u = x[i0], v = x[i1];
+                    x[i0] = fadd(u, v);
+                    x[i1] = trivial ? fsub(u, v) : mont_mul(fsub(u, v), tw[off + j]);
+                }
+            }
+        }
+    }
+}
+
+// scatter the 16 results of round K into the chunk order of round K + 1
+template <int LOG_R, int K>
+__device__ __forceinline__ void n2_scatter(uint32_t* tile, const uint32_t (&x)[N2_E], uint32_t row_rt, uint32_t col)
+{
+    constexpr N2Round r = n2_round(LOG_R, K);
+    constexpr int RAD = 1 << r.LR;
+    uint32_t* base = tile + (n2_slot_of<LOG_R, K + 1>(row_rt) * 8 + col) * N2_PITCH + n2_pos_of<LOG_R, K + 1>(row_rt);
+#pragma unroll
+    for (int u = 0; u < N2_E; u++) {
+        const uint32_t rc = n2_rows<LOG_R, K>(0u, (uint32_t)(u / RAD)) | ((uint32_t)(u % RAD) << r.LS);   // compile-time row bits
+        base[n2_slot_of<LOG_R, K + 1>(rc) * 8 * N2_PITCH + n2_pos_of<LOG_R, K + 1>(rc)] = x[u];
+    }
+}
+__device__ __forceinline__ void n2_gather(const uint32_t* tile, uint32_t (&x)[N2_E], uint32_t rslot, uint32_t col)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(tile + (rslot * 8 + col) * N2_PITCH);
+#pragma unroll
+    for (int q = 0; q < N2_E / 4; q++) {
+        const uint4 v = p[q];
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+}
+// rounds 1 .. NR-1 of the CTA-local transform; x holds round 0's results on entry and the last round's on exit
+template <int LOG_R, int K = 0>
+__device__ __forceinline__ void n2_rounds_after_first(uint32_t* tile, const uint32_t* tw_s, uint32_t (&x)[N2_E], uint32_t rslot,
+                                                      uint32_t col)
+{
+    if constexpr (K + 1 < Ntt2Cfg<LOG_R>::NR) {
+        n2_scatter<LOG_R, K>(tile, x, n2_rows<LOG_R, K>(rslot, 0u), col);
+        __syncthreads();
+        n2_gather(tile, x, rslot, col);
+        if constexpr (K + 2 < Ntt2Cfg<LOG_R>::NR) __syncthreads();     // the tile is overwritten by this round's scatter
+        n2_butterflies<LOG_R, K + 1>(x, tw_s, n2_rows<LOG_R, K + 1>(rslot, 0u));
+        n2_rounds_after_first<LOG_R, K + 1>(tile, tw_s, x, rslot, col);
+    }
+}
+
+// Strided pass, narrow tile.  Same arithmetic as ntt_strided_kernel; the coset factor c_k sigma^k, k = a S + b, is split
+// as sigma^(a S) (per row: a table in shared memory, one multiplication per point) times sigma^b (per column: folded
+// into the start of the output twiddle chain, free), and so is the n^-1 of the inverse transform.
+template <int LOG_R, bool COSET>
+__global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_strided_kernel(const NttPassArgs a)
+{
+    pdl_enter();
+    using C = Ntt2Cfg<LOG_R>;
+    constexpr int NR = C::NR;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* tile = smem;
+    uint32_t* tw_s = smem + C::TILE_WORDS;
+    uint32_t* rf = tw_s + C::TW_WORDS;                            // [NSLOT][N2_PITCH] (COSET)
+    const uint32_t col = threadIdx.x & 7, rslot = threadIdx.x >> 3;
+    const uint32_t log_tpb = a.log_S - 3;                        // tiles of 8 columns per block of M_sub
+    const uint32_t log_per_array = a.log_M - LOG_R - 3;
+    uint32_t tix = blockIdx.x;
+    const uint32_t r = tix >> log_per_array;                     // coset
+    tix &= (1u << log_per_array) - 1u;
+    const uint32_t blk = tix >> log_tpb, b = ((tix & ((1u << log_tpb) - 1u)) << 3) + col;
+    const size_t M = (size_t)1 << a.log_M;
+    const uint32_t* src = a.src + (size_t)blockIdx.y * a.src_stride + (COSET ? 0 : r * M);
+    uint32_t* dst = a.dst + (size_t)blockIdx.y * a.dst_stride + r * M;
+    const size_t base = ((size_t)blk << a.log_Msub) + b;
+    const uint32_t rr = r + a.coset_base;
+
+    // round 0 straight from global memory: rows row0 | (u << LS0)
+    constexpr N2Round r0 = n2_round(LOG_R, 0);
+    static_assert(r0.LR == 4, "the first round is radix 16: one mini-transform per thread");
+    const uint32_t row0 = n2_rows<LOG_R, 0>(rslot, 0u);
+    uint32_t x[N2_E];
+    {
+        const uint32_t* p = src + base + ((size_t)row0 << a.log_S);
+        const size_t step = (size_t)1 << (a.log_S + r0.LS);
+#pragma unroll
+        for (int u = 0; u < N2_E; u++) x[u] = p[u * step];
+    }
+    n2_build_twiddles<LOG_R>(tw_s, a.tw);
+    if (COSET) {   // first pass of the LDE (one block: blk == 0, k = a S + b): sigma^(a S) in the order round 0 reads it
+        for (uint32_t e = threadIdx.x; e < (uint32_t)C::NSLOT * N2_E; e += C::THREADS) {
+            const uint32_t s = e >> 4, u = e & 15;
+            rf[s * N2_PITCH + u] = sigma_pow_m(a, rr, (n2_rows<LOG_R, 0>(s, 0u) | (u << r0.LS)) << a.log_S);
+        }
+    }
+    __syncthreads();
+    if (COSET) {
+        const uint4* rp = reinterpret_cast<const uint4*>(rf + rslot * N2_PITCH);
+#pragma unroll
+        for (int q = 0; q < N2_E / 4; q++) {
+            const uint4 f = rp[q];
+            x[4 * q] = mont_mul(x[4 * q], f.x); x[4 * q + 1] = mont_mul(x[4 * q + 1], f.y);
+            x[4 * q + 2] = mont_mul(x[4 * q + 2], f.z); x[4 * q + 3] = mont_mul(x[4 * q + 3], f.w);
+        }
+    }
+    n2_butterflies<LOG_R, 0>(x, tw_s, row0);
+    n2_rounds_after_first<LOG_R>(tile, tw_s, x, rslot, col);
+    // The thread now holds rows rslot * 16 + u of the bit-reversed result, i.e. outputs c = brev(rslot) + (brev4(u) << (LOG_R - 4)):
+    // twiddle w_Msub^(b c) (times the column's share of the coset factor and the final scale), stores straight from registers.
+    {
+        constexpr N2Round rl = n2_round(LOG_R, NR - 1);
+        static_assert(n2_rows<LOG_R, NR - 1>(1u, 0u) == 16u && rl.LS == 0, "last round: 16 consecutive rows per thread");
+        const uint32_t c0 = brev_c<LOG_R>(rslot << 4);           // < 2^(LOG_R - 4)
+        const uint32_t N1 = (1u << a.hpow.log_N) - 1u, sh = a.hpow.log_N - a.log_Msub;
+        uint32_t e1 = (b << (LOG_R - 4)) << sh, e0 = (b * c0) << sh;   // step: w^(b 2^(LOG_R-4)); start: w^(b c0)
+        if (a.inverse) { e1 = ((N1 + 1u) - (e1 & N1)) & N1; e0 = ((N1 + 1u) - (e0 & N1)) & N1; }
+        const uint32_t w1 = pw(a.hpow, e1 & N1), w2 = mont_mul(w1, w1), w3 = mont_mul(w2, w1), w4 = mont_mul(w2, w2);
+        uint32_t t[4];
+        t[0] = pw(a.hpow, e0 & N1);
+        if (COSET) t[0] = mont_mul(t[0], sigma_pow_m(a, rr, b));
+        if (a.use_scale) t[0] = mont_mul(t[0], a.scale_m);
+        t[1] = mont_mul(t[0], w1); t[2] = mont_mul(t[0], w2); t[3] = mont_mul(t[0], w3);
+        uint32_t* q = dst + ((size_t)blk << a.log_Msub) + ((size_t)c0 << a.log_S) + b;
+        const size_t step = (size_t)1 << (a.log_S + LOG_R - 4);
+        // outputs in the order m = brev4(u) = 0 .. 15 so that the four multiplicative chains advance in step
+#pragma unroll
+        for (int mm = 0; mm < N2_E; mm++) {
+            const int u = (int)brevc((uint32_t)mm, 4);
+            q[mm * step] = mont_mul(x[u], t[mm & 3]);
+            if (mm + 4 < N2_E) t[mm & 3] = mont_mul(t[mm & 3], w4);
+        }
+    }
+}
+
+// Final pass, narrow tile: the CTA takes 8 contiguous rows of R points -- the 8 cosets of one row index (LOG_CS = 3) or
+// 8 consecutive row indices c1 of one array (LOG_CS = 0) -- as the 8 columns of its tile.  Outputs of one digit c are 8
+// consecutive words of the natural-order result: the 8 lanes of a row slot store one sector.
+template <int LOG_R, int LOG_CS>
+__global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(const NttPassArgs a)
+{
+    pdl_enter();
+    using C = Ntt2Cfg<LOG_R>;
+    constexpr int NR = C::NR, CS = 1 << LOG_CS, LOG_U = 3 - LOG_CS;
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* tile = smem;
+    uint32_t* tw_s = smem + C::TILE_WORDS;
+    const uint32_t col = threadIdx.x & 7, rslot = threadIdx.x >> 3;
+    const uint32_t log_tiles_c1 = a.log_R1 - LOG_U;
+    const uint32_t c2 = blockIdx.x >> log_tiles_c1, c1_0 = (blockIdx.x & ((1u << log_tiles_c1) - 1u)) << LOG_U;
+    const size_t M = (size_t)1 << a.log_M;
+    const uint32_t* srcb = a.src + (size_t)blockIdx.y * a.src_stride;
+    uint32_t* dstb = a.dst + (size_t)blockIdx.y * a.dst_stride;
+
+    constexpr N2Round r0 = n2_round(LOG_R, 0);
+    const uint32_t row0 = n2_rows<LOG_R, 0>(rslot, 0u);
+    uint32_t x[N2_E];
+    {
+        // column `col` of the tile is one contiguous row of R points; the other lanes of the CTA pick up the rest of each line
+        const uint32_t rr = col & (CS - 1), uu = col >> LOG_CS;
+        const size_t qrow = ((size_t)(c1_0 + uu) << a.log_Q2) + c2;
+        const uint32_t* p = srcb + rr * M + (qrow << LOG_R) + row0;
+#pragma unroll
+        for (int u = 0; u < N2_E; u++) x[u] = p[u << r0.LS];
+    }
+    n2_build_twiddles<LOG_R>(tw_s, a.tw);
+    __syncthreads();
+    n2_butterflies<LOG_R, 0>(x, tw_s, row0);
+    n2_rounds_after_first<LOG_R>(tile, tw_s, x, rslot, col);
+    {
+        const uint32_t log_rows = a.log_M - LOG_R;
+        const size_t rho = (size_t)c1_0 + ((size_t)c2 << a.log_R1);      // first of the tile's row indices
+        const uint32_t c0 = brev_c<LOG_R>(rslot << 4);
+#pragma unroll
+        for (int u = 0; u < N2_E; u++) {
+            const uint32_t c = c0 + (brevc((uint32_t)u, 4) << (LOG_R - 4));
+            uint32_t v = x[u];
+            if (a.use_scale) v = mont_mul(v, a.scale_m);
+            const size_t o = ((rho + ((size_t)c << log_rows)) << LOG_CS) + col;
+            if (LOG_CS == 0 && a.pack.log_jb != 0) dstb[pack_index(a.pack, (uint32_t)o)] = v;
+            else dstb[o] = v;
+        }
+    }
+}
+
 // After the size-n inverse transform of (a_0..a_{n-2}, 0): c'_k.  The interpolant of the n-1
 // trace points (prover.rs:60: zip truncates to 1023 pairs) has degree <= n-2, i.e. is
 //   c_k = c'_k - t g^(k+1),  t = c'_{n-1}
@@ -404,6 +756,71 @@ static cudaError_t launch_final(bool coset, uint32_t n_cosets, dim3 grid, cudaSt
     return launch_k(ntt_final_kernel<LOG_R, 0, false>, grid, th, smem, s, a);
 }
 
+template <int LOG_R>
+static cudaError_t launch_strided2(bool coset, dim3 grid, cudaStream_t s, const NttPassArgs& a)
+{
+    using C = Ntt2Cfg<LOG_R>;
+    const size_t smem = ((size_t)C::TILE_WORDS + C::TW_WORDS + (coset ? C::RF_WORDS : 0)) * 4;
+    if (coset) return launch_k(ntt2_strided_kernel<LOG_R, true>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
+    return launch_k(ntt2_strided_kernel<LOG_R, false>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
+}
+template <int LOG_R>
+static cudaError_t launch_final2(uint32_t n_cosets, dim3 grid, cudaStream_t s, const NttPassArgs& a)
+{
+    const size_t smem = ((size_t)Ntt2Cfg<LOG_R>::TILE_WORDS + Ntt2Cfg<LOG_R>::TW_WORDS) * 4;
+    if (n_cosets == 8) return launch_k(ntt2_final_kernel<LOG_R, 3>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
+    return launch_k(ntt2_final_kernel<LOG_R, 0>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
+}
+// which kernel family: 2 (narrow tiles, default from 2^12) or 1; ZK_NTT_V=1 forces the wide-tile kernels (experiments)
+static int ntt_version()
+{
+    static const int v = [] { const char* e = getenv("ZK_NTT_V"); return e ? atoi(e) : 2; }();
+    return v;
+}
+// smallest transform that takes the narrow-tile kernels: measured on B200 they win from 2^17 (2^18: 27 vs 30 us, 2^20: 80 vs
+// 83 us, 2^24: 1.31 vs 1.39 ms per LDE; batched 2^20: 103 vs 97 G points/s) and lose below (2^16: 20.5 vs 19.0 us), where a
+// transform is a handful of CTAs and their longer prologue shows.  ZK_NTT2_MIN_MU overrides (>= 12).
+static int ntt2_min_mu()
+{
+    static const int v = [] { const char* e = getenv("ZK_NTT2_MIN_MU"); int m = e ? atoi(e) : 17; return m < 12 ? 12 : m; }();
+    return v;
+}
+// narrow-tile plan: ceil(mu / 10) passes of radix 2^6 .. 2^10, as even as possible, larger first
+static NttPlan make_plan2(uint32_t mu)
+{
+    NttPlan p{};
+    static const uint32_t maxr = [] { const char* e = getenv("ZK_NTT2_MAXR"); uint32_t v = e ? (uint32_t)atoi(e) : 10u; return v < 6 ? 6u : (v > 10 ? 10u : v); }();
+    p.n_pass = (mu + maxr - 1) / maxr;
+    if (p.n_pass > 3) p.n_pass = 3;
+    for (uint32_t i = 0; i < p.n_pass; i++) p.log_r[i] = (mu + p.n_pass - 1 - i) / p.n_pass;
+    return p;
+}
+
+// measurement support: ZK_NTT_TIMING=1 brackets every pass with CUDA events; tools read them back through ntt_pass_times()
+static cudaEvent_t g_pass_ev[5];
+static int g_pass_n = -1;   // -1: off
+static bool pass_timing()
+{
+    static const bool on = [] {
+        const char* e = getenv("ZK_NTT_TIMING");
+        if (!(e && e[0] == '1')) return false;
+        for (auto& ev : g_pass_ev) cudaEventCreate(&ev);
+        return true;
+    }();
+    return on;
+}
+static void pass_mark(cudaStream_t s, int i)
+{
+    if (pass_timing() && i < 5) { cudaEventRecord(g_pass_ev[i], s); g_pass_n = i; }
+}
+int ntt_pass_times(float ms[4])
+{
+    if (!pass_timing() || g_pass_n < 1) return 0;
+    cudaEventSynchronize(g_pass_ev[g_pass_n]);
+    for (int i = 0; i < g_pass_n; i++) cudaEventElapsedTime(&ms[i], g_pass_ev[i], g_pass_ev[i + 1]);
+    return g_pass_n;
+}
+
 // Transform `n_cosets` (1 or 8) arrays of length 2^mu.  Passes before the last run in place on `work`
 // (n_cosets * M words per proof); the last writes natural order (interleaved over cosets) to dst.
 // With coset_scale the first pass reads the single coefficient array `coeffs` instead of `work`.
@@ -416,7 +833,8 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     if (n_cosets != 1 && n_cosets != 8) return cudaErrorInvalidValue;
     uint32_t log_arrays = 0;
     while ((1u << log_arrays) < n_cosets * batch) log_arrays++;
-    NttPlan p = make_plan(mu, log_arrays);
+    const bool v2 = mu >= (uint32_t)ntt2_min_mu() && ntt_version() == 2;
+    NttPlan p = v2 ? make_plan2(mu) : make_plan(mu, log_arrays);
     NttPassArgs a{};
     a.log_M = mu;
     a.inverse = inverse;
@@ -427,6 +845,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     const uint32_t* twb = inverse ? T.tw_inv : T.tw_fwd;
     uint32_t log_S = mu;
     cudaError_t e;
+    pass_mark(s, 0);
     for (uint32_t i = 0; i + 1 < p.n_pass; i++) {
         const uint32_t log_R = p.log_r[i];
         a.log_Msub = log_S;
@@ -438,6 +857,23 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
         a.src_stride = (i == 0) ? coeffs_stride : work_stride;
         a.dst = work;
         a.dst_stride = work_stride;
+        if (v2) {
+            a.use_scale = (i == 0 && use_scale);   // the final scale rides on the first pass's twiddle chain
+            a.scale_m = scale_m;
+            dim3 grid2(((1u << (mu - 3)) >> log_R) * n_cosets, batch);   // (M / (R*S)) * (S/8)
+            switch (log_R) {
+                case 6: e = launch_strided2<6>(cs, grid2, s, a); break;
+                case 7: e = launch_strided2<7>(cs, grid2, s, a); break;
+                case 8: e = launch_strided2<8>(cs, grid2, s, a); break;
+                case 9: e = launch_strided2<9>(cs, grid2, s, a); break;
+                case 10: e = launch_strided2<10>(cs, grid2, s, a); break;
+                default: return cudaErrorInvalidValue;
+            }
+            if (e != cudaSuccess) return e;
+            if (n_launches) (*n_launches)++;
+            pass_mark(s, i + 1);
+            continue;
+        }
         uint32_t tiles = (1u << (mu - 5)) >> log_R;  // (M / (R*S)) * (S/32)
         dim3 grid(tiles * n_cosets, batch);
         switch (log_R) {
@@ -465,6 +901,23 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     a.scale_m = scale_m;
     a.log_R1 = p.n_pass >= 2 ? p.log_r[0] : 0;
     a.log_Q2 = p.n_pass == 3 ? p.log_r[1] : 0;
+    if (v2) {
+        a.use_scale = 0;   // applied by the first pass
+        const uint32_t log_U = n_cosets == 8 ? 0 : 3;
+        dim3 grid(1u << (a.log_R1 - log_U + a.log_Q2), batch);
+        switch (log_R) {
+            case 6: e = launch_final2<6>(n_cosets, grid, s, a); break;
+            case 7: e = launch_final2<7>(n_cosets, grid, s, a); break;
+            case 8: e = launch_final2<8>(n_cosets, grid, s, a); break;
+            case 9: e = launch_final2<9>(n_cosets, grid, s, a); break;
+            case 10: e = launch_final2<10>(n_cosets, grid, s, a); break;
+            default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
+        if (n_launches) (*n_launches)++;
+        pass_mark(s, p.n_pass);
+        return cudaSuccess;
+    }
     {
         uint32_t log_U = n_cosets == 8 ? 2 : 5;
         if (log_U > a.log_R1) log_U = a.log_R1;
