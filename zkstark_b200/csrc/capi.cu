@@ -294,6 +294,11 @@ int enqueue_prove(zk_ctx* ctx, cudaStream_t s, uint32_t log_n, uint32_t p0, uint
         a.log_size = log_N - i;
         a.post = POST_FRI;
         a.fri_layer = i;
+        if (a.log_size <= TILE_MIN_LOG && ctx->fri_tail) {   // this and every following layer: one launch
+            CK(launch_fri_tail(s, a, nb, L));
+            nl++;
+            break;
+        }
         CK(launch_merkle_tree(s, SRC_FOLD, a, nb, &nl));
     }
     if (tm) tm->mark();
@@ -472,6 +477,7 @@ int zk_ctx_create_on_stream(int device, void* cuda_stream, zk_ctx** out)
     for (int i = 0; i < 8; i++)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return ZK_ERR_CUDA; }
     { const char* e = getenv("ZK_NO_LANES"); if (e && e[0] == '1') ctx->lanes = false; }
+    { const char* e = getenv("ZK_NO_FRI_TAIL"); if (e && e[0] == '1') ctx->fri_tail = false; }
     { const char* e = getenv("ZK_TRACE_DEVICE"); if (e && e[0] == '1') ctx->trace_on_device = true; }
     { const char* e = getenv("ZK_HOST_THREADS"); if (e) ctx->host_threads = (uint32_t)atoi(e); }
     if (cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1278,6 +1284,11 @@ int zk_shard_fri_tail_dev(zk_ctx* ctx, uint32_t log_n, uint32_t first_layer, uin
         a.log_size = log_N - i;
         a.post = POST_FRI;
         a.fri_layer = i;
+        if (a.log_size <= TILE_MIN_LOG && ctx->fri_tail) {
+            CK(launch_fri_tail(ctx->stream, a, 1, L));
+            nl++;
+            break;
+        }
         CK(launch_merkle_tree(ctx->stream, SRC_FOLD, a, 1, &nl));
     }
     ctx->launches += nl;

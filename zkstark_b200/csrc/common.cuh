@@ -231,6 +231,8 @@ static inline cudaError_t zk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 // ---- launchers (tree.cu)
 // Builds the whole tree over 2^log_size leaves taken from `src_kind`, per proof of the batch.
 cudaError_t launch_merkle_tree(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, int* n_launches);
+// FRI layers a.fri_layer .. last_layer in one launch (a describes the first of them; every one is a single tile)
+cudaError_t launch_fri_tail(cudaStream_t s, TreeArgs a, uint32_t batch, uint32_t last_layer);
 // levels log_size .. stop_level only (no top kernel, no channel step): used for the rank-local block subtrees
 cudaError_t launch_merkle_partial(cudaStream_t s, int src_kind, TreeArgs a, uint32_t batch, uint32_t stop_level, int* n_launches);
 // upper part of a tree whose level `in_level` digests are already in the heap: digest passes + top (+ channel)

@@ -35,6 +35,7 @@ struct NttPassArgs {
     uint32_t log_R1;     // final pass: first-pass radix (0 when single pass)
     uint32_t log_Q2;     // final pass: second-pass radix (0 unless three passes)
     uint32_t coset_base; // index of the first coset of this launch (sharded LDE: one coset per launch)
+    int use_coset;       // single-pass narrow-tile kernel: scale the input by sigma_r^k
     NttPack pack;        // final pass of a one-coset launch: store straight into the all-to-all send layout
 };
 
@@ -571,12 +572,15 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_strided_kernel(c
 // Final pass, narrow tile: the CTA takes 8 contiguous rows of R points -- the 8 cosets of one row index (LOG_CS = 3) or
 // 8 consecutive row indices c1 of one array (LOG_CS = 0) -- as the 8 columns of its tile.  Outputs of one digit c are 8
 // consecutive words of the natural-order result: the 8 lanes of a row slot store one sector.
-template <int LOG_R, int LOG_CS>
+// SINGLE (whole transform in this pass, M = R <= 2^10): an array is ONE row, so LOG_CS = 3 fills the 8 columns with the 8
+// cosets of the LDE (scaled here by sigma_r^k) and LOG_CS = 0 uses one column of the tile -- still one short launch
+// instead of a 32-column tile kernel that leaves 24 or 31 of its 32 lanes idle (2^10: 27 -> 6 us, 21 -> 5 us).
+template <int LOG_R, int LOG_CS, bool SINGLE = false>
 __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(const NttPassArgs a)
 {
     pdl_enter();
     using C = Ntt2Cfg<LOG_R>;
-    constexpr int NR = C::NR, CS = 1 << LOG_CS, LOG_U = 3 - LOG_CS;
+    constexpr int CS = 1 << LOG_CS, LOG_U = SINGLE ? 0 : 3 - LOG_CS;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* tile = smem;
     uint32_t* tw_s = smem + C::TILE_WORDS;
@@ -586,17 +590,31 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(con
     const size_t M = (size_t)1 << a.log_M;
     const uint32_t* srcb = a.src + (size_t)blockIdx.y * a.src_stride;
     uint32_t* dstb = a.dst + (size_t)blockIdx.y * a.dst_stride;
+    const bool live = !SINGLE || col < (uint32_t)CS;          // SINGLE with one array: only column 0 carries data
 
     constexpr N2Round r0 = n2_round(LOG_R, 0);
     const uint32_t row0 = n2_rows<LOG_R, 0>(rslot, 0u);
     uint32_t x[N2_E];
-    {
+    if (live) {
         // column `col` of the tile is one contiguous row of R points; the other lanes of the CTA pick up the rest of each line
         const uint32_t rr = col & (CS - 1), uu = col >> LOG_CS;
         const size_t qrow = ((size_t)(c1_0 + uu) << a.log_Q2) + c2;
-        const uint32_t* p = srcb + rr * M + (qrow << LOG_R) + row0;
+        // SINGLE LDE: the 8 cosets are transforms of the SAME coefficient array, scaled below by sigma_r^k (prover.rs:69-70)
+        const uint32_t* p = srcb + ((SINGLE && a.use_coset) ? 0 : rr * M) + (qrow << LOG_R) + row0;
 #pragma unroll
         for (int u = 0; u < N2_E; u++) x[u] = p[u << r0.LS];
+        if (SINGLE && a.use_coset) {
+            uint32_t t = sigma_pow_m(a, rr + a.coset_base, row0);
+            const uint32_t step = sigma_pow_m(a, rr + a.coset_base, 1u << r0.LS);
+#pragma unroll
+            for (int u = 0; u < N2_E; u++) {
+                x[u] = mont_mul(x[u], t);
+                if (u + 1 < N2_E) t = mont_mul(t, step);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < N2_E; u++) x[u] = 0u;
     }
     n2_build_twiddles<LOG_R>(tw_s, a.tw);
     __syncthreads();
@@ -612,6 +630,7 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(con
             uint32_t v = x[u];
             if (a.use_scale) v = mont_mul(v, a.scale_m);
             const size_t o = ((rho + ((size_t)c << log_rows)) << LOG_CS) + col;
+            if (!live) continue;
             if (LOG_CS == 0 && a.pack.log_jb != 0) dstb[pack_index(a.pack, (uint32_t)o)] = v;
             else dstb[o] = v;
         }
@@ -771,6 +790,13 @@ static cudaError_t launch_final2(uint32_t n_cosets, dim3 grid, cudaStream_t s, c
     if (n_cosets == 8) return launch_k(ntt2_final_kernel<LOG_R, 3>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
     return launch_k(ntt2_final_kernel<LOG_R, 0>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
 }
+template <int LOG_R>
+static cudaError_t launch_single2(uint32_t n_cosets, dim3 grid, cudaStream_t s, const NttPassArgs& a)
+{
+    const size_t smem = ((size_t)Ntt2Cfg<LOG_R>::TILE_WORDS + Ntt2Cfg<LOG_R>::TW_WORDS) * 4;
+    if (n_cosets == 8) return launch_k(ntt2_final_kernel<LOG_R, 3, true>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
+    return launch_k(ntt2_final_kernel<LOG_R, 0, true>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
+}
 // which kernel family: 2 (narrow tiles, default from 2^12) or 1; ZK_NTT_V=1 forces the wide-tile kernels (experiments)
 static int ntt_version()
 {
@@ -836,6 +862,26 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     const bool v2 = mu >= (uint32_t)ntt2_min_mu() && ntt_version() == 2;
     NttPlan p = v2 ? make_plan2(mu) : make_plan(mu, log_arrays);
     NttPassArgs a{};
+    if (mu >= 6 && mu <= 10 && ntt_version() == 2) {
+        // the whole transform in one narrow-tile CTA per proof: arrays are single rows
+        a.log_M = mu; a.inverse = inverse; a.hpow = T.hpow; a.wpow = T.wpow; a.coset_base = coset_base;
+        if (pack) a.pack = *pack;
+        a.tw = (inverse ? T.tw_inv : T.tw_fwd) + tw_off(mu);
+        a.src = coeffs; a.src_stride = coeffs_stride; a.dst = dst; a.dst_stride = dst_stride;
+        a.use_scale = use_scale; a.scale_m = scale_m; a.use_coset = coset_scale;
+        a.log_Msub = mu;
+        dim3 grid(1, batch);
+        cudaError_t e1;
+        switch (mu) {
+            case 6: e1 = launch_single2<6>(n_cosets, grid, s, a); break;
+            case 7: e1 = launch_single2<7>(n_cosets, grid, s, a); break;
+            case 8: e1 = launch_single2<8>(n_cosets, grid, s, a); break;
+            case 9: e1 = launch_single2<9>(n_cosets, grid, s, a); break;
+            default: e1 = launch_single2<10>(n_cosets, grid, s, a); break;
+        }
+        if (e1 == cudaSuccess && n_launches) (*n_launches)++;
+        return e1;
+    }
     a.log_M = mu;
     a.inverse = inverse;
     a.hpow = T.hpow;

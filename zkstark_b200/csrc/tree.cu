@@ -852,6 +852,49 @@ __global__ void __launch_bounds__(TILE_PAIRS) tree_tile_kernel(const TreeArgs a)
     if (t == 0 && a.post != POST_NONE) post_root(a, b, root);
 }
 
+// ---------------------------------------------------------------- FRI tail: the small layers of a proof in ONE launch
+// Once a layer fits a single tile (<= 2^TILE_MIN_LOG values) nothing is left to spread over SMs: fold, leaf hashes, the
+// levels, the channel step that draws the next beta (prover.rs:200-224) -- and the same for every following layer down to
+// the 8-value last one with its free term and query draw (prover.rs:254,263) -- run back to back in one CTA per proof.
+// Saves a launch (and its dependent-launch hand-over) per layer on the latency path of every proof.
+template <int V = ZK_TILE_SHA_V>
+__global__ void __launch_bounds__(TILE_PAIRS) fri_tail_kernel(const TreeArgs a0, uint32_t last_layer)
+{
+    pdl_wait();
+    TreeArgs a = a0;                                               // the layer-dependent fields advance in the loop
+    TileBufs tb;
+    tb.P = blockDim.x;
+    tb.A = tile_smem;
+    tb.B = tile_smem + 8 * tb.P;
+    tb.coop = 12 * tb.P;
+    tb.coop_cnt = a.coop_cnt;
+    const uint32_t b = blockIdx.y, t = threadIdx.x;
+    for (;;) {
+        uint8_t* heap = a.heap + (size_t)b * a.heap_stride;
+        if (2 * t < (1u << a.log_size)) produce_values<SRC_FOLD>(a, b, 2 * t, 2);   // polynomial.rs:385-400 in evaluation form
+        __syncthreads();
+        const uint32_t* vals = a.vals + (size_t)b * a.vals_stride;
+        uint32_t root[8];
+        tile_reduce<SRC_FOLD, V>(a, heap, vals, a.log_size, 0, a.log_size, false, tb, root);
+        const bool done = a.fri_layer >= last_layer;
+        if (done) pdl_trigger();
+        if (t == 0) post_root(a, b, root);                         // commit the root; next beta, or free term + query
+        if (done) break;
+        __syncthreads();                                           // beta and the layer's values are visible to the whole CTA
+        const uint32_t len = 1u << a.log_size;
+        a.fold.cur = a.vals;
+        a.fold.cur_stride = a.vals_stride;
+        a.fold.layer_k += 1;
+        a.fold.winv2k_m = mont_mul(a.fold.winv2k_m, a.fold.winv2k_m);   // (5^(2^(k+1)))^-1, Montgomery form
+        a.vals += len;
+        a.heap += 64 * (size_t)len;
+        a.log_size -= 1;
+        a.in_level = a.log_size;
+        a.fold.log_half = a.log_size;
+        a.fri_layer += 1;
+    }
+}
+
 // ---------------------------------------------------------------- stand-alone stage kernels
 __global__ void __launch_bounds__(256) fold_kernel(const uint32_t* cur, uint32_t* next, FoldArgs f, PowTab pw,
                                                    uint64_t next_stride, const ProofState* st)
@@ -1311,6 +1354,31 @@ static cudaError_t launch_tile_src(cudaStream_t s, int src, const TreeArgs& a, u
         case SRC_DIGESTS: return launch_tile<SRC_DIGESTS>(s, a, batch);
         default: return cudaErrorInvalidValue;
     }
+}
+// layers fri_layer .. last_layer of a proof (all single tiles: a.log_size <= TILE_MIN_LOG), one CTA per proof
+cudaError_t launch_fri_tail(cudaStream_t s, TreeArgs a, uint32_t batch, uint32_t last_layer)
+{
+    if (a.log_size > TILE_MIN_LOG || a.log_size < 1) return cudaErrorInvalidValue;
+    const TreeTune& T = tune_of(a);
+    a.in_level = a.log_size;
+    a.log_tile = a.log_size;
+    uint32_t threads = 1u << (a.log_size - 1);
+    if (threads < 32) threads = 32;
+    uint32_t coop = T.coop_cnt > 32 * COOP_PAIRS ? 32 * COOP_PAIRS : T.coop_cnt;
+    if (coop) {
+        uint32_t need = 2 * (threads < coop ? threads : coop);
+        need = (need + 63) & ~63u;
+        if (need > threads) threads = need;
+    }
+    a.coop_cnt = coop;
+    const uint32_t npair = coop ? (threads / 64 < COOP_PAIRS ? threads / 64 : COOP_PAIRS) : 0;
+    const size_t smem = 4 * ((size_t)12 * threads + (size_t)COOP_WORDS * npair);
+    {
+        static bool attr_done[64] = {};
+        cudaError_t e = set_max_smem_once(attr_done, fri_tail_kernel<>, (int)(4 * (12 * TILE_PAIRS + COOP_WORDS * COOP_PAIRS)));
+        if (e != cudaSuccess) return e;
+    }
+    return zk_launch(fri_tail_kernel<>, dim3(1, batch), dim3(threads), smem, s, a, last_layer);
 }
 // CTA epilogue levels of a pass over 2^in_level inputs with 2^k per thread, never going above heap level `floor`
 // (needs full CTAs: at least PASS_THREADS threads)
