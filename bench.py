@@ -160,6 +160,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def leaf_hash_logic_ops():
+    """SHF + LOP3 operations one Merkle leaf costs at the very least (merkle.rs:30-46: leaf = SHA256(BE32(v)), node =
+    SHA256(L || R) = data block + constant padding block), with 3-input logic and funnel shifts:
+      round: Sigma0, Sigma1 (3 SHF + 1 LOP3 each), Ch, Maj (1 LOP3 each) = 10; round 0 of a block that starts from the IV
+             has constant inputs (0);
+      schedule word: sigma0, sigma1 (3 SHF + 1 LOP3 each) = 8, nothing for a sigma of a compile-time constant: the leaf
+             block is one value + 15 constant words, the padding block is all constants."""
+    rounds = 10 * 64 * 3 - 10 * 2                       # leaf block and node data block start from the IV
+    node_sched = 8 * 48
+    const = [False] + [True] * 15                       # W0 = v, W1..W15 constants (0x80000000, 0.., 32)
+    leaf_sched = 0
+    for t in range(16, 64):
+        leaf_sched += (0 if const[t - 2] else 4) + (0 if const[t - 15] else 4)
+        const.append(const[t - 2] and const[t - 7] and const[t - 15] and const[t - 16])
+    return rounds + node_sched + leaf_sched             # 1900 + 384 + 292 = 2576
+
+
 def hashlib_sha(hex_list):
     import hashlib
     return hashlib.sha256("".join(hex_list).encode()).hexdigest()
@@ -180,6 +197,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the trace workers of zk_prove_stream_submit: the ranks of a node share its cores (one process per GPU), and the
+    # thread that issues the launches needs one of them
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = max(1, cores // max(local_world, 1) - (1 if local_world > 1 else 0))
+    os.environ.setdefault("ZK_HOST_THREADS", str(host_threads))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -298,6 +324,7 @@ def main():
                        "step ahead and uploaded from pinned memory on a side stream (H2D), transcripts + states out (D2H); the "
                        "first step's trace generation is not overlapped and is inside the timed region",
                 "h2d_note": "the library uploads the traces it generates: 4 (n - 1) bytes per proof, counted here",
+                "host_threads_per_rank": int(os.environ.get("ZK_HOST_THREADS", "0")),
                 "parity": bool(e2e_digests == digests)},
         "e2e_from_trace": {"value": world * nb * args.steps / (ft_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(4 * (n - 1) * nb),
                            "api": "zk_prove_fibsq_batch: pinned host traces in (H2D inside), transcripts out"},
@@ -577,30 +604,48 @@ def extras(args, ctx, zk, line, clocks, world, step_resident):
     # actually issued (static SASS count per leaf x leaves) / live launch time; peak = the same pipe measured
     # live with a SHF/LOP3/IADD3 microbenchmark.  The HBM view of the same launch is given beside it.
     counts = json.load(open(os.path.join(ROOT, "zkstark_b200", "sass_counts.json")))
+    fresh = False
     try:
-        counts.update(json.load(open(os.path.join(ROOT, "zkstark_b200", "ncu_counts.json"))))
+        nc = json.load(open(os.path.join(ROOT, "zkstark_b200", "ncu_counts.json")))
+        import hashlib
+        h = hashlib.sha256()
+        for src in ("sha256.cuh", "tree.cu", "field.cuh", "common.cuh"):
+            h.update(open(os.path.join(ROOT, "zkstark_b200", "csrc", src), "rb").read())
+        fresh = nc.get("source_sha256") == h.hexdigest()      # the capture describes the code that is being timed
+        counts.update(nc)
     except Exception:
         pass
     log_leaves = k + 3
     ms_leaf, ms_leaf_min, _ = ctx.bench_kernel(0, log_leaves, iters=10, flush_l2=True)
     _, _, int_peak = ctx.bench_kernel(6, 0, iters=5, flush_l2=False)
     leaves = 1 << log_leaves
-    # dynamic ALU-pipe instructions per leaf (one leaf hash + one node hash; loops are rolled, so this is
-    # the ncu count smsp__inst_executed_pipe_alu / leaves of the committed profile, not the static SASS size)
-    alu_ops = counts.get("alu_dyn_per_leaf", counts["alu_per_leaf"]) * leaves
-    ach = alu_ops / (ms_leaf * 1e-3) / 1e12
+    # ALGORITHMIC integer work per leaf (one leaf hash + one node hash = 3 compressions): the funnel shifts and 3-input
+    # logic operations SHA-256 cannot do without (leaf_hash_logic_ops below).  They can only run on the ALU pipe; the
+    # additions can (and in this kernel do) go to the FMA pipe.
+    alg_ops_per_leaf = leaf_hash_logic_ops()
+    ach_alg = alg_ops_per_leaf * leaves / (ms_leaf * 1e-3) / 1e12
+    # EXECUTED ALU-pipe instructions per leaf (ncu capture of this very code, else the algorithmic count)
+    alu_dyn = counts.get("alu_dyn_per_leaf") if fresh else None
+    ach = (alu_dyn if alu_dyn else alg_ops_per_leaf) * leaves / (ms_leaf * 1e-3) / 1e12
     alg_bytes = 4 * leaves + 32 * (2 * leaves - (leaves >> 5))
+    traffic = counts.get("dram_bytes_per_launch") if (log_leaves == 23 and fresh) else None
     line["roofline"] = {
-        "kernel": "tree_pass_kernel<values> (Merkle leaf pass, 2^%d leaves, 32 leaves + 31 nodes per thread)" % log_leaves,
+        "kernel": "tree_pass_kernel<values> (Merkle leaf pass, 2^%d leaves, 32 leaves + 31 nodes per thread + one CTA epilogue level: "
+                  "the production launch shape)" % log_leaves,
         "bound": "int", "achieved": ach, "peak": int_peak, "unit": "Tiop/s", "frac": ach / int_peak if int_peak else None,
-        "peak_source": "measured live: zk_bench_kernel(6) SHF/LOP3/IADD3 microbenchmark on this GPU",
+        "achieved_is": ("executed ALU-pipe instructions (ncu capture of this source, zkstark_b200/ncu_counts.json) / live launch time"
+                        if alu_dyn else "algorithmic SHF/LOP3 operations / live launch time (no ncu capture of this exact source)"),
+        "achieved_algorithmic": ach_alg, "frac_algorithmic": ach_alg / int_peak if int_peak else None,
+        "algorithmic_ops_per_leaf": alg_ops_per_leaf, "executed_alu_per_leaf": alu_dyn, "ncu_counts_match_source": fresh,
+        "int_peak_tiops": int_peak,
+        "peak_source": "measured live in this run: zk_bench_kernel(6) SHF/LOP3/IADD3 microbenchmark on this GPU (MEASURED_PEAKS.json has no integer figure)",
         "ms_per_launch": ms_leaf, "compressions_per_s": 3 * leaves / (ms_leaf * 1e-3),
         "hbm": {"achieved": alg_bytes / (ms_leaf * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (ms_leaf * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                "bound": "hbm", "traffic": counts.get("dram_bytes_per_launch") if log_leaves == 23 else None,
-                "note": "the contract's HBM view of the same launch: 6 % of the copy bandwidth, i.e. NOT the bound of this kernel"},
+                "bound": "hbm", "traffic": traffic,
+                "note": "the contract's HBM view of the same launch: ~6 % of the copy bandwidth, i.e. NOT the bound of this kernel"},
         # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the committed `ncu --set full` capture
-        "traffic": counts.get("dram_bytes_per_launch") if log_leaves == 23 else None,
+        "traffic": traffic,
         "share_of_step": None,
         "note": "SHA-256 Merkle hashing is integer-pipe bound (north_star: INT roofline for hashing, HBM roofline for NTT/fold)",
     }
@@ -623,6 +668,22 @@ def extras(args, ctx, zk, line, clocks, world, step_resident):
         gbs = nbytes / (ms * 1e-3) / 1e9
         rk[name] = {"bound": "hbm", "ms": ms, "algorithmic_bytes": nbytes, "achieved": gbs, "peak": hbm_peak,
                     "unit": "GB/s", "frac": gbs / hbm_peak}
+    # the transforms are integer-ISSUE bound, not HBM bound (p > 2^31: a butterfly is 10 instructions, 3 of them 64-bit-result
+    # multiplications): their roofline is the butterfly rate of the same arithmetic without any memory traffic, measured live
+    try:
+        _, _, tbf = ctx.bench_kernel(8, 0, iters=5, flush_l2=False)       # tera-butterflies / s
+        _, _, tmm = ctx.bench_kernel(8, 1, iters=5, flush_l2=False)       # tera-Montgomery-products / s
+        for name, kk, arrays, extra_mul in (("lde (all passes)", k, 8, 3), ("lde (all passes) @2^24 trace", 24, 8, 5), ("interpolate (all passes)", k, 1, 2)):
+            pts = arrays << kk
+            bf = pts * kk / 2                                             # butterflies of the transform(s)
+            passes = (kk + 9) // 10
+            mm = pts * (2 * (passes - 1) + (1 if arrays == 8 else 0))     # inter-pass twiddle (apply + chain) and coset products
+            floor_ms = 1e3 * (bf / (tbf * 1e12) + mm / (tmm * 1e12))
+            rk[name]["instr_roofline"] = {"bound": "int-issue", "butterflies": bf, "extra_products": mm, "floor_ms": floor_ms,
+                                          "frac": floor_ms / rk[name]["ms"],
+                                          "peak": tbf, "peak_unit": "T butterflies/s (zk_bench_kernel(8), live)"}
+    except Exception as ex:
+        rk["instr_roofline_error"] = repr(ex)
     line["roofline_hbm_kernels"] = rk
 
     if world == 1:

@@ -1451,6 +1451,8 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
             case 0: {
                 TreeArgs a = ta; a.in_level = log_size;
                 a.k = ctx->bench_k ? ctx->bench_k : (log_size > 15 ? 5 : 1);
+                // the production launch shape of a single proof: one CTA epilogue level (tree.cu pick_ep)
+                a.ep_levels = (ctx->tune.pass_epilogue && log_size >= a.k + 8) ? 1 : 0;
                 e = launch_tree_leaf_pass(s, a, 1, ctx->bench_variant); nl++;
                 break;
             }
