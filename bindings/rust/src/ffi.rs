@@ -24,6 +24,7 @@ extern "C" {
     pub fn zk_last_error(ctx: *const zk_ctx) -> *const c_char;
     pub fn zk_version() -> *const c_char;
     pub fn zk_ctx_synchronize(ctx: *mut zk_ctx) -> c_int;
+    pub fn zk_ctx_stream(ctx: *const zk_ctx) -> *mut c_void;
     pub fn zk_ctx_launch_count(ctx: *const zk_ctx) -> u64;
     pub fn zk_ctx_last_stage_ms(ctx: *mut zk_ctx, out_ms: *mut f32) -> c_int;
     pub fn zk_ctx_set_stage_timing(ctx: *mut zk_ctx, on: c_int) -> c_int;

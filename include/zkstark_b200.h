@@ -52,6 +52,9 @@ void zk_ctx_destroy(zk_ctx *ctx);
 const char *zk_last_error(const zk_ctx *ctx);
 const char *zk_version(void);
 int zk_ctx_synchronize(zk_ctx *ctx);
+/* the cudaStream_t every call of this context enqueues on (its own, or the one given to zk_ctx_create_on_stream): callers
+ * that mix their own device work with `_dev` calls must issue it on this stream or order it with events */
+void *zk_ctx_stream(const zk_ctx *ctx);
 /* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
 uint64_t zk_ctx_launch_count(const zk_ctx *ctx);
 /* device-side time of the last zk_prove_* call in ms, by stage:

@@ -51,6 +51,7 @@ def lib():
         "zk_last_error": ([vp], C.c_char_p),
         "zk_version": ([], C.c_char_p),
         "zk_ctx_synchronize": ([vp], i32),
+        "zk_ctx_stream": ([vp], vp),
         "zk_ctx_launch_count": ([vp], u64),
         "zk_ctx_last_stage_ms": ([vp, vp], i32),
         "zk_ctx_set_stage_timing": ([vp, i32], i32),
@@ -483,6 +484,10 @@ class Context:
     def shard_fri_tail(self, log_n, first_layer, layers_ptr, heaps_ptr, state_ptr, transcript_ptr):
         self._ck(lib().zk_shard_fri_tail_dev(self._h, log_n, first_layer, C.c_void_p(layers_ptr), C.c_void_p(heaps_ptr),
                                              C.c_void_p(state_ptr), C.c_void_p(transcript_ptr)))
+
+    def stream(self):
+        """raw cudaStream_t of the context (0 for the legacy default stream)"""
+        return lib().zk_ctx_stream(self._h) or 0
 
     def synchronize(self):
         self._ck(lib().zk_ctx_synchronize(self._h))

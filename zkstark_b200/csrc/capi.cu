@@ -526,6 +526,7 @@ void zk_ctx_destroy(zk_ctx* ctx)
 
 const char* zk_last_error(const zk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 uint64_t zk_ctx_launch_count(const zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* zk_ctx_stream(const zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int zk_ctx_synchronize(zk_ctx* ctx)
 {
     if (!ctx) return ZK_ERR_INVALID;

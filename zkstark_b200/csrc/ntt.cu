@@ -859,7 +859,8 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     if (n_cosets != 1 && n_cosets != 8) return cudaErrorInvalidValue;
     uint32_t log_arrays = 0;
     while ((1u << log_arrays) < n_cosets * batch) log_arrays++;
-    const bool v2 = mu >= (uint32_t)ntt2_min_mu() && ntt_version() == 2;
+    // a single array below 2^22 is too few narrow tiles to fill the machine (2^20 interpolation out of DRAM: 39 vs 28 us)
+    const bool v2 = mu >= (uint32_t)ntt2_min_mu() && ntt_version() == 2 && (n_cosets * batch >= 8 || mu >= 22);
     NttPlan p = v2 ? make_plan2(mu) : make_plan(mu, log_arrays);
     NttPassArgs a{};
     if (mu >= 6 && mu <= 10 && ntt_version() == 2) {

@@ -115,6 +115,11 @@ class ShardedProver:
         self.log_N = log_n + 3
         self.N = 1 << self.log_N
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        # torch ops (copies, packs, collectives) and the ctx kernels are interleaved through raw pointers: they must be
+        # ordered by ONE stream.  Create the context on torch's current stream (zk.Context(dev, stream=s.cuda_stream)).
+        if ctx.stream() != torch.cuda.current_stream(self.dev).cuda_stream:
+            raise ValueError("ShardedProver: the zk context must enqueue on torch's current stream "
+                             "(zk.Context(device, stream=torch.cuda.current_stream().cuda_stream))")
         if self.G not in (1, 2, 4, 8):
             raise ValueError("world size must be 1, 2, 4 or 8 (the LDE has 8 cosets)")
         if log_block < 5 or (self.N // self.G) < (1 << (log_block + 1)):
@@ -294,8 +299,12 @@ class ShardedProver:
         full = self.comm.all_reduce_max(transcripts)
         self.comm_bytes += tl
         results = []
+        flag_off = (tl + 3) & ~3
         for idx in range(nr):
-            tr = full[idx][:tl].cpu().numpy().tobytes()
+            host_tr = full[idx].cpu().numpy()
+            if int(host_tr[flag_off: flag_off + 4].view(np.uint32)[0]) != 0:     # set by zk_shard_decommit_dev
+                raise RuntimeError("last FRI layer is not constant (prover.rs:238)")
+            tr = host_tr[:tl].tobytes()
             st_host = states[idx].cpu().numpy().view(np.uint32)
             # channel.rs:19-26 over the decommitment records (host; k + 4 sequential hashes)
             state = b"".join(struct.pack(">I", int(w)) for w in st_host[47:55])
