@@ -37,6 +37,9 @@ extern "C" {
     pub fn zk_merkle_trace(heap: *const u8, size: u64, index: u64, path_out: *mut u8) -> c_int;
     pub fn zk_transcript_len(log_n: u32) -> usize;
     pub fn zk_prove_fibsq(ctx: *mut zk_ctx, log_n: u32, secret: u32, transcript_out: *mut u8, cap: usize, len_out: *mut usize, state_out: *mut u8) -> c_int;
+    pub fn zk_transcript_len_ex(log_n: u32, n_extra_queries: u32) -> usize;
+    pub fn zk_prove_fibsq_ex(ctx: *mut zk_ctx, log_n: u32, secret: u32, init_state: *const u8, n_extra_queries: u32, transcript_out: *mut u8, cap: usize, len_out: *mut usize, state_out: *mut u8) -> c_int;
+    pub fn zk_verify_fibsq_ex(log_n: u32, a_last: u32, transcript: *const u8, len: usize, state: *const u8, init_state: *const u8, n_extra_queries: u32, rederive: c_int, failed_check: *mut c_int) -> c_int;
     pub fn zk_prove_fibsq_from_trace(ctx: *mut zk_ctx, log_n: u32, trace: *const u32, transcript_out: *mut u8, cap: usize, len_out: *mut usize, state_out: *mut u8) -> c_int;
     pub fn zk_prove_fibsq_batch(ctx: *mut zk_ctx, log_n: u32, n_proofs: u32, traces: *const u32, transcripts_out: *mut u8, states_out: *mut u8) -> c_int;
     pub fn zk_prove_fibsq_batch_secrets(ctx: *mut zk_ctx, log_n: u32, n_proofs: u32, secrets: *const u32, transcripts_out: *mut u8, states_out: *mut u8) -> c_int;

@@ -101,6 +101,18 @@ size_t zk_transcript_len(uint32_t log_n);
  * Proof.state.  The trace is generated on the host (prover.rs:32-39 is sequential). */
 int zk_prove_fibsq(zk_ctx *ctx, uint32_t log_n, uint32_t secret, uint8_t *transcript_out, size_t cap,
                    size_t *len_out, uint8_t state_out[32]);
+/* The reference's protocol with the two extensions its readme.md:1 and SURVEY.md 8(f) name: a caller-chosen ("random") initial
+ * channel state instead of Channel::new()'s zeros (init_state: 32 bytes, or NULL), and n_extra_queries further test points,
+ * each drawn from the channel like the first (prover.rs:263) once the records of the previous one are committed: the
+ * transcript is the reference's, followed n_extra_queries times by the raw query word (u32 LE) and the 4 + log_n records
+ * of x = word % (8n - 16) -- zk_transcript_len_ex(log_n, n_extra_queries) bytes.  With NULL and 0 this is zk_prove_fibsq;
+ * zk_verify_fibsq_ex checks such a proof (every test point against proof.rs:63-148, every challenge and test point
+ * against the replayed channel when rederive != 0). */
+size_t zk_transcript_len_ex(uint32_t log_n, uint32_t n_extra_queries);
+int zk_prove_fibsq_ex(zk_ctx *ctx, uint32_t log_n, uint32_t secret, const uint8_t *init_state, uint32_t n_extra_queries,
+                      uint8_t *transcript_out, size_t cap, size_t *len_out, uint8_t state_out[32]);
+int zk_verify_fibsq_ex(uint32_t log_n, uint32_t a_last, const uint8_t *transcript, size_t len, const uint8_t *state,
+                       const uint8_t *init_state, uint32_t n_extra_queries, int rederive, int *failed_check);
 /* same, from a caller-provided host trace of 2^log_n - 1 values (H2D copy is part of the call) */
 int zk_prove_fibsq_from_trace(zk_ctx *ctx, uint32_t log_n, const uint32_t *trace, uint8_t *transcript_out,
                               size_t cap, size_t *len_out, uint8_t state_out[32]);

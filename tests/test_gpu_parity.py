@@ -431,3 +431,51 @@ def test_field_ops_direct(ctx, orc):
         xi = int(x[i])
         assert int(out[4, i]) == (L.orc_inv(xi, P) if xi else 0)
         assert int(out[5, i]) == L.orc_pow(xi, int(b[i]), P) == pow(xi, int(b[i]), P)
+
+
+@pytest.mark.parametrize("log_n", [6, 10, 13])
+def test_prove_ex_seeded_channel_and_channel_drawn_queries(ctx, log_n):
+    """SURVEY 8(f) rank 2 (readme.md:1, prover.rs:263): a caller-chosen initial channel state and further test points drawn
+    from the channel.  With neither it is the reference's proof; with them the product verifier replays the channel from
+    the seed and checks every test point against proof.rs:63-148."""
+    k = log_n
+    base_tr, base_st = ctx.prove_fibsq(k)
+    assert ctx.prove_fibsq_ex(k) == (base_tr, base_st)
+    a_last = int(zk.trace_fibsq(k)[-1])
+    # further test points on the reference's own channel: the reference transcript is a prefix
+    tr2, st2 = ctx.prove_fibsq_ex(k, 3141592, None, 2)
+    dl = zk.lib().zk_decommit_len(k)
+    assert len(tr2) == len(base_tr) + 2 * (4 + dl) == zk.lib().zk_transcript_len_ex(k, 2)
+    assert tr2[: len(base_tr)] == base_tr and st2 != base_st
+    assert zk.verify_fibsq_ex(k, a_last, tr2, st2, None, 2) == (True, 0)
+    # each further opening is what zk_open_queries returns for the channel-drawn position
+    off = len(base_tr)
+    xs = []
+    for _ in range(2):
+        xs.append(int.from_bytes(tr2[off: off + 4], "little") % ((8 << k) - 16))
+        off += 4 + dl
+    ctx.prove_fibsq(k)
+    opened = ctx.open_queries(k, xs)
+    off = len(base_tr)
+    for o in opened:
+        assert tr2[off + 4: off + 4 + dl] == o
+        off += 4 + dl
+    # seeded channel
+    seed = bytes((7 * i + 1) & 0xFF for i in range(32))
+    tr, st = ctx.prove_fibsq_ex(k, 3141592, seed, 3)
+    assert tr[:32] == base_tr[:32]                       # the f root does not depend on the channel ...
+    assert tr[32:44] != base_tr[32:44]                   # ... the challenges do
+    assert zk.verify_fibsq_ex(k, a_last, tr, st, seed, 3) == (True, 0)
+    assert zk.verify_fibsq_ex(k, a_last, tr, None, seed, 3, rederive=False) == (True, 0)   # the reference's checks alone
+    ok, line = zk.verify_fibsq_ex(k, a_last, tr, st, None, 3)                               # replayed from the wrong state
+    assert not ok and line == 22
+    ok, line = zk.verify_fibsq_ex(k, a_last, tr, st, seed, 2)                               # wrong number of test points
+    assert not ok and line == 20
+    bad = bytearray(tr)
+    bad[-40] ^= 1                                                                           # a digest of the last opening
+    ok, line = zk.verify_fibsq_ex(k, a_last, bytes(bad), st, seed, 3)
+    assert not ok and line in (136, 140, 6)
+    bad = bytearray(tr)
+    bad[len(base_tr) + 1] ^= 4                                                              # a channel-drawn query word
+    ok, line = zk.verify_fibsq_ex(k, a_last, bytes(bad), st, seed, 3)
+    assert not ok and line == 37

@@ -23,6 +23,7 @@ from ._binding import (  # noqa: F401
     proof_serialize,
     proof_deserialize,
     verify_fibsq,
+    verify_fibsq_ex,
 )
 from .api import (  # noqa: F401
     Channel,

@@ -70,6 +70,9 @@ def lib():
         "zk_prove_fibsq_batch": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_trace_fibsq": ([u32, u32, vp], i32),
         "zk_prove_fibsq_batch_secrets": ([vp, u32, u32, vp, vp, vp], i32),
+        "zk_transcript_len_ex": ([u32, u32], sz),
+        "zk_prove_fibsq_ex": ([vp, u32, u32, vp, u32, vp, sz, C.POINTER(sz), vp], i32),
+        "zk_verify_fibsq_ex": ([u32, u32, vp, sz, vp, vp, u32, i32, C.POINTER(i32)], i32),
         "zk_prove_stream_submit": ([vp, u32, u32, vp], i32),
         "zk_prove_stream_collect": ([vp, vp, vp], i32),
         "zk_sha256": ([vp, sz, vp], None),
@@ -182,6 +185,16 @@ def proof_deserialize(blob):
         raise ZkError(rc, "truncated proof" if rc == -4 else "proof length prefix does not match the payload")
     off = ptr.value - C.addressof(buf)
     return bytes(st), blob[off: off + n.value]
+
+
+def verify_fibsq_ex(log_n, a_last, transcript, state=None, init_state=None, n_extra_queries=0, rederive=True):
+    """zk_verify_fibsq_ex: a proof with a seeded channel and channel-drawn further test points.  -> (ok, failed_check)"""
+    fc = C.c_int(0)
+    rc = lib().zk_verify_fibsq_ex(log_n, a_last, transcript, len(transcript), state, init_state, n_extra_queries, int(rederive),
+                                  C.byref(fc))
+    if rc not in (0, -6):
+        raise ZkError(rc, "zk_verify_fibsq_ex: invalid argument")
+    return rc == 0, fc.value
 
 
 def merkle_trace_host(heap, index):
@@ -352,6 +365,15 @@ class Context:
         st = np.empty(32, dtype=np.uint8)
         n = C.c_size_t(0)
         self._ck(lib().zk_prove_fibsq(self._h, log_n, secret, _p(tr), cap, C.byref(n), _p(st)))
+        return tr[: n.value].tobytes(), st.tobytes()
+
+    def prove_fibsq_ex(self, log_n, secret=3141592, init_state=None, n_extra_queries=0):
+        """zk_prove_fibsq_ex: seeded initial channel state (32 bytes or None) and channel-drawn further test points."""
+        cap = lib().zk_transcript_len_ex(log_n, n_extra_queries)
+        tr = np.empty(cap, dtype=np.uint8)
+        st = np.empty(32, dtype=np.uint8)
+        n = C.c_size_t(0)
+        self._ck(lib().zk_prove_fibsq_ex(self._h, log_n, secret, init_state, n_extra_queries, _p(tr), cap, C.byref(n), _p(st)))
         return tr[: n.value].tobytes(), st.tobytes()
 
     def prove_fibsq_from_trace(self, log_n, trace):

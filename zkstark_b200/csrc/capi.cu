@@ -245,7 +245,7 @@ int enqueue_prove(zk_ctx* ctx, cudaStream_t s, uint32_t log_n, uint32_t p0, uint
     uint8_t* trd = (uint8_t*)ctx->transcripts.p + (size_t)p0 * trs;
 
     if (tm) tm->mark();
-    CK(launch_state_init(s, states, traces, n, log_n, nb));
+    CK(launch_state_init(s, states, traces, n, log_n, nb, ctx->chan_seed));
     nl++;
     // Part 1 (prover.rs:60-85)
     CK(launch_interpolate(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, true, traces, n, coeffs, n, nb, &nl,
@@ -1008,7 +1008,53 @@ int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transc
     return zk_prove_fibsq_from_trace(ctx, log_n, a.data(), transcript_out, cap, len_out, state_out);
 }
 
-// more query positions than the single one the reference draws.  The evaluation arrays and Merkle heaps
+// the reference's protocol with a seeded ("random", readme.md:1) initial channel state and with more
+// test points than its single one, every further one drawn from the channel like the first (prover.rs:263): after the
+// reference's transcript come, n_extra_queries times, the raw query word and the same 4 + log_n records for
+// x = word % (8n - 16).  The evaluation arrays and heaps of the proof are still resident, so a further test point is one
+// gather (zk_open_queries) and 4 + log_n host hashes.  With init_state null and n_extra_queries 0: zk_prove_fibsq.
+int zk_prove_fibsq_ex(zk_ctx* ctx, uint32_t log_n, uint32_t secret, const uint8_t* init_state, uint32_t n_extra_queries,
+                      uint8_t* transcript_out, size_t cap, size_t* len_out, uint8_t state_out[32])
+{
+    int rc = check_log_n(ctx, log_n);
+    if (rc) return rc;
+    if (!transcript_out || !state_out || n_extra_queries > 65535) return fail(ctx, ZK_ERR_INVALID, "bad argument");
+    const size_t base = transcript_len(log_n), dl = zk_decommit_len(log_n), total = base + (size_t)n_extra_queries * (4 + dl);
+    if (cap < total) return fail(ctx, ZK_ERR_BUFFER, "transcript buffer too small (zk_transcript_len_ex)");
+    if (init_state)
+        for (int i = 0; i < 8; i++)
+            ctx->chan_seed.w[i] = ((uint32_t)init_state[4 * i] << 24) | ((uint32_t)init_state[4 * i + 1] << 16) |
+                                  ((uint32_t)init_state[4 * i + 2] << 8) | init_state[4 * i + 3];
+    rc = zk_prove_fibsq(ctx, log_n, secret, transcript_out, cap, nullptr, state_out);
+    ctx->chan_seed = ChanSeed{};
+    if (rc) return rc;
+    const uint32_t L = log_n, log_N = log_n + LOG_BLOWUP;
+    const uint64_t N = (uint64_t)1 << log_N;
+    std::vector<uint8_t> buf(32 + 24 + 64 * (size_t)log_N);
+    uint8_t* st = state_out;
+    for (uint32_t q = 0; q < n_extra_queries; q++) {
+        uint8_t* out = transcript_out + base + (size_t)q * (4 + dl);
+        const uint32_t f = ((uint32_t)st[0] << 24) | ((uint32_t)st[1] << 16) | ((uint32_t)st[2] << 8) | st[3];   // channel.rs:28-32
+        out[0] = (uint8_t)f; out[1] = (uint8_t)(f >> 8); out[2] = (uint8_t)(f >> 16); out[3] = (uint8_t)(f >> 24);
+        memcpy(buf.data(), st, 32);
+        memcpy(buf.data() + 32, out, 4);
+        sha::host_sha256(buf.data(), 36, st);
+        const uint32_t x = (uint32_t)((uint64_t)f % (N - 16));                                                    // prover.rs:263
+        if ((rc = zk_open_queries(ctx, log_n, 0, &x, 1, out + 4, dl))) return rc;
+        size_t off = 4;
+        for (uint32_t r = 0; r < 4 + L; r++) {                                                                    // prover.rs:274-288
+            const size_t len = r < 4 ? 12 + 32 * (size_t)log_N : 24 + 64 * (size_t)(log_N - (r - 4));
+            memcpy(buf.data(), st, 32);
+            memcpy(buf.data() + 32, out + off, len);
+            sha::host_sha256(buf.data(), 32 + len, st);
+            off += len;
+        }
+    }
+    if (len_out) *len_out = total;
+    return ZK_OK;
+}
+
+// more query positions than the single one the reference draws, at positions the caller chooses.  The evaluation arrays and Merkle heaps
 // of the last prove call are still resident, so further openings are one more gather.
 size_t zk_decommit_len(uint32_t log_n) { return transcript_len(log_n) - tr_off_decommit(log_n); }
 

@@ -267,8 +267,9 @@ cudaError_t launch_shard_decommit(cudaStream_t s, const ShardDecommitArgs& a);
 cudaError_t launch_open_queries(cudaStream_t s, uint32_t log_n, const uint32_t* f_eval, const uint8_t* f_heap,
                                 const uint32_t* layers, const uint8_t* layer_heaps, ProofState* state,
                                 const uint32_t* xs_dev, uint32_t n_q, uint8_t* out_dev, uint64_t out_stride);
+struct ChanSeed { uint32_t w[8]; };   // initial channel state as native words H0..H7 (zeros: Channel::new(), channel.rs:12-17)
 cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
-                              uint32_t log_n, uint32_t batch);
+                              uint32_t log_n, uint32_t batch, ChanSeed seed);
 // stand-alone element-wise stages (stages in isolation, for the per-function C-ABI)
 cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uint32_t log_half,
                         FoldArgs f, PowTab pow, uint32_t batch, uint64_t next_stride, const ProofState* st = nullptr);

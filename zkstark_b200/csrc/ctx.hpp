@@ -102,6 +102,7 @@ struct zk_ctx {
     int bench_variant = -1;
     uint32_t bench_k = 0;
     bool use_cp_tab = true;               // composition polynomial from per-size constant tables (bench knob)
+    zk::ChanSeed chan_seed{};             // initial channel state of the next proofs (zk_prove_fibsq_ex sets and clears it)
     bool fri_tail = true;                 // the single-tile FRI layers of a proof run in one launch (ZK_NO_FRI_TAIL=1: one each)
     bool lanes = true;                    // batches run as two lanes on two streams (bench knob)
     zk::TreeTune tune;                    // launch-shape knobs of the tree kernels (per context; zk_bench_set*)

@@ -1278,7 +1278,7 @@ cudaError_t launch_chan_tail(cudaStream_t s, ProofState* states, const uint8_t* 
 
 // channel.rs:12-17 + public inputs: zero state, a[0], a[n-2]
 __global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64_t trace_stride,
-                                  uint32_t log_n, uint32_t batch)
+                                  uint32_t log_n, uint32_t batch, ChanSeed seed)
 {
     pdl_enter();
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1289,6 +1289,7 @@ __global__ void state_init_kernel(ProofState* st, const uint32_t* traces, uint64
     const uint32_t* tr = traces + (size_t)b * trace_stride;
     s.a_first = tr[0];
     s.a_last = tr[(1u << log_n) - 2];
+    for (int i = 0; i < 8; i++) s.chan[i] = seed.w[i];    // Channel::new() is all zeros (channel.rs:12-17)
     st[b] = s;
 }
 
@@ -1626,9 +1627,9 @@ cudaError_t launch_open_queries(cudaStream_t s, uint32_t log_n, const uint32_t* 
 }
 
 cudaError_t launch_state_init(cudaStream_t s, ProofState* st, const uint32_t* traces, uint64_t trace_stride,
-                              uint32_t log_n, uint32_t batch)
+                              uint32_t log_n, uint32_t batch, ChanSeed seed)
 {
-    return zk_launch(state_init_kernel, dim3((batch + 127) / 128), dim3(128), 0, s, st, traces, trace_stride, log_n, batch);
+    return zk_launch(state_init_kernel, dim3((batch + 127) / 128), dim3(128), 0, s, st, traces, trace_stride, log_n, batch, seed);
 }
 
 cudaError_t launch_fold(cudaStream_t s, const uint32_t* cur, uint32_t* next, uint32_t log_half, FoldArgs f,
