@@ -83,6 +83,7 @@ int get_tables(zk_ctx* ctx, uint32_t log_N, SizeTables** out)
 int init_tw(zk_ctx* ctx)
 {
     // radix tables: for R = 2^m (m = 1..10) the R/2 powers of w_R at offset 2^(m-1)-1
+    const size_t words = ntt_table_words();   // 1024 plain + the narrow-tile kernels' chunked copies (built on the device)
     std::vector<uint32_t> f(1023), inv(1023);
     for (uint32_t m = 1; m <= 10; m++) {
         uint32_t w = h_root(m), wi = h_inv(w), c = 1, ci = 1;
@@ -94,10 +95,12 @@ int init_tw(zk_ctx* ctx)
             ci = h_mul(ci, wi);
         }
     }
-    CK(cudaMalloc(&ctx->tw_fwd, 1023 * 4));
-    CK(cudaMalloc(&ctx->tw_inv, 1023 * 4));
+    CK(cudaMalloc(&ctx->tw_fwd, words * 4));
+    CK(cudaMalloc(&ctx->tw_inv, words * 4));
     CK(cudaMemcpy(ctx->tw_fwd, f.data(), 1023 * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->tw_inv, inv.data(), 1023 * 4, cudaMemcpyHostToDevice));
+    CK(ntt2_build_tables(ctx->stream, ctx->tw_fwd, ctx->tw_inv));
+    CK(cudaStreamSynchronize(ctx->stream));
     return ZK_OK;
 }
 

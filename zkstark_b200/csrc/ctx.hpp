@@ -30,6 +30,8 @@ cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
 double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
 int ntt_pass_times(float ms[4]);
+size_t ntt_table_words();
+cudaError_t ntt2_build_tables(cudaStream_t s, uint32_t* tw_fwd, uint32_t* tw_inv);
 double bench_bfly(cudaStream_t s, uint32_t* out, int n_sm, int mode);
 cudaError_t launch_field_ops(cudaStream_t s, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* out);
 }  // namespace zk

@@ -30,6 +30,7 @@ struct NttPassArgs {
     int use_scale;
     uint32_t scale_m;    // Montgomery constant multiplied into the final outputs (n^-1)
     const uint32_t* tw;  // w_R^j (or inverse), j < R/2, Montgomery form
+    const uint32_t* tw2; // the same radix's twiddles in the narrow-tile kernels' per-thread order (ntt2_build_tables)
     PowTab hpow;         // powers of h, order N = 2^hpow.log_N  (M divides N)
     PowTab wpow;         // powers of 5, exponents < 2^wpow.log_N
     uint32_t log_R1;     // final pass: first-pass radix (0 when single pass)
@@ -382,26 +383,62 @@ struct Ntt2Cfg {
     static constexpr int RF_WORDS = NSLOT * N2_PITCH;  // per-row coset factors in round-0 chunk order (strided pass with COSET)
 };
 
-// twiddle tables of all rounds in per-thread order: T_k[lo * RAD + slot(t, j)] = w_R^(((j << LS) + lo) << (S0 + t))
+// twiddle tables of all rounds in per-thread order: T_k[lo * RAD + slot(t, j)] = w_R^(((j << LS) + lo) << (S0 + t)).
+// Built once per context for every radix and direction (ntt2_build_tables) behind the plain tables; a CTA copies its
+// radix's table into shared memory.
 template <int LOG_R>
-__device__ __forceinline__ void n2_build_twiddles(uint32_t* tw_s, const uint32_t* __restrict__ tw_g)
+__device__ __forceinline__ void n2_fill_twiddles(uint32_t* out, const uint32_t* __restrict__ tw_g, uint32_t tid, uint32_t nthreads)
 {
     using C = Ntt2Cfg<LOG_R>;
 #pragma unroll
     for (int k = 0; k < C::NR; k++) {
-        constexpr int dummy = 0; (void)dummy;
         const N2Round r = n2_round(LOG_R, k);
         const int rad = 1 << r.LR, total = (1 << r.LS) << r.LR;
-        uint32_t* T = tw_s + C::tw_off(k);
-        for (int e = threadIdx.x; e < total; e += C::THREADS) {
+        uint32_t* T = out + C::tw_off(k);
+        for (int e = tid; e < total; e += nthreads) {
             const int lo = e >> r.LR, slot = e & (rad - 1);
-            if (slot == rad - 1) continue;
             int t = 0, off = 0, h = rad >> 1;
-            while (slot >= off + h) { off += h; h >>= 1; t++; }
+            while (h && slot >= off + h) { off += h; h >>= 1; t++; }
             const int j = slot - off;
-            T[e] = tw_g[((j << r.LS) + lo) << (r.S0 + t)];
+            T[e] = slot == rad - 1 ? 0u : tw_g[((j << r.LS) + lo) << (r.S0 + t)];
         }
     }
+}
+// offset (words) of radix 2^LOG_R's chunked table behind the 1024 words of plain tables
+constexpr int NTT2_TAB_BASE = 1024;
+__host__ __device__ constexpr int ntt2_tab_off(int log_r)
+{
+    int o = NTT2_TAB_BASE;
+    if (log_r > 6) o += Ntt2Cfg<6>::TW_WORDS;
+    if (log_r > 7) o += Ntt2Cfg<7>::TW_WORDS;
+    if (log_r > 8) o += Ntt2Cfg<8>::TW_WORDS;
+    if (log_r > 9) o += Ntt2Cfg<9>::TW_WORDS;
+    if (log_r > 10) o += Ntt2Cfg<10>::TW_WORDS;
+    return o;
+}
+__global__ void ntt2_tables_kernel(uint32_t* tw)   // tw: [plain 1023 | pad | chunked tables], built in place
+{
+    const uint32_t t = threadIdx.x, n = blockDim.x;
+    n2_fill_twiddles<6>(tw + ntt2_tab_off(6), tw + ((1 << 5) - 1), t, n);
+    n2_fill_twiddles<7>(tw + ntt2_tab_off(7), tw + ((1 << 6) - 1), t, n);
+    n2_fill_twiddles<8>(tw + ntt2_tab_off(8), tw + ((1 << 7) - 1), t, n);
+    n2_fill_twiddles<9>(tw + ntt2_tab_off(9), tw + ((1 << 8) - 1), t, n);
+    n2_fill_twiddles<10>(tw + ntt2_tab_off(10), tw + ((1 << 9) - 1), t, n);
+}
+size_t ntt_table_words() { return (size_t)ntt2_tab_off(11); }
+cudaError_t ntt2_build_tables(cudaStream_t s, uint32_t* tw_fwd, uint32_t* tw_inv)
+{
+    ntt2_tables_kernel<<<1, 256, 0, s>>>(tw_fwd);
+    ntt2_tables_kernel<<<1, 256, 0, s>>>(tw_inv);
+    return cudaGetLastError();
+}
+template <int LOG_R>
+__device__ __forceinline__ void n2_load_twiddles(uint32_t* tw_s, const uint32_t* __restrict__ tab)
+{
+    using C = Ntt2Cfg<LOG_R>;
+    const uint4* src = reinterpret_cast<const uint4*>(tab);
+    uint4* dst = reinterpret_cast<uint4*>(tw_s);
+    for (int e = threadIdx.x; e < C::TW_WORDS / 4; e += C::THREADS) dst[e] = src[e];
 }
 
 // the butterflies of one round on the 16 points of a thread (TRIPS mini-transforms of radix 2^LR); x[trip * RAD + d]
@@ -521,9 +558,23 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_strided_kernel(c
         const uint32_t* p = src + base + ((size_t)row0 << a.log_S);
         const size_t step = (size_t)1 << (a.log_S + r0.LS);
 #pragma unroll
-        for (int u = 0; u < N2_E; u++) x[u] = p[u * step];
+        for (int u = 0; u < N2_E; u++, p += step) x[u] = *p;
     }
-    n2_build_twiddles<LOG_R>(tw_s, a.tw);
+    n2_load_twiddles<LOG_R>(tw_s, a.tw2);
+    // per-COLUMN constants of the output twiddle chain, computed once per column (by row slot 0) and shared: the step
+    // w^(b 2^(LOG_R-4)) and its powers, and the column's share sigma^b of the coset factor (times the final scale)
+    uint32_t* colc = rf + (COSET ? C::RF_WORDS : 0);            // [8][8]
+    if (rslot == 0) {
+        const uint32_t N1 = (1u << a.hpow.log_N) - 1u, sh = a.hpow.log_N - a.log_Msub;
+        uint32_t e1 = ((b << (LOG_R - 4)) << sh) & N1;
+        if (a.inverse) e1 = ((N1 + 1u) - e1) & N1;
+        const uint32_t w1 = pw(a.hpow, e1), w2 = mont_mul(w1, w1);
+        uint32_t f = R1;                                         // Montgomery form of 1
+        if (COSET) f = sigma_pow_m(a, rr, b);
+        if (a.use_scale) f = mont_mul(f, a.scale_m);
+        uint32_t* cc = colc + col * 8;
+        cc[0] = w1; cc[1] = w2; cc[2] = mont_mul(w2, w1); cc[3] = mont_mul(w2, w2); cc[4] = f;
+    }
     if (COSET) {   // first pass of the LDE (one block: blk == 0, k = a S + b): sigma^(a S) in the order round 0 reads it
         for (uint32_t e = threadIdx.x; e < (uint32_t)C::NSLOT * N2_E; e += C::THREADS) {
             const uint32_t s = e >> 4, u = e & 15;
@@ -549,21 +600,20 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_strided_kernel(c
         static_assert(n2_rows<LOG_R, NR - 1>(1u, 0u) == 16u && rl.LS == 0, "last round: 16 consecutive rows per thread");
         const uint32_t c0 = brev_c<LOG_R>(rslot << 4);           // < 2^(LOG_R - 4)
         const uint32_t N1 = (1u << a.hpow.log_N) - 1u, sh = a.hpow.log_N - a.log_Msub;
-        uint32_t e1 = (b << (LOG_R - 4)) << sh, e0 = (b * c0) << sh;   // step: w^(b 2^(LOG_R-4)); start: w^(b c0)
-        if (a.inverse) { e1 = ((N1 + 1u) - (e1 & N1)) & N1; e0 = ((N1 + 1u) - (e0 & N1)) & N1; }
-        const uint32_t w1 = pw(a.hpow, e1 & N1), w2 = mont_mul(w1, w1), w3 = mont_mul(w2, w1), w4 = mont_mul(w2, w2);
+        uint32_t e0 = ((b * c0) << sh) & N1;                     // start: w^(b c0)
+        if (a.inverse) e0 = ((N1 + 1u) - e0) & N1;
+        const uint32_t* cc = colc + col * 8;
+        const uint32_t w1 = cc[0], w2 = cc[1], w3 = cc[2], w4 = cc[3];
         uint32_t t[4];
-        t[0] = pw(a.hpow, e0 & N1);
-        if (COSET) t[0] = mont_mul(t[0], sigma_pow_m(a, rr, b));
-        if (a.use_scale) t[0] = mont_mul(t[0], a.scale_m);
+        t[0] = mont_mul(pw(a.hpow, e0), cc[4]);
         t[1] = mont_mul(t[0], w1); t[2] = mont_mul(t[0], w2); t[3] = mont_mul(t[0], w3);
         uint32_t* q = dst + ((size_t)blk << a.log_Msub) + ((size_t)c0 << a.log_S) + b;
         const size_t step = (size_t)1 << (a.log_S + LOG_R - 4);
         // outputs in the order m = brev4(u) = 0 .. 15 so that the four multiplicative chains advance in step
 #pragma unroll
-        for (int mm = 0; mm < N2_E; mm++) {
+        for (int mm = 0; mm < N2_E; mm++, q += step) {
             const int u = (int)brevc((uint32_t)mm, 4);
-            q[mm * step] = mont_mul(x[u], t[mm & 3]);
+            *q = mont_mul(x[u], t[mm & 3]);
             if (mm + 4 < N2_E) t[mm & 3] = mont_mul(t[mm & 3], w4);
         }
     }
@@ -602,7 +652,7 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(con
         // SINGLE LDE: the 8 cosets are transforms of the SAME coefficient array, scaled below by sigma_r^k (prover.rs:69-70)
         const uint32_t* p = srcb + ((SINGLE && a.use_coset) ? 0 : rr * M) + (qrow << LOG_R) + row0;
 #pragma unroll
-        for (int u = 0; u < N2_E; u++) x[u] = p[u << r0.LS];
+        for (int u = 0; u < N2_E; u++) x[u] = p[u << r0.LS];      // immediates
         if (SINGLE && a.use_coset) {
             uint32_t t = sigma_pow_m(a, rr + a.coset_base, row0);
             const uint32_t step = sigma_pow_m(a, rr + a.coset_base, 1u << r0.LS);
@@ -616,7 +666,7 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(con
 #pragma unroll
         for (int u = 0; u < N2_E; u++) x[u] = 0u;
     }
-    n2_build_twiddles<LOG_R>(tw_s, a.tw);
+    n2_load_twiddles<LOG_R>(tw_s, a.tw2);
     __syncthreads();
     n2_butterflies<LOG_R, 0>(x, tw_s, row0);
     n2_rounds_after_first<LOG_R>(tile, tw_s, x, rslot, col);
@@ -624,15 +674,26 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(con
         const uint32_t log_rows = a.log_M - LOG_R;
         const size_t rho = (size_t)c1_0 + ((size_t)c2 << a.log_R1);      // first of the tile's row indices
         const uint32_t c0 = brev_c<LOG_R>(rslot << 4);
+        // outputs c = c0 + (m << (LOG_R - 4)), m = brev4(u) = 0 .. 15: a constant stride in the natural-order result
+        const size_t o0 = ((rho + ((size_t)c0 << log_rows)) << LOG_CS) + col;
+        const size_t step = (size_t)1 << (LOG_R - 4 + log_rows + LOG_CS);
+        if (live) {
+            if (LOG_CS == 0 && a.pack.log_jb != 0) {
 #pragma unroll
-        for (int u = 0; u < N2_E; u++) {
-            const uint32_t c = c0 + (brevc((uint32_t)u, 4) << (LOG_R - 4));
-            uint32_t v = x[u];
-            if (a.use_scale) v = mont_mul(v, a.scale_m);
-            const size_t o = ((rho + ((size_t)c << log_rows)) << LOG_CS) + col;
-            if (!live) continue;
-            if (LOG_CS == 0 && a.pack.log_jb != 0) dstb[pack_index(a.pack, (uint32_t)o)] = v;
-            else dstb[o] = v;
+                for (int mm = 0; mm < N2_E; mm++) {
+                    uint32_t v = x[brevc((uint32_t)mm, 4)];
+                    if (a.use_scale) v = mont_mul(v, a.scale_m);
+                    dstb[pack_index(a.pack, (uint32_t)(o0 + mm * step))] = v;
+                }
+            } else {
+                uint32_t* q = dstb + o0;
+#pragma unroll
+                for (int mm = 0; mm < N2_E; mm++, q += step) {
+                    uint32_t v = x[brevc((uint32_t)mm, 4)];
+                    if (a.use_scale) v = mont_mul(v, a.scale_m);
+                    *q = v;
+                }
+            }
         }
     }
 }
@@ -779,7 +840,7 @@ template <int LOG_R>
 static cudaError_t launch_strided2(bool coset, dim3 grid, cudaStream_t s, const NttPassArgs& a)
 {
     using C = Ntt2Cfg<LOG_R>;
-    const size_t smem = ((size_t)C::TILE_WORDS + C::TW_WORDS + (coset ? C::RF_WORDS : 0)) * 4;
+    const size_t smem = ((size_t)C::TILE_WORDS + C::TW_WORDS + (coset ? C::RF_WORDS : 0) + 64) * 4;
     if (coset) return launch_k(ntt2_strided_kernel<LOG_R, true>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
     return launch_k(ntt2_strided_kernel<LOG_R, false>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
 }
@@ -803,12 +864,12 @@ static int ntt_version()
     static const int v = [] { const char* e = getenv("ZK_NTT_V"); return e ? atoi(e) : 2; }();
     return v;
 }
-// smallest transform that takes the narrow-tile kernels: measured on B200 they win from 2^17 (2^18: 27 vs 30 us, 2^20: 80 vs
-// 83 us, 2^24: 1.31 vs 1.39 ms per LDE; batched 2^20: 103 vs 97 G points/s) and lose below (2^16: 20.5 vs 19.0 us), where a
-// transform is a handful of CTAs and their longer prologue shows.  ZK_NTT2_MIN_MU overrides (>= 12).
+// smallest transform that takes the narrow-tile kernels.  Measured on B200 (LDE, us, narrow vs wide tiles): 2^12 9.5 / 10.6,
+// 2^14 10.5 / 12.7, 2^16 12.8 / 24.0, 2^18 24.8 / 30.0, 2^20 70.1 / 83.4, 2^22 267 / 316, 2^24 1180 / 1386: they win from the
+// first size they can run (two passes of radix >= 2^6).  ZK_NTT2_MIN_MU overrides (>= 12).
 static int ntt2_min_mu()
 {
-    static const int v = [] { const char* e = getenv("ZK_NTT2_MIN_MU"); int m = e ? atoi(e) : 17; return m < 12 ? 12 : m; }();
+    static const int v = [] { const char* e = getenv("ZK_NTT2_MIN_MU"); int m = e ? atoi(e) : 12; return m < 12 ? 12 : m; }();
     return v;
 }
 // narrow-tile plan: ceil(mu / 10) passes of radix 2^6 .. 2^10, as even as possible, larger first
@@ -868,6 +929,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
         a.log_M = mu; a.inverse = inverse; a.hpow = T.hpow; a.wpow = T.wpow; a.coset_base = coset_base;
         if (pack) a.pack = *pack;
         a.tw = (inverse ? T.tw_inv : T.tw_fwd) + tw_off(mu);
+        a.tw2 = (inverse ? T.tw_inv : T.tw_fwd) + ntt2_tab_off((int)mu);
         a.src = coeffs; a.src_stride = coeffs_stride; a.dst = dst; a.dst_stride = dst_stride;
         a.use_scale = use_scale; a.scale_m = scale_m; a.use_coset = coset_scale;
         a.log_Msub = mu;
@@ -899,6 +961,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
         log_S -= log_R;
         a.log_S = log_S;
         a.tw = twb + tw_off(log_R);
+        a.tw2 = twb + ntt2_tab_off((int)log_R);
         const bool cs = (i == 0 && coset_scale);
         a.src = (i == 0) ? coeffs : work;
         a.src_stride = (i == 0) ? coeffs_stride : work_stride;
@@ -939,6 +1002,7 @@ static cudaError_t run_ntt(cudaStream_t s, const NttTables& T, uint32_t mu, uint
     a.log_Msub = log_R;
     a.log_S = 0;
     a.tw = twb + tw_off(log_R);
+    a.tw2 = twb + ntt2_tab_off((int)log_R);
     const bool cs = (p.n_pass == 1 && coset_scale);
     a.src = (p.n_pass == 1) ? coeffs : work;
     a.src_stride = (p.n_pass == 1) ? coeffs_stride : work_stride;
