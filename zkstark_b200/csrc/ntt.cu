@@ -575,10 +575,19 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_strided_kernel(c
         uint32_t* cc = colc + col * 8;
         cc[0] = w1; cc[1] = w2; cc[2] = mont_mul(w2, w1); cc[3] = mont_mul(w2, w2); cc[4] = f;
     }
-    if (COSET) {   // first pass of the LDE (one block: blk == 0, k = a S + b): sigma^(a S) in the order round 0 reads it
+    if (COSET) {
+        // first pass of the LDE (one block: blk == 0, k = a S + b): sigma^(a S) in the order round 0 reads it.  A row is
+        // (slot bits) | (digit << LS0) with disjoint bits, so the factor is a product of a per-slot and a per-digit power:
+        // NSLOT + 16 table look-ups per CTA, then one multiplication per entry.
+        uint32_t* fa = colc + 64;                                 // [NSLOT] sigma^(rows(s) S)   [16] sigma^((u << LS0) S)
+        for (uint32_t e = threadIdx.x; e < (uint32_t)C::NSLOT + 16; e += C::THREADS) {
+            const uint32_t row = e < (uint32_t)C::NSLOT ? n2_rows<LOG_R, 0>(e, 0u) : ((e - C::NSLOT) << r0.LS);
+            fa[e] = sigma_pow_m(a, rr, row << a.log_S);
+        }
+        __syncthreads();
         for (uint32_t e = threadIdx.x; e < (uint32_t)C::NSLOT * N2_E; e += C::THREADS) {
             const uint32_t s = e >> 4, u = e & 15;
-            rf[s * N2_PITCH + u] = sigma_pow_m(a, rr, (n2_rows<LOG_R, 0>(s, 0u) | (u << r0.LS)) << a.log_S);
+            rf[s * N2_PITCH + u] = mont_mul(fa[s], fa[C::NSLOT + u]);
         }
     }
     __syncthreads();
@@ -840,7 +849,7 @@ template <int LOG_R>
 static cudaError_t launch_strided2(bool coset, dim3 grid, cudaStream_t s, const NttPassArgs& a)
 {
     using C = Ntt2Cfg<LOG_R>;
-    const size_t smem = ((size_t)C::TILE_WORDS + C::TW_WORDS + (coset ? C::RF_WORDS : 0) + 64) * 4;
+    const size_t smem = ((size_t)C::TILE_WORDS + C::TW_WORDS + (coset ? C::RF_WORDS + C::NSLOT + 16 : 0) + 64) * 4;
     if (coset) return launch_k(ntt2_strided_kernel<LOG_R, true>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
     return launch_k(ntt2_strided_kernel<LOG_R, false>, grid, Ntt2Cfg<LOG_R>::THREADS, smem, s, a);
 }
