@@ -60,6 +60,22 @@ def test_native_full_size_matches_single_gpu_and_golden(ctx, G):
     assert ph["total"] > 0
 
 
+@pytest.mark.parametrize("log_n,G,lb", [(9, 4, 5), (12, 2, 10), (13, 8, 7)])
+def test_native_all_to_all_path_matches_peer_path(ctx, orc, log_n, G, lb, monkeypatch):
+    """ZK_SHARD_NO_P2P=1: the coset transforms fill a local send buffer and an all-to-all re-owns the evaluations, instead
+    of storing straight into the owners' receive buffers (the default, fused path).  Same transcript either way."""
+    trace = zk.trace_fibsq(log_n, 99)
+    otr, ost, _ = orc.prove_fibsq(log_n, 99)
+    for no_p2p in ("1", "0"):
+        monkeypatch.setenv("ZK_SHARD_NO_P2P", no_p2p)
+        comm = zk.ShardComm.local(ctx, G)
+        try:
+            comm.set(log_block=lb, log_tail_len=0)
+            assert comm.prove(log_n, trace) == (otr, ost)
+        finally:
+            comm.close()
+
+
 def test_native_rejects_bad_arguments(ctx):
     with pytest.raises(zk.ZkError):
         zk.ShardComm.local(ctx, 3)

@@ -172,6 +172,13 @@ struct zk_shard_comm {
     float phase_ms[16] = {};
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // fused LDE + exchange: every rank's receive buffer mapped into this process (cudaIpc), so the last pass of the coset
+    // transforms stores each evaluation straight into its owner's memory over NVLink and no all-to-all follows
+    bool p2p_wanted = true;                  // ZK_SHARD_NO_P2P=1: always the NCCL all-to-all
+    bool p2p = false;                        // the peers' buffers are mapped (all ranks agree)
+    void* p2p_for = nullptr;                 // the local receive buffer the mapping was made for
+    uint32_t* peer_recv[8] = {};
+    DevBuf flag;                             // 64-byte-per-rank staging of the handle exchange; word 0 doubles as the barrier word
 };
 
 namespace {
@@ -296,6 +303,60 @@ size_t upper_off(const Geometry& g, uint32_t t)
     return off;
 }
 
+void close_peers(zk_shard_comm* cm)
+{
+    for (uint32_t p = 0; p < cm->G; p++) {
+        if (cm->peer_recv[p] && !cm->local && p != cm->rk[0].rank) cudaIpcCloseMemHandle(cm->peer_recv[p]);
+        cm->peer_recv[p] = nullptr;
+    }
+    cm->p2p = false;
+    cm->p2p_for = nullptr;
+}
+
+// (Re)maps the peers' receive buffers after they were (re)allocated.  Collective: every rank calls it at the same point
+// (buffer sizes depend on the geometry only).  Any rank that cannot map a peer makes ALL ranks fall back to the all-to-all.
+int setup_peers(zk_shard_comm* cm)
+{
+    zk_ctx* ctx = cm->ctx;
+    if (cm->G == 1 || !cm->p2p_wanted) { cm->p2p = false; return ZK_OK; }
+    if (cm->local) {   // virtual ranks: the "peers" are buffers of the same device
+        cm->p2p = true;
+        return ZK_OK;
+    }
+    RankBufs& b = cm->rk[0];
+    if (cm->p2p_for == b.recv.p) return ZK_OK;           // still valid
+    close_peers(cm);
+    cudaStream_t s = ctx->stream;
+    const uint32_t me = b.rank, G = cm->G;
+    CK(cm->flag.ensure(64 * 8 + 64));
+    cudaIpcMemHandle_t h;
+    unsigned char fail_flag = 0;
+    if (cudaIpcGetMemHandle(&h, b.recv.p) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; memset(&h, 0, sizeof h); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    uint8_t* st = (uint8_t*)cm->flag.p;
+    CK(cudaMemcpyAsync(st + 64 * me, &h, 64, cudaMemcpyHostToDevice, s));
+    NK(nccl_api()->AllGather(st + 64 * me, st, 64, ncclUint8, cm->nccl, s));
+    cudaIpcMemHandle_t all[8];
+    CK(cudaMemcpyAsync(all, st, 64 * G, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (uint32_t p = 0; p < G && !fail_flag; p++) {
+        if (p == me) { cm->peer_recv[p] = (uint32_t*)b.recv.p; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; break; }
+        cm->peer_recv[p] = (uint32_t*)ptr;
+    }
+    // agree: one failure anywhere means nobody uses the mapping
+    CK(cudaMemcpyAsync(st + 512, &fail_flag, 1, cudaMemcpyHostToDevice, s));
+    NK(nccl_api()->AllReduce(st + 512, st + 512, 1, ncclUint8, ncclMax, cm->nccl, s));
+    unsigned char any = 0;
+    CK(cudaMemcpyAsync(&any, st + 512, 1, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (any) { close_peers(cm); return ZK_OK; }
+    cm->p2p = true;
+    cm->p2p_for = b.recv.p;
+    return ZK_OK;
+}
+
 int ensure_bufs(zk_shard_comm* cm, const Geometry& g, size_t tail_first_len)
 {
     zk_ctx* ctx = cm->ctx;
@@ -327,7 +388,7 @@ int ensure_bufs(zk_shard_comm* cm, const Geometry& g, size_t tail_first_len)
         CK(cudaMallocHost(&cm->pinned, pin));
         cm->pinned_bytes = pin;
     }
-    return ZK_OK;
+    return setup_peers(cm);
 }
 
 // Distributed Merkle tree of one layer: the rank-local block subtrees are already in `heap` (levels down to the block
@@ -415,17 +476,31 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
         pk.log_nbl = ilog2_u64(g.nbl);
         pk.n_slots = g.C;
         for (RankBufs& b : cm->rk) {
+            uint32_t* out = (uint32_t*)b.send.p;
+            if (cm->p2p) {   // fused exchange: straight into the owners' receive buffers
+                pk.src_rank = b.rank;
+                for (uint32_t d = 0; d < g.G; d++) pk.peer[d] = cm->local ? (uint32_t*)cm->rk[d].recv.p : cm->peer_recv[d];
+                out = (uint32_t*)b.recv.p;
+            }
             for (uint32_t c = 0; c < g.C; c++) {
                 pk.slot = c;
                 int nl = 0;
                 CK(launch_lde_one_coset(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, b.rank + c * g.G,
-                                        (const uint32_t*)b.coeffs.p, (uint32_t*)b.work.p, (uint32_t*)b.send.p, &nl, &pk));
+                                        (const uint32_t*)b.coeffs.p, (uint32_t*)b.work.p, out, &nl, &pk));
                 ctx->launches += nl;
             }
         }
     }
     mark(cm, PH_LDE);
-    {
+    if (cm->p2p) {
+        // every rank's stores must have landed before anybody unpacks: a one-word all-reduce is the barrier (a kernel's
+        // writes to peer memory are complete when the kernel is, and the collective cannot finish anywhere before every
+        // rank has entered it, i.e. finished its transforms)
+        if (!cm->local) {
+            NK(nccl_api()->AllReduce(cm->flag.p, cm->flag.p, 1, ncclUint32, ncclMax, cm->nccl, s));
+        }
+        cm->comm_bytes += 4 * (g.Nloc / g.G) * (g.G - 1);
+    } else {
         std::vector<const uint8_t*> send;
         std::vector<uint8_t*> recv;
         for (RankBufs& b : cm->rk) { send.push_back((const uint8_t*)b.send.p); recv.push_back((uint8_t*)b.recv.p); }
@@ -582,6 +657,7 @@ static int comm_common(zk_ctx* ctx, zk_shard_comm* cm)
     for (int i = 0; i < PH_COUNT; i++) CK(cudaEventCreate(&cm->ev[i]));
     if (const char* e = getenv("ZK_SHARD_LOG_BLOCK")) cm->log_block = (uint32_t)atoi(e);
     if (const char* e = getenv("ZK_SHARD_TAIL_LOG")) cm->tail_len = (uint64_t)1 << atoi(e);
+    if (const char* e = getenv("ZK_SHARD_NO_P2P")) cm->p2p_wanted = !(e[0] == '1');
     return ZK_OK;
 }
 
@@ -635,6 +711,8 @@ void zk_shard_comm_destroy(zk_shard_comm* cm)
     if (!cm) return;
     cudaSetDevice(cm->ctx->device);
     cudaStreamSynchronize(cm->ctx->stream);
+    close_peers(cm);
+    cm->flag.release();
     if (cm->nccl && nccl_api()) nccl_api()->CommDestroy(cm->nccl);
     for (RankBufs& b : cm->rk) {
         DevBuf* bufs[] = {&b.state, &b.transcript, &b.y, &b.coeffs, &b.work, &b.send, &b.recv, &b.f_local, &b.layers, &b.heap_f,

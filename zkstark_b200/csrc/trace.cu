@@ -1,7 +1,8 @@
 // prover.rs:32-39 for a BATCH of proofs: a[0] = 1, a[1] = secret, a[i] = a[i-2]^2 + a[i-1]^2.
-// The recurrence is sequential per proof, so one thread runs one proof; a warp stages 32 x 32 values in shared
-// memory and writes them transposed, so global stores are full 128-byte rows.  ~45 cycles per step: worth it for
-// batches (1024 proofs of 2^16 in ~1.5 ms instead of 0.6 s of host time), not for one long trace.
+// The recurrence is one dependent squaring per step, so one thread runs one proof and a warp runs 32 of them; the warp
+// stages 32 x 32 values in shared memory and writes them transposed, so global stores are full 128-byte rows.
+// The loop carries (s, y) = (a[i-2]^2, a[i-1]) in Montgomery form: per step one squaring and one addition on the critical
+// path (~35 cycles of dependent latency); the conversion of a[i] out of Montgomery form is off the path.
 #include "common.cuh"
 
 namespace zk {
@@ -13,23 +14,26 @@ __global__ void __launch_bounds__(32) trace_batch_kernel(const uint32_t* secrets
     const uint32_t lane = threadIdx.x, b0 = blockIdx.x * 32, b = b0 + lane;
     const uint32_t n1 = (1u << log_n) - 1;  // values per trace
     const uint32_t secret = b < batch ? secrets[b] % P : 0u;
-    uint32_t x_m = to_mont(1u), y_m = to_mont(secret);  // a[i-2], a[i-1] in Montgomery form
+    // state before step i: s_m = a[i-2]^2, y_m = a[i-1] (Montgomery form); the first block starts at i = 2
+    uint32_t y_m = to_mont(secret);
+    uint32_t s_m = to_mont(1u);             // a[0]^2 = 1
     for (uint32_t i0 = 0; i0 < n1; i0 += 32) {
-#pragma unroll 4
+#pragma unroll
         for (uint32_t t = 0; t < 32; t++) {
-            const uint32_t i = i0 + t;
             uint32_t v;
-            if (i == 0) v = 1u;
-            else if (i == 1) v = secret;
+            if (i0 == 0 && t == 0) v = 1u;
+            else if (i0 == 0 && t == 1) v = secret;
             else {
-                const uint32_t z_m = fadd(mont_mul(x_m, x_m), mont_mul(y_m, y_m));
-                x_m = y_m;
-                y_m = z_m;
-                v = from_mont(z_m);
+                const uint32_t yy = mont_mul(y_m, y_m);     // a[i-1]^2
+                const uint32_t z = fadd(s_m, yy);           // a[i]
+                s_m = yy;
+                y_m = z;
+                v = from_mont(z);
             }
             tile[lane][t] = v;
         }
         __syncwarp();
+#pragma unroll 8
         for (uint32_t r = 0; r < 32; r++) {
             const uint32_t i = i0 + lane;
             if (b0 + r < batch && i < n1) traces[(size_t)(b0 + r) * stride + i] = tile[r][lane];
