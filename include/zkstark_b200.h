@@ -242,8 +242,9 @@ int zk_shard_decommit_dev(zk_ctx *ctx, uint32_t log_n, uint32_t n_ranks, uint32_
  *   every rank: zk_shard_comm_init(ctx, id, n_ranks, rank, &comm)            -- ncclCommInitRank; collective
  *   every rank: zk_prove_fibsq_sharded(comm, log_n, trace, ...)              -- collective; every rank gets the proof
  * NCCL is bound at run time (libnccl.so.2; ZK_NCCL_LIB overrides the path): single-GPU users do not need it.
- * The ranks must share a node: the coset transforms store their results straight into the owners' memory over NVLink
- * (cudaIpc peer mappings; ZK_SHARD_NO_P2P=1 or a failed mapping falls back to an NCCL all-to-all on all ranks).
+ * Ranks that share a node exchange the LDE through peer memory: every rank reads the evaluations it owns straight out of
+ * the other ranks' buffers over NVLink (cudaIpc peer mappings; ZK_SHARD_NO_P2P=1 or a failed mapping falls back to an NCCL
+ * all-to-all on all ranks).
  * zk_shard_comm_init_local runs G VIRTUAL ranks on the context's own device (collectives become device copies): the
  * same driver and kernels on one GPU, used by the single-GPU test tier.  n_ranks: 1, 2, 4 or 8 (the LDE has 8 cosets).
  * A comm borrows its ctx: destroy the comm first.  Generalises generate_proof (prover.rs:9) like zk_prove_fibsq. */

@@ -116,11 +116,6 @@ struct NttPack {
     uint32_t log_nbl;    // log2 of the blocks per rank
     uint32_t slot;       // which of this rank's n_slots coset transforms this is
     uint32_t n_slots;    // 8 / G
-    // Peer mode (fused transform + exchange): peer[d] != null is rank d's RECEIVE buffer, mapped into this process
-    // (cudaIpc over NVLink / NVSwitch, or simply the same device for virtual ranks); the last pass then stores every
-    // evaluation straight into its owner's memory, at [src_rank][slot][bl][tt], and no all-to-all follows.
-    uint32_t src_rank;
-    uint32_t* peer[8];
 };
 __host__ __device__ inline size_t pack_index(const NttPack& p, uint32_t j)
 {
@@ -128,15 +123,6 @@ __host__ __device__ inline size_t pack_index(const NttPack& p, uint32_t j)
     const uint32_t d = b & ((1u << p.log_G) - 1u), bl = b >> p.log_G;
     return ((((size_t)d * p.n_slots + p.slot) << p.log_nbl) + bl) << p.log_jb | tt;
 }
-// where point j of the transform goes: the local send buffer `dst` (exchange by all-to-all) or its owner's memory
-__device__ __forceinline__ uint32_t* pack_target(const NttPack& p, uint32_t* dst, uint32_t j)
-{
-    if (p.peer[0] == nullptr) return dst + pack_index(p, j);
-    const uint32_t tt = j & ((1u << p.log_jb) - 1u), b = j >> p.log_jb;
-    const uint32_t d = b & ((1u << p.log_G) - 1u), bl = b >> p.log_G;
-    return p.peer[d] + ((((((size_t)p.src_rank * p.n_slots + p.slot) << p.log_nbl) + bl) << p.log_jb) | tt);
-}
-
 // Fused leaf sources.  `vals` is where leaf values live (or are produced into).
 struct FoldArgs {           // polynomial.rs:385-400 + prover.rs:204-211 in evaluation form
     const uint32_t* cur;    // layer k, len = 2*half (batch stride cur_stride)

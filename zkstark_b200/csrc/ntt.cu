@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NttCfg<LOG_R>::THREADS) ntt_final_kernel(const
             const uint32_t c = warp + i * C::NW;
             uint32_t x = sm[brev_c<LOG_R>(c) * TP + lane];
             if (a.use_scale) x = mont_mul(x, a.scale_m);
-            if (packed) *pack_target(a.pack, dstb, (uint32_t)(rho + ((size_t)c << log_rows))) = x;   // 32 lanes: 32 consecutive j, one block
+            if (packed) dstb[pack_index(a.pack, (uint32_t)(rho + ((size_t)c << log_rows)))] = x;   // 32 lanes: 32 consecutive j, one block
             else q[((size_t)c << log_rows) << LOG_CS] = x;
         }
     }
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(Ntt2Cfg<LOG_R>::THREADS) ntt2_final_kernel(con
                 for (int mm = 0; mm < N2_E; mm++) {
                     uint32_t v = x[brevc((uint32_t)mm, 4)];
                     if (a.use_scale) v = mont_mul(v, a.scale_m);
-                    *pack_target(a.pack, dstb, (uint32_t)(o0 + mm * step)) = v;
+                    dstb[pack_index(a.pack, (uint32_t)(o0 + mm * step))] = v;
                 }
             } else {
                 uint32_t* q = dstb + o0;

@@ -88,20 +88,23 @@ NcclApi* nccl_api()
 }
 
 // ---------------------------------------------------------------- small data-movement kernels
-// all-to-all result [g][c][bl][tt] (from source rank g, its c-th coset transform) -> rank-local evaluations in
-// blocked-cyclic order: local[(bl jb + tt) 8 + (c G + g)].  One thread per point (bl, tt): 8 coalesced reads, 32 B out.
-__global__ void __launch_bounds__(256) shard_unpack_kernel(const uint32_t* __restrict__ recv, uint32_t* __restrict__ local,
+// The evaluations this rank owns, gathered from the G ranks that computed them: src.p[g] points at the [c][bl][tt] chunk
+// source rank g produced for this rank (its c-th coset transform) -- in g's SEND buffer, read over NVLink through a peer
+// mapping (fused exchange + unpack), or in the local receive buffer after an all-to-all -- and becomes the rank-local
+// array in blocked-cyclic order: local[(bl jb + tt) 8 + (c G + g)].  One thread per point (bl, tt): 8 coalesced reads (a
+// warp reads 128 contiguous bytes of each stream), 32 bytes out.
+struct UnpackSrc { const uint32_t* p[8]; };
+__global__ void __launch_bounds__(256) shard_unpack_kernel(UnpackSrc src, uint32_t* __restrict__ local,
                                                            uint32_t log_per_stream /* log2(nbl jb) */, uint32_t G)
 {
     pdl_enter();
     const uint32_t q = blockIdx.x * 256 + threadIdx.x;
     if (q >> log_per_stream) return;
-    const uint32_t C = 8 / G;
     uint32_t v[8];
 #pragma unroll
     for (uint32_t s = 0; s < 8; s++) {
         const uint32_t c = s / G, g = s % G;
-        v[s] = recv[((size_t)(g * C + c) << log_per_stream) + q];
+        v[s] = src.p[g][((size_t)c << log_per_stream) + q];
     }
     uint4* o = reinterpret_cast<uint4*>(local + (size_t)q * 8);
     o[0] = make_uint4(v[0], v[1], v[2], v[3]);
@@ -172,12 +175,12 @@ struct zk_shard_comm {
     float phase_ms[16] = {};
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
-    // fused LDE + exchange: every rank's receive buffer mapped into this process (cudaIpc), so the last pass of the coset
-    // transforms stores each evaluation straight into its owner's memory over NVLink and no all-to-all follows
+    // fused exchange + unpack: every rank's SEND buffer is mapped into this process (cudaIpc), so the unpack kernel reads the
+    // evaluations it owns straight from the ranks that computed them over NVLink and no all-to-all follows
     bool p2p_wanted = true;                  // ZK_SHARD_NO_P2P=1: always the NCCL all-to-all
     bool p2p = false;                        // the peers' buffers are mapped (all ranks agree)
-    void* p2p_for = nullptr;                 // the local receive buffer the mapping was made for
-    uint32_t* peer_recv[8] = {};
+    void* p2p_for = nullptr;                 // the local send buffer the mapping was made for
+    uint32_t* peer_send[8] = {};
     DevBuf flag;                             // 64-byte-per-rank staging of the handle exchange; word 0 doubles as the barrier word
 };
 
@@ -306,14 +309,14 @@ size_t upper_off(const Geometry& g, uint32_t t)
 void close_peers(zk_shard_comm* cm)
 {
     for (uint32_t p = 0; p < cm->G; p++) {
-        if (cm->peer_recv[p] && !cm->local && p != cm->rk[0].rank) cudaIpcCloseMemHandle(cm->peer_recv[p]);
-        cm->peer_recv[p] = nullptr;
+        if (cm->peer_send[p] && !cm->local && p != cm->rk[0].rank) cudaIpcCloseMemHandle(cm->peer_send[p]);
+        cm->peer_send[p] = nullptr;
     }
     cm->p2p = false;
     cm->p2p_for = nullptr;
 }
 
-// (Re)maps the peers' receive buffers after they were (re)allocated.  Collective: every rank calls it at the same point
+// (Re)maps the peers' send buffers after they were (re)allocated.  Collective: every rank calls it at the same point
 // (buffer sizes depend on the geometry only).  Any rank that cannot map a peer makes ALL ranks fall back to the all-to-all.
 int setup_peers(zk_shard_comm* cm)
 {
@@ -324,14 +327,14 @@ int setup_peers(zk_shard_comm* cm)
         return ZK_OK;
     }
     RankBufs& b = cm->rk[0];
-    if (cm->p2p_for == b.recv.p) return ZK_OK;           // still valid
+    if (cm->p2p_for == b.send.p) return ZK_OK;           // still valid
     close_peers(cm);
     cudaStream_t s = ctx->stream;
     const uint32_t me = b.rank, G = cm->G;
     CK(cm->flag.ensure(64 * 8 + 64));
     cudaIpcMemHandle_t h;
     unsigned char fail_flag = 0;
-    if (cudaIpcGetMemHandle(&h, b.recv.p) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; memset(&h, 0, sizeof h); }
+    if (cudaIpcGetMemHandle(&h, b.send.p) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; memset(&h, 0, sizeof h); }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
     uint8_t* st = (uint8_t*)cm->flag.p;
     CK(cudaMemcpyAsync(st + 64 * me, &h, 64, cudaMemcpyHostToDevice, s));
@@ -340,10 +343,10 @@ int setup_peers(zk_shard_comm* cm)
     CK(cudaMemcpyAsync(all, st, 64 * G, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (uint32_t p = 0; p < G && !fail_flag; p++) {
-        if (p == me) { cm->peer_recv[p] = (uint32_t*)b.recv.p; continue; }
+        if (p == me) { cm->peer_send[p] = (uint32_t*)b.send.p; continue; }
         void* ptr = nullptr;
         if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; break; }
-        cm->peer_recv[p] = (uint32_t*)ptr;
+        cm->peer_send[p] = (uint32_t*)ptr;
     }
     // agree: one failure anywhere means nobody uses the mapping
     CK(cudaMemcpyAsync(st + 512, &fail_flag, 1, cudaMemcpyHostToDevice, s));
@@ -353,7 +356,7 @@ int setup_peers(zk_shard_comm* cm)
     CK(cudaStreamSynchronize(s));
     if (any) { close_peers(cm); return ZK_OK; }
     cm->p2p = true;
-    cm->p2p_for = b.recv.p;
+    cm->p2p_for = b.send.p;
     return ZK_OK;
 }
 
@@ -476,42 +479,45 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
         pk.log_nbl = ilog2_u64(g.nbl);
         pk.n_slots = g.C;
         for (RankBufs& b : cm->rk) {
-            uint32_t* out = (uint32_t*)b.send.p;
-            if (cm->p2p) {   // fused exchange: straight into the owners' receive buffers
-                pk.src_rank = b.rank;
-                for (uint32_t d = 0; d < g.G; d++) pk.peer[d] = cm->local ? (uint32_t*)cm->rk[d].recv.p : cm->peer_recv[d];
-                out = (uint32_t*)b.recv.p;
-            }
             for (uint32_t c = 0; c < g.C; c++) {
                 pk.slot = c;
                 int nl = 0;
                 CK(launch_lde_one_coset(s, ctx->tw_fwd, ctx->tw_inv, T->h.tab, T->w.tab, log_n, b.rank + c * g.G,
-                                        (const uint32_t*)b.coeffs.p, (uint32_t*)b.work.p, out, &nl, &pk));
+                                        (const uint32_t*)b.coeffs.p, (uint32_t*)b.work.p, (uint32_t*)b.send.p, &nl, &pk));
                 ctx->launches += nl;
             }
         }
     }
     mark(cm, PH_LDE);
+    const size_t per_dest = g.Nloc / g.G;                     // words every rank produced for every other rank
     if (cm->p2p) {
-        // every rank's stores must have landed before anybody unpacks: a one-word all-reduce is the barrier (a kernel's
-        // writes to peer memory are complete when the kernel is, and the collective cannot finish anywhere before every
-        // rank has entered it, i.e. finished its transforms)
+        // every rank's transforms must be complete before anybody reads them: a one-word all-reduce is the barrier (it cannot
+        // finish anywhere before every rank has entered it, i.e. finished the kernels in front of it on its stream)
         if (!cm->local) {
             NK(nccl_api()->AllReduce(cm->flag.p, cm->flag.p, 1, ncclUint32, ncclMax, cm->nccl, s));
         }
-        cm->comm_bytes += 4 * (g.Nloc / g.G) * (g.G - 1);
+        cm->comm_bytes += 4 * per_dest * (g.G - 1);
     } else {
         std::vector<const uint8_t*> send;
         std::vector<uint8_t*> recv;
         for (RankBufs& b : cm->rk) { send.push_back((const uint8_t*)b.send.p); recv.push_back((uint8_t*)b.recv.p); }
-        if ((rc = all_to_all(cm, send, recv, 4 * g.Nloc / g.G))) return rc;
+        if ((rc = all_to_all(cm, send, recv, 4 * per_dest))) return rc;
     }
     mark(cm, PH_A2A);
     {
         const uint32_t log_ps = ilog2_u64(g.Nloc >> LOG_BLOWUP);
         for (RankBufs& b : cm->rk) {
-            CK(zk_launch(shard_unpack_kernel, dim3((unsigned)(((g.Nloc >> LOG_BLOWUP) + 255) / 256)), dim3(256), 0, s,
-                         (const uint32_t*)b.recv.p, (uint32_t*)b.f_local.p, log_ps, g.G));
+            UnpackSrc us{};
+            for (uint32_t gs = 0; gs < g.G; gs++) {
+                if (cm->p2p) {   // rank gs's send buffer, the chunk it produced for rank b.rank
+                    const uint32_t* base = cm->local ? (const uint32_t*)cm->rk[gs].send.p : cm->peer_send[gs];
+                    us.p[gs] = base + (size_t)b.rank * per_dest;
+                } else {         // after the all-to-all: chunk gs of the local receive buffer
+                    us.p[gs] = (const uint32_t*)b.recv.p + (size_t)gs * per_dest;
+                }
+            }
+            CK(zk_launch(shard_unpack_kernel, dim3((unsigned)(((g.Nloc >> LOG_BLOWUP) + 255) / 256)), dim3(256), 0, s, us,
+                         (uint32_t*)b.f_local.p, log_ps, g.G));
             ctx->launches++;
         }
     }
