@@ -122,10 +122,12 @@ __global__ void __launch_bounds__(256) shard_heads_kernel(const uint32_t* __rest
     heads[i] = local[((size_t)(i >> 4) << log_block) + (i & 15)];
 }
 
-// [g][bl][unit] -> [bl][g][unit] in 16-byte words (all-gather results -> global block order b = bl G + g); `unit`
-// 16-byte words per block: 2 for a digest, 2^log_block / 4 for a block of values
-__global__ void __launch_bounds__(256) shard_interleave_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint32_t G,
-                                                               uint32_t n_bl, uint32_t unit)
+// [g][bl][unit] -> [bl][g][unit] in 16-byte words (per-rank pieces -> global block order b = bl G + g); `unit` 16-byte words
+// per block: 2 for a digest, 2^log_block / 4 for a block of values.  src.p[g] is rank g's piece: a slice of an all-gather
+// result, or rank g's own buffer read over NVLink through its peer mapping (fused gather + re-order).
+struct PeerSrc { const uint4* p[8]; };
+__global__ void __launch_bounds__(256) shard_interleave_kernel(PeerSrc src, uint4* __restrict__ dst, uint32_t G, uint32_t n_bl,
+                                                               uint32_t unit)
 {
     pdl_enter();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;   // index into dst
@@ -134,7 +136,32 @@ __global__ void __launch_bounds__(256) shard_interleave_kernel(const uint4* __re
     const uint32_t u = (uint32_t)(i % unit);
     const size_t b = i / unit;
     const uint32_t g = (uint32_t)(b % G), bl = (uint32_t)(b / G);
-    dst[i] = src[((size_t)g * n_bl + bl) * unit + u];
+    dst[i] = src.p[g][(size_t)bl * unit + u];
+}
+
+// Barrier between the ranks of a node through peer memory: rank `me` raises flag[me] = epoch in every rank's flag array
+// (system-scope release stores over NVLink) and waits until its own array shows `epoch` from everybody.  The kernel sits
+// in the stream behind the work whose results the peers are about to read (griddepcontrol.wait: that work is complete and
+// its writes are performed) and in front of the kernel that reads the peers' results.  ~4 us instead of the ~15-20 us of a
+// one-word NCCL collective.  A peer that never arrives (a failed process) trips a 2-second time-out, reported to the host.
+struct FlagPeers { uint32_t* p[8]; };
+__global__ void shard_barrier_kernel(FlagPeers peers, uint32_t* mine, uint32_t me, uint32_t G, uint32_t epoch, uint32_t* err)
+{
+    pdl_wait();
+    const uint32_t t = threadIdx.x;
+    if (t < G) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.p[t] + me), "r"(epoch) : "memory");
+        const long long t0 = clock64();
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + t) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+            if (clock64() - t0 > 4000000000ll) { *err = 1u; break; }
+        }
+    }
+    __syncthreads();
+    pdl_trigger();
 }
 
 // virtual ranks: byte-wise maximum over G buffers, written back to all of them
@@ -175,13 +202,18 @@ struct zk_shard_comm {
     float phase_ms[16] = {};
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
-    // fused exchange + unpack: every rank's SEND buffer is mapped into this process (cudaIpc), so the unpack kernel reads the
-    // evaluations it owns straight from the ranks that computed them over NVLink and no all-to-all follows
-    bool p2p_wanted = true;                  // ZK_SHARD_NO_P2P=1: always the NCCL all-to-all
+    // Peer memory (cudaIpc over NVLink / NVSwitch): the buffers the other ranks read from are mapped into this process, so
+    // the exchanges are fused into the kernels that consume them -- the unpack reads the evaluations a rank owns straight
+    // out of the send buffers of the ranks that computed them, the block roots of every tree and the first tail layer are
+    // gathered and re-ordered by one kernel -- with a flag barrier in peer memory in front of each instead of a collective.
+    bool p2p_wanted = true;                  // ZK_SHARD_NO_P2P=1: NCCL collectives only
     bool p2p = false;                        // the peers' buffers are mapped (all ranks agree)
-    void* p2p_for = nullptr;                 // the local send buffer the mapping was made for
-    uint32_t* peer_send[8] = {};
-    DevBuf flag;                             // 64-byte-per-rank staging of the handle exchange; word 0 doubles as the barrier word
+    enum { MAP_SEND = 0, MAP_HEAP_F, MAP_HEAP_L, MAP_LAYERS, MAP_FLAGS, MAP_COUNT };
+    void* mapped_for[MAP_COUNT] = {};        // the local buffers the mappings were made for
+    uint8_t* peer[MAP_COUNT][8] = {};        // [buffer][rank]: that rank's buffer in this process's address space
+    DevBuf flags;                            // [0, 8) barrier flags written by the peers; word 16: time-out flag; word 32: scratch
+    DevBuf xchg;                             // staging of the handle exchange
+    uint32_t epoch = 0;
 };
 
 namespace {
@@ -308,56 +340,93 @@ size_t upper_off(const Geometry& g, uint32_t t)
 
 void close_peers(zk_shard_comm* cm)
 {
-    for (uint32_t p = 0; p < cm->G; p++) {
-        if (cm->peer_send[p] && !cm->local && p != cm->rk[0].rank) cudaIpcCloseMemHandle(cm->peer_send[p]);
-        cm->peer_send[p] = nullptr;
+    for (int m = 0; m < zk_shard_comm::MAP_COUNT; m++) {
+        for (uint32_t p = 0; p < cm->G; p++) {
+            if (cm->peer[m][p] && !cm->local && p != cm->rk[0].rank) cudaIpcCloseMemHandle(cm->peer[m][p]);
+            cm->peer[m][p] = nullptr;
+        }
+        cm->mapped_for[m] = nullptr;
     }
     cm->p2p = false;
-    cm->p2p_for = nullptr;
 }
 
-// (Re)maps the peers' send buffers after they were (re)allocated.  Collective: every rank calls it at the same point
-// (buffer sizes depend on the geometry only).  Any rank that cannot map a peer makes ALL ranks fall back to the all-to-all.
+// (Re)maps the peers' buffers after they were (re)allocated.  Collective: every rank calls it at the same point (buffer
+// sizes depend on the geometry only).  Any rank that cannot map a peer makes ALL ranks fall back to NCCL collectives.
 int setup_peers(zk_shard_comm* cm)
 {
     zk_ctx* ctx = cm->ctx;
     if (cm->G == 1 || !cm->p2p_wanted) { cm->p2p = false; return ZK_OK; }
-    if (cm->local) {   // virtual ranks: the "peers" are buffers of the same device
+    if (cm->local) {   // virtual ranks: the "peers" are buffers of the same device, the single stream is the barrier
         cm->p2p = true;
         return ZK_OK;
     }
+    constexpr int NM = zk_shard_comm::MAP_COUNT;
     RankBufs& b = cm->rk[0];
-    if (cm->p2p_for == b.send.p) return ZK_OK;           // still valid
+    CK(cm->flags.ensure(256));
+    CK(cm->xchg.ensure(64 * NM * 8 + 64));
+    void* bases[NM] = {b.send.p, b.heap_f.p, b.heap_layers.p, b.layers.p, cm->flags.p};
+    bool same = cm->p2p;
+    for (int m = 0; m < NM; m++) same = same && cm->mapped_for[m] == bases[m];
+    if (same) return ZK_OK;
     close_peers(cm);
     cudaStream_t s = ctx->stream;
     const uint32_t me = b.rank, G = cm->G;
-    CK(cm->flag.ensure(64 * 8 + 64));
-    cudaIpcMemHandle_t h;
+    // the flags start at zero and the epoch with them; the exchange below orders this against every peer's first signal
+    CK(cudaMemsetAsync(cm->flags.p, 0, 256, s));
+    cm->epoch = 0;
+    cudaIpcMemHandle_t h[NM];
     unsigned char fail_flag = 0;
-    if (cudaIpcGetMemHandle(&h, b.send.p) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; memset(&h, 0, sizeof h); }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
-    uint8_t* st = (uint8_t*)cm->flag.p;
-    CK(cudaMemcpyAsync(st + 64 * me, &h, 64, cudaMemcpyHostToDevice, s));
-    NK(nccl_api()->AllGather(st + 64 * me, st, 64, ncclUint8, cm->nccl, s));
-    cudaIpcMemHandle_t all[8];
-    CK(cudaMemcpyAsync(all, st, 64 * G, cudaMemcpyDeviceToHost, s));
+    for (int m = 0; m < NM; m++)
+        if (cudaIpcGetMemHandle(&h[m], bases[m]) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; memset(&h[m], 0, 64); }
+    uint8_t* st = (uint8_t*)cm->xchg.p;
+    const size_t per = 64 * NM;
+    CK(cudaMemcpyAsync(st + per * me, h, per, cudaMemcpyHostToDevice, s));
+    NK(nccl_api()->AllGather(st + per * me, st, per, ncclUint8, cm->nccl, s));
+    std::vector<cudaIpcMemHandle_t> all((size_t)NM * G);
+    CK(cudaMemcpyAsync(all.data(), st, per * G, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (uint32_t p = 0; p < G && !fail_flag; p++) {
-        if (p == me) { cm->peer_send[p] = (uint32_t*)b.send.p; continue; }
-        void* ptr = nullptr;
-        if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); fail_flag = 1; break; }
-        cm->peer_send[p] = (uint32_t*)ptr;
+        for (int m = 0; m < NM && !fail_flag; m++) {
+            if (p == me) { cm->peer[m][p] = (uint8_t*)bases[m]; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[(size_t)p * NM + m], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                fail_flag = 1;
+                break;
+            }
+            cm->peer[m][p] = (uint8_t*)ptr;
+        }
     }
-    // agree: one failure anywhere means nobody uses the mapping
-    CK(cudaMemcpyAsync(st + 512, &fail_flag, 1, cudaMemcpyHostToDevice, s));
-    NK(nccl_api()->AllReduce(st + 512, st + 512, 1, ncclUint8, ncclMax, cm->nccl, s));
+    // agree: one failure anywhere means nobody uses the mappings
+    CK(cudaMemcpyAsync(st + per * G, &fail_flag, 1, cudaMemcpyHostToDevice, s));
+    NK(nccl_api()->AllReduce(st + per * G, st + per * G, 1, ncclUint8, ncclMax, cm->nccl, s));
     unsigned char any = 0;
-    CK(cudaMemcpyAsync(&any, st + 512, 1, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&any, st + per * G, 1, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (any) { close_peers(cm); return ZK_OK; }
     cm->p2p = true;
-    cm->p2p_for = b.send.p;
+    for (int m = 0; m < NM; m++) cm->mapped_for[m] = bases[m];
     return ZK_OK;
+}
+
+// all ranks have finished what is in front of this point of their streams (peer mode; virtual ranks: one stream, nothing to do)
+int peer_barrier(zk_shard_comm* cm)
+{
+    zk_ctx* ctx = cm->ctx;
+    if (cm->local || cm->G == 1) return ZK_OK;
+    FlagPeers fp{};
+    for (uint32_t p = 0; p < cm->G; p++) fp.p[p] = (uint32_t*)cm->peer[zk_shard_comm::MAP_FLAGS][p];
+    cm->epoch++;
+    CK(zk_launch(shard_barrier_kernel, dim3(1), dim3(32), 0, ctx->stream, fp, (uint32_t*)cm->flags.p, cm->rk[0].rank, cm->G,
+                 cm->epoch, (uint32_t*)cm->flags.p + 16));
+    ctx->launches++;
+    return ZK_OK;
+}
+// rank r's buffer `map` as local rank `i` sees it (peer mode)
+const uint8_t* peer_ptr(zk_shard_comm* cm, int map, uint32_t r, DevBuf RankBufs::*member)
+{
+    return cm->local ? (const uint8_t*)(cm->rk[r].*member).p : cm->peer[map][r];
 }
 
 int ensure_bufs(zk_shard_comm* cm, const Geometry& g, size_t tail_first_len)
@@ -394,31 +463,39 @@ int ensure_bufs(zk_shard_comm* cm, const Geometry& g, size_t tail_first_len)
     return setup_peers(cm);
 }
 
-// Distributed Merkle tree of one layer: the rank-local block subtrees are already in `heap` (levels down to the block
-// roots); gathers the block roots, builds the replicated upper tree and runs the channel step `post` on every rank.
-int commit_upper(zk_shard_comm* cm, const Geometry& g, uint32_t tree, size_t length, const std::vector<uint8_t*>& heaps,
-                 int post, uint32_t fri_layer)
+// Distributed Merkle tree of one layer: the rank-local block subtrees are already in the heaps (levels down to the block
+// roots; the layer's heap starts `heap_off` bytes into the buffer `member`); gathers the block roots, builds the replicated
+// upper tree and runs the channel step `post` on every rank.
+int commit_upper(zk_shard_comm* cm, const Geometry& g, uint32_t tree, size_t length, int map, DevBuf RankBufs::*member,
+                 size_t heap_off, int post, uint32_t fri_layer)
 {
     zk_ctx* ctx = cm->ctx;
     const size_t nbl = (length / g.G) >> g.lb, nbt = length >> g.lb;
     const uint32_t log_nbt = ilog2_u64(nbt);
-    std::vector<const uint8_t*> send;
-    std::vector<uint8_t*> recv;
-    for (size_t i = 0; i < cm->rk.size(); i++) {
-        send.push_back(heaps[i] + 32 * (nbl - 1));          // heap level log2(nbl): the block roots
-        recv.push_back((uint8_t*)cm->rk[i].stage.p);
+    const size_t roots_off = heap_off + 32 * (nbl - 1);       // heap level log2(nbl): the block roots
+    int rc;
+    if (cm->p2p) {
+        if ((rc = peer_barrier(cm))) return rc;
+        cm->comm_bytes += 32 * nbl * (g.G - 1);
+    } else {
+        std::vector<const uint8_t*> send;
+        std::vector<uint8_t*> recv;
+        for (RankBufs& b : cm->rk) {
+            send.push_back((const uint8_t*)(b.*member).p + roots_off);
+            recv.push_back((uint8_t*)b.stage.p);
+        }
+        if ((rc = all_gather(cm, send, recv, 32 * nbl))) return rc;
     }
-    int rc = all_gather(cm, send, recv, 32 * nbl);
-    if (rc) return rc;
-    for (size_t i = 0; i < cm->rk.size(); i++) {
-        uint8_t* upper = (uint8_t*)cm->rk[i].upper.p + upper_off(g, tree);
+    for (RankBufs& b : cm->rk) {
+        uint8_t* upper = (uint8_t*)b.upper.p + upper_off(g, tree);
+        PeerSrc ps{};
+        for (uint32_t r = 0; r < g.G; r++)
+            ps.p[r] = cm->p2p ? (const uint4*)(peer_ptr(cm, map, r, member) + roots_off) : (const uint4*)((const uint8_t*)b.stage.p + 32 * nbl * r);
         const size_t total = nbt * 2;
-        CK(zk_launch(shard_interleave_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ctx->stream,
-                     (const uint4*)cm->rk[i].stage.p, (uint4*)(upper + 32 * (nbt - 1)), g.G, (uint32_t)nbl, 2u));
+        CK(zk_launch(shard_interleave_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ctx->stream, ps,
+                     (uint4*)(upper + 32 * (nbt - 1)), g.G, (uint32_t)nbl, 2u));
         ctx->launches++;
-        if ((rc = zk_shard_upper_tree_dev(ctx, upper, log_nbt, post, fri_layer, g.k, cm->rk[i].state.p,
-                                          (uint8_t*)cm->rk[i].transcript.p)))
-            return rc;
+        if ((rc = zk_shard_upper_tree_dev(ctx, upper, log_nbt, post, fri_layer, g.k, b.state.p, (uint8_t*)b.transcript.p))) return rc;
     }
     return ZK_OK;
 }
@@ -491,11 +568,8 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
     mark(cm, PH_LDE);
     const size_t per_dest = g.Nloc / g.G;                     // words every rank produced for every other rank
     if (cm->p2p) {
-        // every rank's transforms must be complete before anybody reads them: a one-word all-reduce is the barrier (it cannot
-        // finish anywhere before every rank has entered it, i.e. finished the kernels in front of it on its stream)
-        if (!cm->local) {
-            NK(nccl_api()->AllReduce(cm->flag.p, cm->flag.p, 1, ncclUint32, ncclMax, cm->nccl, s));
-        }
+        // every rank's transforms must be complete before anybody reads them
+        if ((rc = peer_barrier(cm))) return rc;
         cm->comm_bytes += 4 * per_dest * (g.G - 1);
     } else {
         std::vector<const uint8_t*> send;
@@ -510,7 +584,7 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
             UnpackSrc us{};
             for (uint32_t gs = 0; gs < g.G; gs++) {
                 if (cm->p2p) {   // rank gs's send buffer, the chunk it produced for rank b.rank
-                    const uint32_t* base = cm->local ? (const uint32_t*)cm->rk[gs].send.p : cm->peer_send[gs];
+                    const uint32_t* base = (const uint32_t*)peer_ptr(cm, zk_shard_comm::MAP_SEND, gs, &RankBufs::send);
                     us.p[gs] = base + (size_t)b.rank * per_dest;
                 } else {         // after the all-to-all: chunk gs of the local receive buffer
                     us.p[gs] = (const uint32_t*)b.recv.p + (size_t)gs * per_dest;
@@ -524,12 +598,9 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
     mark(cm, PH_UNPACK);
 
     // ---- f tree (prover.rs:81-85), then alpha_0..2 (prover.rs:163-165) on every rank
-    std::vector<uint8_t*> heaps;
-    for (RankBufs& b : cm->rk) {
+    for (RankBufs& b : cm->rk)
         if ((rc = zk_shard_merkle_blocks_dev(ctx, (const uint32_t*)b.f_local.p, g.Nloc, g.lb, (uint8_t*)b.heap_f.p))) return rc;
-        heaps.push_back((uint8_t*)b.heap_f.p);
-    }
-    if ((rc = commit_upper(cm, g, 0, g.N, heaps, POST_F, 0))) return rc;
+    if ((rc = commit_upper(cm, g, 0, g.N, zk_shard_comm::MAP_HEAP_F, &RankBufs::heap_f, 0, POST_F, 0))) return rc;
     mark(cm, PH_FTREE);
 
     // ---- Part 2: composition polynomial (prover.rs:101-180), fused into the leaf pass of the block subtrees
@@ -546,7 +617,6 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
         if ((rc = ring_from_next(cm, send, recv, 64 * g.nbl))) return rc;
     }
     mark(cm, PH_HALO);
-    heaps.clear();
     for (RankBufs& b : cm->rk) {
         // the block after local block bl of the LAST rank is rank 0's block bl + 1 (wrapping around the domain)
         const uint32_t roll = (b.rank + 1 == g.G) ? 1u : 0u;
@@ -556,40 +626,47 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
         if ((rc = shard_cp_blocks(ctx, (const uint32_t*)b.f_local.p, (const uint32_t*)b.halo.p, roll, g.Nloc, log_n, g.G, b.rank, g.lb,
                                   b.state.p, (uint32_t*)b.layers.p, (uint8_t*)b.heap_layers.p, &b.cp_tab)))
             return rc;
-        heaps.push_back((uint8_t*)b.heap_layers.p);
     }
-    if ((rc = commit_upper(cm, g, 1, g.N, heaps, POST_CP, 0))) return rc;
+    if ((rc = commit_upper(cm, g, 1, g.N, zk_shard_comm::MAP_HEAP_L, &RankBufs::heap_layers, 0, POST_CP, 0))) return rc;
     mark(cm, PH_CPTREE);
 
     // ---- Part 3: FRI (prover.rs:192-254).  Folds stay rank-local; fold + next layer's block subtrees are one pass.
     size_t length = g.N;
     for (uint32_t i = 0; i < first_tail; i++) {
-        heaps.clear();
         for (RankBufs& b : cm->rk) {
             uint32_t* cur = (uint32_t*)b.layers.p + local_vals_off(g, i);
             uint32_t* nxt = (uint32_t*)b.layers.p + local_vals_off(g, i + 1);
             uint8_t* heap = (uint8_t*)b.heap_layers.p + local_heap_off(g, i + 1);
             if ((rc = zk_shard_fold_blocks_dev(ctx, cur, length / g.G, i, g.log_N, g.G, b.rank, g.lb, b.state.p, nxt, heap))) return rc;
-            heaps.push_back(heap);
         }
-        if ((rc = commit_upper(cm, g, 2 + i, length / 2, heaps, POST_FRI, i + 1))) return rc;
+        if ((rc = commit_upper(cm, g, 2 + i, length / 2, zk_shard_comm::MAP_HEAP_L, &RankBufs::heap_layers, local_heap_off(g, i + 1), POST_FRI, i + 1))) return rc;
         length >>= 1;
     }
     mark(cm, PH_FRI);
     // replicated tail: gather layer first_tail and finish on every rank
     {
-        std::vector<const uint8_t*> send;
-        std::vector<uint8_t*> recv;
-        for (RankBufs& b : cm->rk) {
-            send.push_back((const uint8_t*)((uint32_t*)b.layers.p + local_vals_off(g, first_tail)));
-            recv.push_back((uint8_t*)b.stage.p);
+        const size_t vals_off = 4 * local_vals_off(g, first_tail), piece = 4 * (length / g.G);   // bytes
+        if (cm->p2p) {
+            if ((rc = peer_barrier(cm))) return rc;
+            cm->comm_bytes += piece * (g.G - 1);
+        } else {
+            std::vector<const uint8_t*> send;
+            std::vector<uint8_t*> recv;
+            for (RankBufs& b : cm->rk) {
+                send.push_back((const uint8_t*)b.layers.p + vals_off);
+                recv.push_back((uint8_t*)b.stage.p);
+            }
+            if ((rc = all_gather(cm, send, recv, piece))) return rc;
         }
-        if ((rc = all_gather(cm, send, recv, 4 * (length / g.G)))) return rc;
         const size_t nblc = (length / g.G) >> g.lb;
         for (RankBufs& b : cm->rk) {
+            PeerSrc ps{};
+            for (uint32_t r = 0; r < g.G; r++)
+                ps.p[r] = cm->p2p ? (const uint4*)(peer_ptr(cm, zk_shard_comm::MAP_LAYERS, r, &RankBufs::layers) + vals_off)
+                                  : (const uint4*)((const uint8_t*)b.stage.p + piece * r);
             const size_t total = length / 4;
-            CK(zk_launch(shard_interleave_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, (const uint4*)b.stage.p,
-                         (uint4*)b.tail_vals.p, g.G, (uint32_t)nblc, (uint32_t)(1u << (g.lb - 2))));
+            CK(zk_launch(shard_interleave_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, ps, (uint4*)b.tail_vals.p, g.G,
+                         (uint32_t)nblc, (uint32_t)(1u << (g.lb - 2))));
             ctx->launches++;
             if ((rc = zk_shard_fri_tail_dev(ctx, log_n, first_tail, (uint32_t*)b.tail_vals.p, (uint8_t*)b.tail_heaps.p, b.state.p,
                                             (uint8_t*)b.transcript.p)))
@@ -621,8 +698,14 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
         CK(cudaMemcpyAsync(pin + per * i, cm->rk[i].transcript.p, g.trs + 64, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(pin + per * i + g.trs + 64, cm->rk[i].state.p, sizeof(ProofState), cudaMemcpyDeviceToHost, s));
     }
+    uint32_t peer_timeout = 0;
+    if (cm->p2p && !cm->local) CK(cudaMemcpyAsync(&peer_timeout, (uint32_t*)cm->flags.p + 16, 4, cudaMemcpyDeviceToHost, s));
     mark(cm, PH_END);
     CK(cudaStreamSynchronize(s));
+    if (peer_timeout) {
+        cudaMemsetAsync((uint32_t*)cm->flags.p + 16, 0, 4, s);
+        return fail(ctx, ZK_ERR_COMM, "a rank did not reach a peer-memory barrier within 2 s");
+    }
     for (int p = 0; p + 1 < PH_COUNT; p++) cudaEventElapsedTime(&cm->phase_ms[p], cm->ev[p], cm->ev[p + 1]);
     cudaEventElapsedTime(&cm->phase_ms[PH_COUNT - 1], cm->ev[PH_START], cm->ev[PH_END]);
 
@@ -718,7 +801,8 @@ void zk_shard_comm_destroy(zk_shard_comm* cm)
     cudaSetDevice(cm->ctx->device);
     cudaStreamSynchronize(cm->ctx->stream);
     close_peers(cm);
-    cm->flag.release();
+    cm->flags.release();
+    cm->xchg.release();
     if (cm->nccl && nccl_api()) nccl_api()->CommDestroy(cm->nccl);
     for (RankBufs& b : cm->rk) {
         DevBuf* bufs[] = {&b.state, &b.transcript, &b.y, &b.coeffs, &b.work, &b.send, &b.recv, &b.f_local, &b.layers, &b.heap_f,
