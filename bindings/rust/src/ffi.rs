@@ -52,6 +52,7 @@ extern "C" {
     pub fn zk_proof_deserialize(bytes: *const u8, len: usize, state_out: *mut u8, transcript_out: *mut *const u8, transcript_len_out: *mut usize) -> c_int;
     pub fn zk_trace_fibsq(log_n: u32, secret: u32, trace_out: *mut u32) -> c_int;
     pub fn zk_ctx_trim(ctx: *mut zk_ctx, tables_too: c_int) -> c_int;
+    pub fn zk_trace_fibsq_batch(log_n: u32, secrets: *const u32, n_proofs: u32, threads: u32, out: *mut u32) -> c_int;
     pub fn zk_ctx_set_memory_budget(ctx: *mut zk_ctx, bytes: usize) -> c_int;
     pub fn zk_interpolate_subgroup_dev(ctx: *mut zk_ctx, y_inout_n: *mut u32, n_points: u32, log_n: u32, coeffs_out: *mut u32) -> c_int;
     pub fn zk_lde_coset_dev(ctx: *mut zk_ctx, coeffs: *const u32, log_n: u32, log_blowup: u32, shift: u32, evals_out: *mut u32) -> c_int;

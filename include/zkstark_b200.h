@@ -154,6 +154,10 @@ int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t *trace_out);
 /* releases the proving work space, the scratch buffers and the per-size composition-polynomial tables (tables_too != 0:
  * also the power tables); everything is re-created on demand.  Synchronises the context's streams. */
 int zk_ctx_trim(zk_ctx *ctx, int tables_too);
+/* the same for n_proofs secrets at once (host): groups of 8 traces advance together as SIMD lanes (AVX2), the groups are
+ * spread over `threads` host threads (0: all).  out: n_proofs rows of 2^log_n - 1 values.  This is what
+ * zk_prove_stream_submit and zk_prove_fibsq_batch_secrets run one batch ahead of the proving. */
+int zk_trace_fibsq_batch(uint32_t log_n, const uint32_t *secrets, uint32_t n_proofs, uint32_t threads, uint32_t *out);
 /* cap on device bytes a ctx may hold for proving work space (default: 70% of free memory) */
 int zk_ctx_set_memory_budget(zk_ctx *ctx, size_t bytes);
 

@@ -133,3 +133,24 @@ def test_rust_patches_apply(tmp_path):
     src = (work / "src" / "polynomial.rs").read_text()
     assert "crate::gpu::lagrange_hook(points)" in src and "pub fn lagrange<T>(points: &Vec<(T, T)>) -> Polynomial<T>" in src
     assert "pub fn new(mut size: usize, data: impl Iterator<Item = u32>) -> Self" in (work / "src" / "merkle.rs").read_text()
+
+
+def test_trace_batch_simd_matches_scalar(orc):
+    """zk_trace_fibsq_batch (8 traces per SIMD group, several threads) == zk_trace_fibsq == the oracle's trace, incl. a
+    batch that is not a multiple of 8 and secrets 0, 1, p - 1, >= p."""
+    P = 3221225473
+    secrets = np.array([3141592, 0, 1, P - 1, P, P + 7, 0xFFFFFFFF, 12345, 99, 2**31, 2**31 + 1, 7, 8, 9, 10, 11, 12, 13, 14], dtype=np.uint32)
+    for log_n in (1, 2, 3, 10, 13):
+        for threads in (1, 3):
+            got = zk.trace_fibsq_batch(log_n, secrets, threads)
+            for j, s in enumerate(secrets.tolist()):
+                assert np.array_equal(got[j], zk.trace_fibsq(log_n, s)), (log_n, j)
+    assert int(zk.trace_fibsq_batch(10, secrets[:1])[0][1022]) == 2338775057      # prover.rs:42
+    import time
+    t0 = time.perf_counter()
+    zk.trace_fibsq_batch(18, np.arange(8, dtype=np.uint32) + 5, 1)
+    t8 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    zk.trace_fibsq(18, 5)
+    t1 = time.perf_counter() - t0
+    print(f"8 traces SIMD {t8 * 1e3:.2f} ms vs 1 scalar {t1 * 1e3:.2f} ms")

@@ -9,7 +9,7 @@ mkdir -p ../variants
 obj=/tmp/zkvar_${name}_$(basename $src .cu).o
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC "$@" -c $src -o $obj
 objs=""
-for o in tree.o ntt.o capi.o sharded.o benchsupport.o trace.o host_sha256.o verify.o; do
+for o in tree.o ntt.o capi.o sharded.o benchsupport.o trace.o host_sha256.o host_trace.o verify.o; do
   if [ "$o" = "$(basename $src .cu).o" ]; then objs="$objs $obj"; else objs="$objs $o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libzk_${name}.so $objs -lcudart -ldl

@@ -19,6 +19,7 @@ from ._binding import (  # noqa: F401
     lib,
     transcript_len,
     trace_fibsq,
+    trace_fibsq_batch,
     merkle_trace_host,
     proof_serialize,
     proof_deserialize,

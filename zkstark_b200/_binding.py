@@ -69,6 +69,7 @@ def lib():
         "zk_prove_fibsq_from_trace": ([vp, u32, vp, vp, sz, C.POINTER(sz), vp], i32),
         "zk_prove_fibsq_batch": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_trace_fibsq": ([u32, u32, vp], i32),
+        "zk_trace_fibsq_batch": ([u32, vp, u32, u32, vp], i32),
         "zk_prove_fibsq_batch_secrets": ([vp, u32, u32, vp, vp, vp], i32),
         "zk_transcript_len_ex": ([u32, u32], sz),
         "zk_prove_fibsq_ex": ([vp, u32, u32, vp, u32, vp, sz, C.POINTER(sz), vp], i32),
@@ -150,6 +151,16 @@ def trace_fibsq(log_n, secret=3141592):
     rc = lib().zk_trace_fibsq(log_n, secret, _p(out))
     if rc:
         raise ZkError(rc, "zk_trace_fibsq")
+    return out
+
+
+def trace_fibsq_batch(log_n, secrets, threads=0):
+    """prover.rs:32-39 for many secrets at once (host, SIMD lanes x threads): rows of 2^log_n - 1 values."""
+    secrets = _u32(secrets)
+    out = np.empty((len(secrets), (1 << log_n) - 1), dtype=np.uint32)
+    rc = lib().zk_trace_fibsq_batch(log_n, _p(secrets), len(secrets), threads, _p(out))
+    if rc:
+        raise ZkError(rc, "zk_trace_fibsq_batch")
     return out
 
 

@@ -828,6 +828,32 @@ int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t* out)
     return ZK_OK;
 }
 
+// prover.rs:32-39 for n_proofs secrets at once on the host: groups of 8 traces advance as SIMD lanes (AVX2), the groups are
+// spread over `threads` host threads (0: all hardware threads).  out: n_proofs rows of 2^log_n - 1 values.
+int zk_trace_fibsq_batch(uint32_t log_n, const uint32_t* secrets, uint32_t n_proofs, uint32_t threads, uint32_t* out)
+{
+    if (!secrets || !out || n_proofs == 0 || log_n < 1 || log_n > 30) return ZK_ERR_INVALID;
+    const size_t n1 = ((size_t)1 << log_n) - 1;
+    uint32_t T = threads ? threads : std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    const uint32_t gsz = (n_proofs + 7) / 8 >= T ? 8 : 4;
+    const uint32_t n_groups = (n_proofs + gsz - 1) / gsz;
+    if (T > n_groups) T = n_groups;
+    auto body = [&](uint32_t t) {
+        for (uint32_t gi = t; gi < n_groups; gi += T) {
+            const uint32_t b0 = gsz * gi, cnt = n_proofs - b0 < gsz ? n_proofs - b0 : gsz;
+            uint32_t* rows[8];
+            for (uint32_t j = 0; j < cnt; j++) rows[j] = out + n1 * (b0 + j);
+            host_traces(log_n, secrets + b0, rows, cnt);
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < T; t++) th.emplace_back(body, t);
+    body(0);
+    for (auto& x : th) x.join();
+    return ZK_OK;
+}
+
 int zk_prove_fibsq_resident(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const uint32_t* traces_dev,
                             uint8_t* transcripts_out, uint8_t* states_out)
 {
@@ -913,13 +939,24 @@ static void stream_worker(zk_ctx* ctx, zk_ctx::StreamSlot* sl)
     if (T < 1) T = 1;
     if (T > sl->n) T = sl->n;
     std::vector<cudaError_t> errs(T, cudaSuccess);
+    // a task is a group of 8 proofs (4 when there are more threads than such groups): they advance together as SIMD lanes
+    // (host_traces), then their rows are uploaded
+    const uint32_t gsz = (sl->n + 7) / 8 >= T ? 8 : 4;
+    const uint32_t n_groups = (sl->n + gsz - 1) / gsz;
+    if (T > n_groups) T = n_groups;
+    errs.assign(T, cudaSuccess);
     auto body = [&](uint32_t t) {
         cudaSetDevice(ctx->device);
-        for (uint32_t b = t; b < sl->n; b += T) {
-            uint32_t* row = (uint32_t*)sl->pinned + n * b;
-            zk_trace_fibsq(sl->log_n, sl->host_secrets[b], row);
-            cudaError_t e = cudaMemcpyAsync((uint32_t*)sl->traces.p + n * b, row, 4 * (n - 1), cudaMemcpyHostToDevice, ctx->trace_stream);
-            if (e != cudaSuccess) errs[t] = e;
+        for (uint32_t gi = t; gi < n_groups; gi += T) {
+            const uint32_t b0 = gsz * gi, cnt = sl->n - b0 < gsz ? sl->n - b0 : gsz;
+            uint32_t* rows[8];
+            for (uint32_t j = 0; j < cnt; j++) rows[j] = (uint32_t*)sl->pinned + n * (b0 + j);
+            host_traces(sl->log_n, sl->host_secrets.data() + b0, rows, cnt);
+            for (uint32_t j = 0; j < cnt; j++) {
+                cudaError_t e = cudaMemcpyAsync((uint32_t*)sl->traces.p + n * (b0 + j), rows[j], 4 * (n - 1), cudaMemcpyHostToDevice,
+                                                ctx->trace_stream);
+                if (e != cudaSuccess) errs[t] = e;
+            }
         }
     };
     std::vector<std::thread> th;

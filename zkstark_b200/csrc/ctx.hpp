@@ -29,6 +29,7 @@ cudaError_t launch_trace_batch(cudaStream_t s, const uint32_t* secrets_dev, uint
 cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
 double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
+void host_traces(uint32_t log_n, const uint32_t* secrets, uint32_t* const* rows, uint32_t count);
 int ntt_pass_times(float ms[4]);
 size_t ntt_table_words();
 cudaError_t ntt2_build_tables(cudaStream_t s, uint32_t* tw_fwd, uint32_t* tw_inv);
