@@ -299,11 +299,12 @@ def test_launch_counter_counts_own_kernels(ctx):
 
 # ---------------------------------------------------------------- 8(f) rows: device trace generation, verifier
 def test_prove_batch_from_secrets(ctx, orc):
-    """zk_prove_fibsq_batch_secrets: traces generated on the device (one thread per proof, prover.rs:32-39)."""
+    """zk_prove_fibsq_batch_secrets: traces generated inside the call (host SIMD lanes x threads, one sub-batch ahead of the
+    proving; 70 proofs: cut into four sub-batches), prover.rs:32-39."""
     log_n = 9
-    secrets = np.array([3141592, 0, 1, P - 1, P + 5, 0xFFFFFFFF] + list(range(100, 140)), dtype=np.uint32)
+    secrets = np.array([3141592, 0, 1, P - 1, P + 5, 0xFFFFFFFF] + list(range(100, 164)), dtype=np.uint32)
     trs, sts = ctx.prove_fibsq_batch_secrets(log_n, secrets)
-    for j in (0, 1, 2, 3, 4, 5, 17, 45):
+    for j in (0, 1, 2, 3, 4, 5, 17, 18, 35, 36, 53, 69):
         otr, ost, info = orc.prove_fibsq(log_n, int(secrets[j]))
         assert trs[j].tobytes() == otr and sts[j].tobytes() == ost
         assert zk.verify_fibsq(log_n, info.a_last, otr, ost) == (True, 0)

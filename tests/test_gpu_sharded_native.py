@@ -76,6 +76,17 @@ def test_native_all_to_all_path_matches_peer_path(ctx, orc, log_n, G, lb, monkey
             comm.close()
 
 
+def test_native_single_real_rank(ctx, orc):
+    """zk_shard_comm_init with n_ranks = 1: the real-rank code path without NCCL (no peers, no collectives)."""
+    comm = zk.ShardComm(ctx, 1, 0, bytes(128))
+    try:
+        trace = zk.trace_fibsq(13, 5)
+        assert comm.prove(13, trace) == orc.prove_fibsq(13, 5)[:2]
+        assert comm.last_comm_bytes() == 0
+    finally:
+        comm.close()
+
+
 def test_native_rejects_bad_arguments(ctx):
     with pytest.raises(zk.ZkError):
         zk.ShardComm.local(ctx, 3)

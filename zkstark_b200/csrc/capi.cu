@@ -901,8 +901,11 @@ int zk_prove_fibsq_batch_secrets(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs,
     if (ctx->slot_count) return fail(ctx, ZK_ERR_INVALID, "batches of zk_prove_stream_submit are in flight: collect them first");
     CK(cudaSetDevice(ctx->device));
     const size_t trl = transcript_len(log_n);
-    // sub-batches go through the submit / collect pipeline: the traces of sub-batch j + 1 are produced while j is proved
-    const uint32_t nbmax = pick_subbatch(ctx, log_n, n_proofs);
+    // sub-batches go through the submit / collect pipeline: the traces of sub-batch j + 1 are produced while j is proved.
+    // A call that would fit one sub-batch is still cut in four (of at least 16 proofs) so that only the first quarter's
+    // trace generation is exposed.
+    uint32_t nbmax = pick_subbatch(ctx, log_n, n_proofs);
+    if (n_proofs >= 64 && nbmax >= n_proofs) nbmax = (n_proofs + 3) / 4;
     auto count = [&](uint32_t done) { return n_proofs - done < nbmax ? n_proofs - done : nbmax; };
     if ((rc = zk_prove_stream_submit(ctx, log_n, count(0), secrets))) return rc;
     for (uint32_t done = 0; done < n_proofs; done += nbmax) {
