@@ -452,8 +452,8 @@ def other_configs(args, ctx, zk, torch, dist, world, rank, local, stream, barrie
     best = min(phases, key=lambda p: p["total"])
     line["sharded_2p%d" % ks] = {
         "workload": f"BASELINE configs[4]: ONE FibonacciSq proof, trace 2^{ks} (LDE 2^{ks + 3}), sharded over {world} GPU(s): "
-                    "coset-split LDE + one NCCL all-to-all, blocked-cyclic ownership (zk_prove_fibsq_sharded); pinned host "
-                    "trace in, transcript out",
+                    "coset-split LDE, one exchange through NVLink peer memory fused into the unpack kernel (NCCL all-to-all "
+                    "as fallback), blocked-cyclic ownership (zk_prove_fibsq_sharded); pinned host trace in, transcript out",
         "ms": ms_sh, "ms_1gpu": ms_1gpu, "efficiency": (ms_1gpu / (world * ms_sh)) if ms_1gpu else None, "n_gpus": world,
         "scaling": "strong", "nvlink_bytes_per_rank": comm.last_comm_bytes(), "first_tail_layer": comm.last_first_tail(),
         "phase_ms": {a: round(b, 4) for a, b in best.items()},
