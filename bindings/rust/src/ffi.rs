@@ -11,6 +11,22 @@ pub struct zk_ctx {
 pub struct zk_shard_comm {
     _private: [u8; 0],
 }
+/// The program being proven as data (include/zkstark_b200.h `zk_air`): a[0] = a0, a[1] = secret,
+/// a[i+2] = c20 a[i+1]^2 + c02 a[i]^2 + c11 a[i] a[i+1] + c10 a[i+1] + c01 a[i] + c00.  FIBSQ is the reference's program.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub struct zk_air {
+    pub a0: u32,
+    pub c20: u32,
+    pub c02: u32,
+    pub c11: u32,
+    pub c10: u32,
+    pub c01: u32,
+    pub c00: u32,
+    pub flags: u32,
+}
+pub const ZK_AIR_FIBSQ: zk_air = zk_air { a0: 1, c20: 1, c02: 1, c11: 0, c10: 0, c01: 0, c00: 0, flags: 0 };
+pub const ZK_AIR_NO_SPECIALISE: u32 = 1;
 
 pub const ZK_OK: c_int = 0;
 pub const ZK_ERR_VERIFY: c_int = -6;
@@ -53,6 +69,11 @@ extern "C" {
     pub fn zk_trace_fibsq(log_n: u32, secret: u32, trace_out: *mut u32) -> c_int;
     pub fn zk_ctx_trim(ctx: *mut zk_ctx, tables_too: c_int) -> c_int;
     pub fn zk_trace_fibsq_batch(log_n: u32, secrets: *const u32, n_proofs: u32, threads: u32, out: *mut u32) -> c_int;
+    pub fn zk_ctx_set_air(ctx: *mut zk_ctx, air: *const zk_air) -> c_int;
+    pub fn zk_ctx_get_air(ctx: *const zk_ctx, out: *mut zk_air) -> c_int;
+    pub fn zk_trace_air(air: *const zk_air, log_n: u32, secret: u32, trace_out: *mut u32) -> c_int;
+    pub fn zk_trace_air_batch(air: *const zk_air, log_n: u32, secrets: *const u32, n_proofs: u32, threads: u32, out: *mut u32) -> c_int;
+    pub fn zk_verify_air(air: *const zk_air, log_n: u32, a_last: u32, transcript: *const u8, len: usize, state: *const u8, init_state: *const u8, n_extra_queries: u32, rederive: c_int, failed_check: *mut c_int) -> c_int;
     pub fn zk_ctx_set_memory_budget(ctx: *mut zk_ctx, bytes: usize) -> c_int;
     pub fn zk_interpolate_subgroup_dev(ctx: *mut zk_ctx, y_inout_n: *mut u32, n_points: u32, log_n: u32, coeffs_out: *mut u32) -> c_int;
     pub fn zk_lde_coset_dev(ctx: *mut zk_ctx, coeffs: *const u32, log_n: u32, log_blowup: u32, shift: u32, evals_out: *mut u32) -> c_int;

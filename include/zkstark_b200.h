@@ -158,6 +158,28 @@ int zk_ctx_trim(zk_ctx *ctx, int tables_too);
  * spread over `threads` host threads (0: all).  out: n_proofs rows of 2^log_n - 1 values.  This is what
  * zk_prove_stream_submit and zk_prove_fibsq_batch_secrets run one batch ahead of the proving. */
 int zk_trace_fibsq_batch(uint32_t log_n, const uint32_t *secrets, uint32_t n_proofs, uint32_t threads, uint32_t *out);
+
+/* ---- the program being proven as data.  The reference hard-codes FibonacciSq (trace loop prover.rs:32-39,
+ * transition numerator prover.rs:134-138, verifier proof.rs:66-70); a zk_air describes a one-column program over a
+ * three-row window with the reference's two boundary constraints (first value, value n - 2):
+ *   a[0] = a0, a[1] = secret, a[i+2] = c20 a[i+1]^2 + c02 a[i]^2 + c11 a[i] a[i+1] + c10 a[i+1] + c01 a[i] + c00.
+ * The coefficients are u32 reduced mod p like every value that enters the field (field.rs:20-24).  The transition degree
+ * is at most 2, so the composition polynomial keeps degree < n and every other step of the protocol (domains, folds,
+ * transcript layout and length) is the reference's.  {1, 1,1,0,0,0,0} is FibonacciSq and runs the specialised code unless
+ * ZK_AIR_NO_SPECIALISE is set (testing: the general code path on the reference's program must give the reference's
+ * transcript).  zk_ctx_set_air (null: FibonacciSq) applies to every prove entry point of the context -- from secrets, from
+ * traces, batched, pipelined, sharded -- and to zk_cp_eval_fibsq[_dev]; traces handed in must satisfy the program. */
+typedef struct zk_air { uint32_t a0, c20, c02, c11, c10, c01, c00, flags; } zk_air;
+#define ZK_AIR_NO_SPECIALISE 1u
+int zk_ctx_set_air(zk_ctx *ctx, const zk_air *air);
+int zk_ctx_get_air(const zk_ctx *ctx, zk_air *out);
+/* the trace of the program (host; SIMD lanes over proofs like zk_trace_fibsq_batch): rows of 2^log_n - 1 values */
+int zk_trace_air(const zk_air *air, uint32_t log_n, uint32_t secret, uint32_t *trace_out);
+int zk_trace_air_batch(const zk_air *air, uint32_t log_n, const uint32_t *secrets, uint32_t n_proofs, uint32_t threads,
+                       uint32_t *out);
+/* zk_verify_fibsq_ex for a proof of the program `air` (null: FibonacciSq) */
+int zk_verify_air(const zk_air *air, uint32_t log_n, uint32_t a_last, const uint8_t *transcript, size_t len,
+                  const uint8_t *state, const uint8_t *init_state, uint32_t n_extra_queries, int rederive, int *failed_check);
 /* cap on device bytes a ctx may hold for proving work space (default: 70% of free memory) */
 int zk_ctx_set_memory_budget(zk_ctx *ctx, size_t bytes);
 

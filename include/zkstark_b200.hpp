@@ -218,11 +218,12 @@ struct Proof {  // proof.rs:5-13
     std::vector<uint8_t> data;
     uint32_t log_n = 10;
     uint32_t a_last = 2338775057u;  // proof.rs:70
+    zk_air air{1, 1, 1, 0, 0, 0, 0, 0};  // the program the proof is about; the reference's FibonacciSq
     // proof.rs:15-149; throws where the reference panics.  Also replays the channel (alpha/beta/query, state).
     void verify() const
     {
         int line = 0;
-        int rc = zk_verify_fibsq(log_n, a_last, data.data(), data.size(), state.data(), 1, &line);
+        int rc = zk_verify_air(&air, log_n, a_last, data.data(), data.size(), state.data(), nullptr, 0, 1, &line);
         if (rc != ZK_OK) throw Error(rc, "proof rejected: the assert at proof.rs:" + std::to_string(line) + " fails");
     }
     size_t size() const { return 48 + data.size(); }  // proof.rs:151-154 (size_of::<Proof>() == 48)
@@ -270,6 +271,28 @@ inline Proof generate_proof(const Channel& channel, uint32_t log_n = 10, uint32_
     x.check(zk_prove_fibsq(x.get(), log_n, secret, p.data.data(), p.data.size(), &len, p.state.data()));
     p.data.resize(len);
     p.a_last = trace_fibsq(log_n, secret).back();
+    return p;
+}
+
+// generate_proof for another program of the zk_air family (the context proves `air` for the duration of the
+// call and returns to the reference's program afterwards).
+inline std::vector<uint32_t> trace_air(const zk_air& air, uint32_t log_n, uint32_t secret)
+{
+    std::vector<uint32_t> a((size_t(1) << log_n) - 1);
+    if (zk_trace_air(&air, log_n, secret, a.data()) != ZK_OK) throw Error(ZK_ERR_INVALID, "bad log_n or zk_air");
+    return a;
+}
+inline Proof generate_proof_air(const Channel& channel, const zk_air& air, uint32_t log_n, uint32_t secret)
+{
+    auto& x = Context::current();
+    x.check(zk_ctx_set_air(x.get(), &air));
+    struct Reset {
+        zk_ctx* c;
+        ~Reset() { zk_ctx_set_air(c, nullptr); }
+    } reset{x.get()};
+    Proof p = generate_proof(channel, log_n, secret);
+    p.air = air;
+    p.a_last = trace_air(air, log_n, secret).back();
     return p;
 }
 

@@ -74,6 +74,11 @@ def lib():
     L.orc_prove_fibsq.restype = i32
     L.orc_transcript_len.argtypes = [u32]; L.orc_transcript_len.restype = C.c_size_t
     L.orc_verify_fibsq.argtypes = [u32, u32, vp, C.c_size_t, i32, vp]; L.orc_verify_fibsq.restype = i32
+    L.orc_air_step.argtypes = [vp, u32, u32]; L.orc_air_step.restype = u32
+    L.orc_trace_air.argtypes = [vp, u32, u32, vp]; L.orc_trace_air.restype = None
+    L.orc_cp_eval_air.argtypes = [vp, vp, u32, u32, vp, u32, u32, vp, i32]; L.orc_cp_eval_air.restype = i32
+    L.orc_prove_air.argtypes = [vp, u32, u32, i32, i32, vp, C.c_size_t, vp, vp, vp]; L.orc_prove_air.restype = i32
+    L.orc_verify_air.argtypes = [vp, u32, u32, vp, C.c_size_t, i32, vp]; L.orc_verify_air.restype = i32
     _lib = L
     return L
 
@@ -155,6 +160,48 @@ def root_from_path(element, index, path):
     out = np.empty(32, dtype=np.uint8)
     lib().orc_root_from_path(element, index, _ptr(path), path.shape[0], _ptr(out))
     return out
+
+
+# ---- the AIR family of SURVEY 8(f4): air = (a0, c20, c02, c11, c10, c01, c00), see oracle.h
+AIR_FIBSQ = (1, 1, 1, 0, 0, 0, 0)
+
+
+def _air(air):
+    a = (C.c_uint32 * 7)(*[int(v) for v in air])
+    return a
+
+
+def trace_air(air, log_n, secret=3141592):
+    out = np.empty((1 << log_n) - 1, dtype=np.uint32)
+    lib().orc_trace_air(_air(air), log_n, secret, _ptr(out))
+    return out
+
+
+def cp_eval_air(air, f_eval, log_n, alpha_raw, a_first, a_last, log_blowup=3, threads=1):
+    f_eval = _u32(f_eval)
+    al = _u32(alpha_raw)
+    out = np.empty_like(f_eval)
+    rc = lib().orc_cp_eval_air(_air(air), _ptr(f_eval), log_n, log_blowup, _ptr(al), a_first, a_last, _ptr(out), threads)
+    assert rc == 0, rc
+    return out
+
+
+def prove_air(air, log_n, secret=3141592, route=ROUTE_FAST, threads=None):
+    """-> (transcript bytes, state bytes, ProveInfo)"""
+    threads = threads or default_threads()
+    cap = lib().orc_transcript_len(log_n)
+    buf = C.create_string_buffer(cap)
+    state = C.create_string_buffer(32)
+    n = C.c_size_t(0)
+    info = ProveInfo()
+    rc = lib().orc_prove_air(_air(air), log_n, secret, route, threads, buf, cap, C.byref(n), state, C.byref(info))
+    if rc != 0:
+        raise RuntimeError(f"orc_prove_air failed rc={rc}")
+    return buf.raw[: n.value], state.raw, info
+
+
+def verify_air(air, log_n, a_last, transcript: bytes, rederive=True, expect_state: bytes = None):
+    return lib().orc_verify_air(_air(air), log_n, a_last, transcript, len(transcript), int(rederive), expect_state)
 
 
 def prove_fibsq(log_n, secret=3141592, route=ROUTE_FAST, threads=None):

@@ -48,6 +48,23 @@ void orc_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t *a)
     if (n1 > 1) a[1] = secret % P;
     for (uint64_t i = 2; i < n1; i++) a[i] = addp(mulp(a[i - 2], a[i - 2]), mulp(a[i - 1], a[i - 1]));
 }
+/* the recurrence of an orc_air at (x0, x1) = (a[i], a[i+1]) */
+uint32_t orc_air_step(const orc_air *air, uint32_t x0, uint32_t x1)
+{
+    uint32_t r = mulp(air->c20 % P, mulp(x1, x1));
+    r = addp(r, mulp(air->c02 % P, mulp(x0, x0)));
+    r = addp(r, mulp(air->c11 % P, mulp(x0, x1)));
+    r = addp(r, mulp(air->c10 % P, x1));
+    r = addp(r, mulp(air->c01 % P, x0));
+    return addp(r, air->c00 % P);
+}
+void orc_trace_air(const orc_air *air, uint32_t log_n, uint32_t secret, uint32_t *a)
+{
+    uint64_t n1 = ((uint64_t)1 << log_n) - 1;
+    a[0] = air->a0 % P;
+    if (n1 > 1) a[1] = secret % P;
+    for (uint64_t i = 2; i < n1; i++) a[i] = orc_air_step(air, a[i - 2], a[i - 1]);
+}
 
 /* in-place radix-2 NTT, natural order in and out: x[k] <- sum_j x[j] w^(jk) */
 static void ntt(uint32_t *x, uint32_t log_n, uint32_t w, int threads)
@@ -135,6 +152,14 @@ int orc_cp_eval_fibsq(const uint32_t *f, uint32_t log_n, uint32_t log_blowup,
                       const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last,
                       uint32_t *cp, int threads)
 {
+    const orc_air fibsq = ORC_AIR_FIBSQ;
+    return orc_cp_eval_air(&fibsq, f, log_n, log_blowup, alpha_raw, a_first, a_last, cp, threads);
+}
+/* the same with the transition numerator f(g^2 x) - step(f(x), f(g x)) of an orc_air */
+int orc_cp_eval_air(const orc_air *air, const uint32_t *f, uint32_t log_n, uint32_t log_blowup,
+                    const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last,
+                    uint32_t *cp, int threads)
+{
     uint32_t log_N = log_n + log_blowup;
     if (log_N > 30 || log_n < 2) return -1;
     uint64_t n = (uint64_t)1 << log_n, N = (uint64_t)1 << log_N, B = (uint64_t)1 << log_blowup;
@@ -143,6 +168,7 @@ int orc_cp_eval_fibsq(const uint32_t *f, uint32_t log_n, uint32_t log_blowup,
     uint32_t g1 = powp(g, n - 1), g2 = powp(g, n - 2), g3 = powp(g, n - 3);
     uint32_t wn = powp(5, n), hn = powp(h, n);
     a_first %= P; a_last %= P;
+    const int fibsq = air->c20 == 1 && air->c02 == 1 && !air->c11 && !air->c10 && !air->c01 && !air->c00;
     enum { CH = 1024 };
     uint64_t nch = (N + CH - 1) / CH;
 #pragma omp parallel for schedule(static) NT(threads)
@@ -168,7 +194,8 @@ int orc_cp_eval_fibsq(const uint32_t *f, uint32_t log_n, uint32_t log_blowup,
             uint32_t xx = xs[k];
             uint32_t p0 = mulp(subp(fx, a_first), den[3 * k]);
             uint32_t p1 = mulp(subp(fx, a_last), den[3 * k + 1]);
-            uint32_t num = subp(subp(fggx, mulp(fgx, fgx)), mulp(fx, fx));
+            uint32_t num = fibsq ? subp(subp(fggx, mulp(fgx, fgx)), mulp(fx, fx))       /* prover.rs:134-138 */
+                                 : subp(fggx, orc_air_step(air, fx, fgx));
             uint32_t cub = mulp(mulp(subp(xx, g3), subp(xx, g2)), subp(xx, g1));
             uint32_t p2 = mulp(mulp(num, cub), den[3 * k + 2]);
             cp[i] = addp(addp(mulp(a0, p0), mulp(a1, p1)), mulp(a2, p2));

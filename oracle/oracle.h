@@ -81,6 +81,14 @@ int orc_poly_div(const uint32_t *lhs, uint32_t lhs_len, const uint32_t *rhs, uin
 void orc_fri_coeff(const uint32_t *c, uint32_t len, uint32_t beta, uint32_t *out, uint32_t p);
 
 /* ---- stage functions, fast route (what the CUDA kernels are compared with) */
+/* the program being proven as data -- a one-column AIR over a three-row window,
+ *   a[0] = a0, a[1] = secret, a[i+2] = c20 a[i+1]^2 + c02 a[i]^2 + c11 a[i] a[i+1] + c10 a[i+1] + c01 a[i] + c00,
+ * with the reference's two boundary constraints (first value, value n-2).  The reference's own program
+ * (prover.rs:32-39, :134-138) is ORC_AIR_FIBSQ; every *_fibsq function below is the *_air one at that point. */
+typedef struct { uint32_t a0, c20, c02, c11, c10, c01, c00; } orc_air;
+#define ORC_AIR_FIBSQ {1u, 1u, 1u, 0u, 0u, 0u, 0u}
+uint32_t orc_air_step(const orc_air *air, uint32_t x0, uint32_t x1);   /* the right-hand side at (a[i], a[i+1]) */
+void orc_trace_air(const orc_air *air, uint32_t log_n, uint32_t secret, uint32_t *out);
 /* prover.rs:32-39 generalised: a0=1, a1=secret, a_i=a_{i-2}^2+a_{i-1}^2; n-1 values */
 void orc_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t *out);
 /* polynomial.rs:337 for x_i = g^i: n_points = n-1 (phantom point) or n; n coeffs ascending */
@@ -93,6 +101,9 @@ int orc_lde_coset(const uint32_t *coeffs, uint32_t log_n, uint32_t log_blowup, u
 int orc_cp_eval_fibsq(const uint32_t *f_eval, uint32_t log_n, uint32_t log_blowup,
                       const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last,
                       uint32_t *cp_out, int threads);
+int orc_cp_eval_air(const orc_air *air, const uint32_t *f_eval, uint32_t log_n, uint32_t log_blowup,
+                    const uint32_t alpha_raw[3], uint32_t a_first, uint32_t a_last,
+                    uint32_t *cp_out, int threads);
 /* polynomial.rs:385 + prover.rs:204-211 in evaluation form; cur has len values on the
  * domain (5 h^i)^(2^layer_k), h of order domain_size0 = len << layer_k */
 int orc_fri_fold(const uint32_t *cur, uint64_t len, uint32_t layer_k, uint32_t beta_raw,
@@ -115,12 +126,17 @@ typedef struct {
 int orc_prove_fibsq(uint32_t log_n, uint32_t secret, int route, int threads,
                     uint8_t *transcript_out, size_t cap, size_t *len_out,
                     uint8_t state_out[32], orc_prove_info *info /* may be NULL */);
+int orc_prove_air(const orc_air *air, uint32_t log_n, uint32_t secret, int route, int threads,
+                  uint8_t *transcript_out, size_t cap, size_t *len_out,
+                  uint8_t state_out[32], orc_prove_info *info /* may be NULL */);
 size_t orc_transcript_len(uint32_t log_n);
 
 /* ---- proof.rs:15-149 generalised; rederive != 0 additionally re-derives alpha/beta/query
  * from the transcript through the channel (the reference reads them from the proof). */
 int orc_verify_fibsq(uint32_t log_n, uint32_t a_last, const uint8_t *transcript, size_t len,
                      int rederive, const uint8_t *expect_state /* may be NULL */);
+int orc_verify_air(const orc_air *air, uint32_t log_n, uint32_t a_last, const uint8_t *transcript, size_t len,
+                   int rederive, const uint8_t *expect_state /* may be NULL */);
 
 #ifdef __cplusplus
 }

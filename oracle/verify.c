@@ -33,6 +33,13 @@ static uint32_t be32(const uint8_t *s) { return ((uint32_t)s[0] << 24) | (s[1] <
 int orc_verify_fibsq(uint32_t k, uint32_t a_last, const uint8_t *tr, size_t len, int rederive,
                      const uint8_t *expect_state)
 {
+    const orc_air fibsq = ORC_AIR_FIBSQ;
+    return orc_verify_air(&fibsq, k, a_last, tr, len, rederive, expect_state);
+}
+/* the same for an orc_air: first boundary value air->a0, transition numerator f(g^2 x) - step(f(x), f(g x)) */
+int orc_verify_air(const orc_air *air, uint32_t k, uint32_t a_last, const uint8_t *tr, size_t len, int rederive,
+                   const uint8_t *expect_state)
+{
     if (k < 2 || k + LOG_BLOWUP > 30) return -1;
     if (len != orc_transcript_len(k)) return -2;
     const uint32_t n = 1u << k, N = n << LOG_BLOWUP, B = 1u << LOG_BLOWUP, L = k, pl0 = k + LOG_BLOWUP;
@@ -105,9 +112,9 @@ int orc_verify_fibsq(uint32_t k, uint32_t a_last, const uint8_t *tr, size_t len,
     {
         uint32_t f_x = fv[0] % P, f_gx = fv[1] % P, f_ggx = fv[2] % P;
         uint32_t g1 = orc_pow(gen_g, n - 1, P), g2 = orc_pow(gen_g, n - 2, P), g3 = orc_pow(gen_g, n - 3, P);
-        uint32_t p0 = orc_mul(orc_sub(f_x, 1, P), orc_inv(orc_sub(x, 1, P), P), P);
+        uint32_t p0 = orc_mul(orc_sub(f_x, air->a0 % P, P), orc_inv(orc_sub(x, 1, P), P), P);
         uint32_t p1 = orc_mul(orc_sub(f_x, a_last % P, P), orc_inv(orc_sub(x, g2, P), P), P);
-        uint32_t num = orc_sub(orc_sub(f_ggx, orc_mul(f_gx, f_gx, P), P), orc_mul(f_x, f_x, P), P);
+        uint32_t num = orc_sub(f_ggx, orc_air_step(air, f_x, f_gx), P);
         uint32_t cub = orc_mul(orc_mul(orc_sub(x, g3, P), orc_sub(x, g2, P), P), orc_sub(x, g1, P), P);
         uint32_t z = orc_sub(orc_pow(x, n, P), 1, P);
         uint32_t den = orc_mul(z, orc_inv(cub, P), P);

@@ -107,6 +107,20 @@ int main(int argc, char** argv)
             try { Proof::from_bytes(std::vector<uint8_t>(blob.begin(), blob.end() - 1)); } catch (const Error&) { threw = true; }
             if (!threw) { std::printf("FAIL: truncated proof accepted\n"); return 1; }
         }
+        // another program of the AIR family through the same entry point; its proof verifies under its own
+        // program and under no other
+        {
+            const zk_air fib{1, 0, 0, 0, 1, 1, 0, 0};                                     // a[i+2] = a[i+1] + a[i]
+            Proof p = generate_proof_air(Channel{}, fib, 12, 2u);
+            p.verify();
+            if (p.a_last != trace_air(fib, 12, 2u).back()) { std::printf("FAIL: air a_last\n"); return 1; }
+            bool rejected = false;
+            p.air = zk_air{1, 1, 1, 0, 0, 0, 0, 0};
+            try { p.verify(); } catch (const Error&) { rejected = true; }
+            if (!rejected) { std::printf("FAIL: a Fibonacci proof verified as FibonacciSq\n"); return 1; }
+            const Proof q = generate_proof(Channel{}, 10, 3141592u);                      // the context is back on FibonacciSq
+            q.verify();
+        }
         // lagrange() refuses abscissae that are not g^i: there is no CPU fallback to fall into
         bool threw = false;
         try { lagrange({{1u, 5u}, {7u, 9u}, {11u, 2u}}); } catch (const Error&) { threw = true; }

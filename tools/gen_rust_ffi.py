@@ -11,7 +11,7 @@ HEADER = os.path.join(ROOT, "include", "zkstark_b200.h")
 FFI = os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")
 
 BASE = {"uint32_t": "u32", "uint64_t": "u64", "uint8_t": "u8", "size_t": "usize", "int": "c_int", "float": "f32", "char": "c_char",
-        "void": "c_void", "zk_ctx": "zk_ctx", "zk_shard_comm": "zk_shard_comm"}
+        "void": "c_void", "zk_ctx": "zk_ctx", "zk_shard_comm": "zk_shard_comm", "zk_air": "zk_air"}
 
 
 def rust_type(ctype, is_array):

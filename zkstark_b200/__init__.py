@@ -20,6 +20,10 @@ from ._binding import (  # noqa: F401
     transcript_len,
     trace_fibsq,
     trace_fibsq_batch,
+    trace_air,
+    trace_air_batch,
+    verify_air,
+    AIR_FIBSQ,
     merkle_trace_host,
     proof_serialize,
     proof_deserialize,

@@ -74,6 +74,11 @@ def lib():
         "zk_transcript_len_ex": ([u32, u32], sz),
         "zk_prove_fibsq_ex": ([vp, u32, u32, vp, u32, vp, sz, C.POINTER(sz), vp], i32),
         "zk_verify_fibsq_ex": ([u32, u32, vp, sz, vp, vp, u32, i32, C.POINTER(i32)], i32),
+        "zk_ctx_set_air": ([vp, vp], i32),
+        "zk_ctx_get_air": ([vp, vp], i32),
+        "zk_trace_air": ([vp, u32, u32, vp], i32),
+        "zk_trace_air_batch": ([vp, u32, vp, u32, u32, vp], i32),
+        "zk_verify_air": ([vp, u32, u32, vp, sz, vp, vp, u32, i32, C.POINTER(i32)], i32),
         "zk_prove_stream_submit": ([vp, u32, u32, vp], i32),
         "zk_prove_stream_collect": ([vp, vp, vp], i32),
         "zk_sha256": ([vp, sz, vp], None),
@@ -162,6 +167,48 @@ def trace_fibsq_batch(log_n, secrets, threads=0):
     if rc:
         raise ZkError(rc, "zk_trace_fibsq_batch")
     return out
+
+
+# ---- the program as data (include/zkstark_b200.h zk_air)
+AIR_FIBSQ = (1, 1, 1, 0, 0, 0, 0)
+
+
+def _air(air, no_specialise=False):
+    """(a0, c20, c02, c11, c10, c01, c00) -> zk_air (None: null pointer = the reference's FibonacciSq)"""
+    if air is None:
+        return None
+    air = tuple(int(v) for v in air)
+    if len(air) != 7:
+        raise ValueError("an AIR is (a0, c20, c02, c11, c10, c01, c00)")
+    return (C.c_uint32 * 8)(*air, 1 if no_specialise else 0)
+
+
+def trace_air(air, log_n, secret=3141592):
+    """The trace of the program `air` (host): a[0] = a0, a[1] = secret, a[i+2] = step(a[i], a[i+1])."""
+    out = np.empty((1 << log_n) - 1, dtype=np.uint32)
+    rc = lib().zk_trace_air(_air(air), log_n, secret, _p(out))
+    if rc:
+        raise ZkError(rc, "zk_trace_air")
+    return out
+
+
+def trace_air_batch(air, log_n, secrets, threads=0, no_specialise=False):
+    secrets = _u32(secrets)
+    out = np.empty((len(secrets), (1 << log_n) - 1), dtype=np.uint32)
+    rc = lib().zk_trace_air_batch(_air(air, no_specialise), log_n, _p(secrets), len(secrets), threads, _p(out))
+    if rc:
+        raise ZkError(rc, "zk_trace_air_batch")
+    return out
+
+
+def verify_air(air, log_n, a_last, transcript, state=None, init_state=None, n_extra_queries=0, rederive=True):
+    """zk_verify_air: proof.rs:15-149 for a proof of the program `air`.  -> (ok, failed_check)"""
+    fc = C.c_int(0)
+    rc = lib().zk_verify_air(_air(air), log_n, a_last, transcript, len(transcript), state, init_state, n_extra_queries,
+                             int(rederive), C.byref(fc))
+    if rc not in (0, -6):
+        raise ZkError(rc, "zk_verify_air: invalid argument")
+    return rc == 0, fc.value
 
 
 def verify_fibsq(log_n, a_last, transcript, state=None, rederive=True):
@@ -548,6 +595,15 @@ class Context:
 
     def bench_set(self, sha_variant=-1, leaf_pass_k=0):
         self._ck(lib().zk_bench_set(self._h, sha_variant, leaf_pass_k))
+
+    def set_air(self, air, no_specialise=False):
+        """The program every prove entry point of this context proves (None: the reference's FibonacciSq)."""
+        self._ck(lib().zk_ctx_set_air(self._h, _air(air, no_specialise)))
+
+    def get_air(self):
+        out = (C.c_uint32 * 8)()
+        self._ck(lib().zk_ctx_get_air(self._h, out))
+        return tuple(out[:7]), int(out[7])
 
     def trim(self, tables_too=False):
         self._ck(lib().zk_ctx_trim(self._h, int(tables_too)))

@@ -121,9 +121,10 @@ FoldArgs make_fold_args(uint32_t layer_k)
     return f;
 }
 
-CpArgs make_cp_args(uint32_t log_n)
+CpArgs make_cp_args(const zk_ctx* ctx, uint32_t log_n)
 {
     CpArgs c{};
+    c.air = ctx->air_dev;
     const uint32_t log_N = log_n + LOG_BLOWUP;
     const uint64_t n = (uint64_t)1 << log_n;
     const uint32_t g = h_root(log_n), h = h_root(log_N);
@@ -278,7 +279,7 @@ int enqueue_prove(zk_ctx* ctx, cudaStream_t s, uint32_t log_n, uint32_t p0, uint
     a.heap = layer_heaps;
     a.heap_stride = 128 * N;
     a.post = POST_CP;
-    a.cp = make_cp_args(log_n);
+    a.cp = make_cp_args(ctx, log_n);
     a.cp.f = f_eval;
     a.cp.f_stride = N;
     a.cp.alpha_from_state = 1;
@@ -349,7 +350,7 @@ static int prove_subbatch_body(zk_ctx* ctx, uint32_t log_n, uint32_t nb, uint8_t
     uint8_t* trd = (uint8_t*)ctx->transcripts.p;
     const bool device_tail = nb >= 8;  // the sequential channel tail: one CTA per proof on the device, or the host
     // per-size constants are built on the ctx stream before the lanes fork
-    CpArgs cp0 = make_cp_args(log_n);
+    CpArgs cp0 = make_cp_args(ctx, log_n);
     CK(attach_cp_tab(ctx, T, cp0, &nl));
     const bool two_lanes = ctx->lanes && nb >= 4 && !ctx->stage_timing && ctx->lane_stream;
     if (!two_lanes) {
@@ -665,7 +666,7 @@ int zk_cp_eval_fibsq_dev(zk_ctx* ctx, const uint32_t* f_eval, uint32_t log_n, ui
     CK(cudaSetDevice(ctx->device));
     SizeTables* T;
     if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
-    CpArgs c = make_cp_args(log_n);
+    CpArgs c = make_cp_args(ctx, log_n);
     c.f = f_eval;
     c.f_stride = 0;
     for (int j = 0; j < 3; j++) c.alpha_raw[j] = alpha_raw[j];
@@ -832,7 +833,57 @@ int zk_trace_fibsq(uint32_t log_n, uint32_t secret, uint32_t* out)
 // spread over `threads` host threads (0: all hardware threads).  out: n_proofs rows of 2^log_n - 1 values.
 int zk_trace_fibsq_batch(uint32_t log_n, const uint32_t* secrets, uint32_t n_proofs, uint32_t threads, uint32_t* out)
 {
+    return zk_trace_air_batch(nullptr, log_n, secrets, n_proofs, threads, out);
+}
+
+// the public description of a program (include/zkstark_b200.h zk_air) -> host and device forms.  Null: the
+// reference's FibonacciSq.  Coefficients are reduced like every u32 that enters the field (field.rs:20-24).
+static void air_forms(const zk_air* a, HostAir& h, AirCoef& d)
+{
+    h = HostAir{};
+    d = AirCoef{};
+    if (!a) return;
+    h.a0 = a->a0 % P; h.c20 = a->c20 % P; h.c02 = a->c02 % P; h.c11 = a->c11 % P; h.c10 = a->c10 % P; h.c01 = a->c01 % P;
+    h.c00 = a->c00 % P;
+    const bool fibsq_shape = h.c20 == 1 && h.c02 == 1 && !h.c11 && !h.c10 && !h.c01 && !h.c00;
+    const bool keep_generic = (a->flags & ZK_AIR_NO_SPECIALISE) != 0;
+    h.generic = keep_generic || !(fibsq_shape && h.a0 == 1);        // the trace recurrence
+    d.generic = (keep_generic || !fibsq_shape) ? 1u : 0u;           // the transition constraint
+    d.c20m = h_to_mont(h.c20); d.c02m = h_to_mont(h.c02); d.c11m = h_to_mont(h.c11);
+    d.c10 = h.c10; d.c01 = h.c01;
+    d.c00r = from_mont(h.c00);
+}
+
+int zk_ctx_set_air(zk_ctx* ctx, const zk_air* air)
+{
+    if (!ctx) return ZK_ERR_INVALID;
+    if (air && (air->flags & ~ZK_AIR_NO_SPECIALISE)) return fail(ctx, ZK_ERR_INVALID, "unknown zk_air flag");
+    if (ctx->slot_count) return fail(ctx, ZK_ERR_INVALID, "a submitted batch is still uncollected");
+    air_forms(air, ctx->air, ctx->air_dev);
+    ctx->air_public = air ? *air : zk_air{1, 1, 1, 0, 0, 0, 0, 0};
+    return ZK_OK;
+}
+
+int zk_ctx_get_air(const zk_ctx* ctx, zk_air* out)
+{
+    if (!ctx || !out) return ZK_ERR_INVALID;
+    *out = ctx->air_public;
+    return ZK_OK;
+}
+
+int zk_trace_air(const zk_air* air, uint32_t log_n, uint32_t secret, uint32_t* out)
+{
+    return zk_trace_air_batch(air, log_n, &secret, 1, 1, out);
+}
+
+int zk_trace_air_batch(const zk_air* air_in, uint32_t log_n, const uint32_t* secrets, uint32_t n_proofs, uint32_t threads,
+                       uint32_t* out)
+{
     if (!secrets || !out || n_proofs == 0 || log_n < 1 || log_n > 30) return ZK_ERR_INVALID;
+    if (air_in && (air_in->flags & ~ZK_AIR_NO_SPECIALISE)) return ZK_ERR_INVALID;
+    HostAir air;
+    AirCoef unused;
+    air_forms(air_in, air, unused);
     const size_t n1 = ((size_t)1 << log_n) - 1;
     uint32_t T = threads ? threads : std::thread::hardware_concurrency();
     if (T < 1) T = 1;
@@ -844,7 +895,7 @@ int zk_trace_fibsq_batch(uint32_t log_n, const uint32_t* secrets, uint32_t n_pro
             const uint32_t b0 = gsz * gi, cnt = n_proofs - b0 < gsz ? n_proofs - b0 : gsz;
             uint32_t* rows[8];
             for (uint32_t j = 0; j < cnt; j++) rows[j] = out + n1 * (b0 + j);
-            host_traces(log_n, secrets + b0, rows, cnt);
+            host_traces(air, log_n, secrets + b0, rows, cnt);
         }
     };
     std::vector<std::thread> th;
@@ -954,7 +1005,7 @@ static void stream_worker(zk_ctx* ctx, zk_ctx::StreamSlot* sl)
             const uint32_t b0 = gsz * gi, cnt = sl->n - b0 < gsz ? sl->n - b0 : gsz;
             uint32_t* rows[8];
             for (uint32_t j = 0; j < cnt; j++) rows[j] = (uint32_t*)sl->pinned + n * (b0 + j);
-            host_traces(sl->log_n, sl->host_secrets.data() + b0, rows, cnt);
+            host_traces(ctx->air, sl->log_n, sl->host_secrets.data() + b0, rows, cnt);
             for (uint32_t j = 0; j < cnt; j++) {
                 cudaError_t e = cudaMemcpyAsync((uint32_t*)sl->traces.p + n * (b0 + j), rows[j], 4 * (n - 1), cudaMemcpyHostToDevice,
                                                 ctx->trace_stream);
@@ -992,7 +1043,7 @@ int zk_prove_stream_submit(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const
     sl.log_n = log_n;
     sl.n = n_proofs;
     sl.err = cudaSuccess;
-    if (ctx->trace_on_device) {
+    if (ctx->trace_on_device && !ctx->air.generic) {   // the device generator knows the reference's recurrence only
         CK(sl.secrets.ensure(4 * (size_t)n_proofs));
         CK(cudaMemcpyAsync(sl.secrets.p, sl.host_secrets.data(), 4 * (size_t)n_proofs, cudaMemcpyHostToDevice, ctx->trace_stream));
         CK(launch_trace_batch(ctx->trace_stream, (const uint32_t*)sl.secrets.p, (uint32_t*)sl.traces.p, n, log_n, n_proofs));
@@ -1045,8 +1096,13 @@ int zk_prove_fibsq(zk_ctx* ctx, uint32_t log_n, uint32_t secret, uint8_t* transc
     int rc = check_log_n(ctx, log_n);
     if (rc) return rc;
     std::vector<uint32_t> a(((size_t)1 << log_n) - 1);
-    zk_trace_fibsq(log_n, secret, a.data());
-    if (log_n == 10 && secret == 3141592u && a[1022] != 2338775057u)  // prover.rs:42
+    if (ctx->air.generic) {
+        uint32_t* row = a.data();
+        host_traces(ctx->air, log_n, &secret, &row, 1);
+    } else {
+        zk_trace_fibsq(log_n, secret, a.data());
+    }
+    if (!ctx->air.generic && log_n == 10 && secret == 3141592u && a[1022] != 2338775057u)  // prover.rs:42
         return fail(ctx, ZK_ERR_ASSERT, "a[1022] != 2338775057 (prover.rs:42)");
     return zk_prove_fibsq_from_trace(ctx, log_n, a.data(), transcript_out, cap, len_out, state_out);
 }
@@ -1211,7 +1267,7 @@ int zk_shard_cp_dev(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* halo, 
     CK(cudaSetDevice(ctx->device));
     SizeTables* T;
     if ((rc = get_tables(ctx, log_n + LOG_BLOWUP, &T))) return rc;
-    CpArgs c = make_cp_args(log_n);
+    CpArgs c = make_cp_args(ctx, log_n);
     c.f = f_local;
     c.halo = halo;
     c.log_len = ilog2_u64(local_len);
@@ -1273,7 +1329,7 @@ int zkh::shard_cp_blocks(zk_ctx* ctx, const uint32_t* f_local, const uint32_t* h
     a.counters = (uint32_t*)ctx->counters.p;
     a.state = (ProofState*)const_cast<void*>(state_dev);
     a.pow = T->h.tab;
-    a.cp = make_cp_args(log_n);
+    a.cp = make_cp_args(ctx, log_n);
     a.cp.f = f_local;
     a.cp.halo = halo;
     if (halo_roll) {
@@ -1517,7 +1573,7 @@ int zk_bench_kernel(zk_ctx* ctx, int which, uint32_t log_size, uint32_t iters, i
             if ((rc = get_tables(ctx, log_size + LOG_BLOWUP, &T))) return rc;
             CK(ctx->s0.ensure(4 * N8)); CK(ctx->s1.ensure(4 * N8));
             CK(bench_fill(s, (uint32_t*)ctx->s0.p, N8, 5));
-            ca = make_cp_args(log_size); ca.f = (const uint32_t*)ctx->s0.p;
+            ca = make_cp_args(ctx, log_size); ca.f = (const uint32_t*)ctx->s0.p;
             ca.alpha_raw[0] = 361545003u; ca.alpha_raw[1] = 3235878091u; ca.alpha_raw[2] = 2708123352u;
             ca.a_first = 1; ca.a_last = 2338775057u;
             CK(attach_cp_tab(ctx, T, ca, nullptr));

@@ -135,6 +135,16 @@ struct FoldArgs {           // polynomial.rs:385-400 + prover.rs:204-211 in eval
     uint32_t beta_raw;
     ShardMap shard;         // local -> global index (domain point) when the layer is sharded
 };
+// The transition constraint of the program being proven (hostair.hpp): the numerator is
+//   f(g^2 x) - [c20 f(gx)^2 + c02 f(x)^2 + c11 f(x) f(gx) + c10 f(gx) + c01 f(x) + c00].
+// generic == 0: the reference's FibonacciSq (prover.rs:134-138), the specialised expression; the fields are unused.
+struct AirCoef {
+    uint32_t generic;
+    uint32_t c20m, c02m, c11m;   // c R (Montgomery form): mont_mul(mont_mul(u, v), cm) = c u v / R
+    uint32_t c10, c01;           // canonical:             mont_mul(u, c)               = c u / R
+    uint32_t c00r;               // c00 / R
+};
+
 struct CpArgs {             // prover.rs:101-173 pointwise
     const uint32_t* f;      // f_eval, N values (batch stride f_stride)
     uint64_t f_stride;
@@ -153,6 +163,7 @@ struct CpArgs {             // prover.rs:101-173 pointwise
     // domain only, like twiddles): tab[i] = 1/(x_i - 1) R, tab[N + i] = 1/(x_i - g^(n-2)) R,
     // tab[2N + i] = (x_i - g^(n-3))(x_i - g^(n-2))(x_i - g^(n-1)) / (x_i^n - 1) R^2, x_i = 5 h^i.  Null: computed on the fly.
     const uint32_t* tab;
+    AirCoef air;               // the transition constraint (zk_ctx_set_air); zero = the reference's program
 };
 
 // Launch-shape knobs of the tree kernels.  One copy per context (zk_ctx::tune; zk_bench_set* edit it), so contexts of

@@ -10,6 +10,7 @@
 
 #include "../../include/zkstark_b200.h"
 #include "common.cuh"
+#include "hostair.hpp"
 
 // launchers of ntt.cu / trace.cu / benchsupport.cu (tree.cu's are in common.cuh)
 namespace zk {
@@ -29,7 +30,7 @@ cudaError_t launch_trace_batch(cudaStream_t s, const uint32_t* secrets_dev, uint
 cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
 double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
-void host_traces(uint32_t log_n, const uint32_t* secrets, uint32_t* const* rows, uint32_t count);
+void host_traces(const HostAir& air, uint32_t log_n, const uint32_t* secrets, uint32_t* const* rows, uint32_t count);
 int ntt_pass_times(float ms[4]);
 size_t ntt_table_words();
 cudaError_t ntt2_build_tables(cudaStream_t s, uint32_t* tw_fwd, uint32_t* tw_inv);
@@ -135,6 +136,9 @@ struct zk_ctx {
     StreamSlot slot[2];
     uint32_t slot_head = 0, slot_count = 0;
     cudaStream_t trace_stream = nullptr;
+    zk::HostAir air;                       // the program being proven (zk_ctx_set_air; default: the reference's FibonacciSq)
+    zk::AirCoef air_dev{};                 //   its transition constraint as the CP kernels take it
+    zk_air air_public{1, 1, 1, 0, 0, 0, 0, 0};
     bool trace_on_device = false;          // ZK_TRACE_DEVICE=1
     uint32_t host_threads = 0;             // ZK_HOST_THREADS (0: all hardware threads)
 };
@@ -156,7 +160,7 @@ int get_tables(zk_ctx* ctx, uint32_t log_N, SizeTables** out);
 bool is_pow2(uint64_t v);
 uint32_t ilog2_u64(uint64_t v);
 zk::FoldArgs make_fold_args(uint32_t layer_k);
-zk::CpArgs make_cp_args(uint32_t log_n);
+zk::CpArgs make_cp_args(const zk_ctx* ctx, uint32_t log_n);
 cudaError_t attach_cp_tab(zk_ctx* ctx, SizeTables* T, zk::CpArgs& c, int* nl);
 void finish_channel_host(uint32_t log_n, const zk::ProofState& ps, const uint8_t* tr, uint8_t state_out[32]);
 int check_log_n(zk_ctx* ctx, uint32_t log_n);

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "field.cuh"
+#include "hostair.hpp"
 
 namespace zk {
 
@@ -91,6 +92,54 @@ __attribute__((target("avx2"))) static void traces_avx2(uint32_t log_n, const ui
     }
 }
 #undef step
+
+// Other programs of the AIR family (ctx.hpp HostAir): a[i] = c20 a[i-1]^2 + c02 a[i-2]^2 + c11 a[i-2] a[i-1] + c10 a[i-1]
+// + c01 a[i-2] + c00, four traces per vector, NV vectors interleaved.  Seven multiplications per step instead of one.
+__attribute__((target("avx2"), always_inline)) static inline __m256i addmod4(__m256i a, __m256i b, __m256i p, __m256i one)
+{
+    __m256i z = _mm256_add_epi64(a, b);
+    const __m256i ge = _mm256_cmpgt_epi64(z, _mm256_sub_epi64(p, one));
+    return _mm256_sub_epi64(z, _mm256_and_si256(ge, p));
+}
+template <int NV>
+__attribute__((target("avx2"))) static void traces_air_avx2(const HostAir& air, uint32_t log_n, const uint32_t* secrets, uint32_t* const* rows)
+{
+    constexpr int NT = 4 * NV;
+    const uint64_t n1 = ((uint64_t)1 << log_n) - 1;
+    const __m256i p = _mm256_set1_epi64x(P), pinv = _mm256_set1_epi64x(P_INV), lo32 = _mm256_set1_epi64x(0xffffffffll);
+    const __m256i one = _mm256_set1_epi64x(1);
+    const __m256i c20 = _mm256_set1_epi64x(to_mont(air.c20)), c02 = _mm256_set1_epi64x(to_mont(air.c02)),
+                  c11 = _mm256_set1_epi64x(to_mont(air.c11)), c10 = _mm256_set1_epi64x(to_mont(air.c10)),
+                  c01 = _mm256_set1_epi64x(to_mont(air.c01)), c00 = _mm256_set1_epi64x(to_mont(air.c00));
+    alignas(32) uint64_t tmp[NT];
+    __m256i x0[NV], x1[NV], q0[NV];   // a[i-2], a[i-1], a[i-2]^2 (Montgomery form)
+    for (int h = 0; h < NV; h++) {
+        alignas(32) uint64_t ym[4];
+        for (int j = 0; j < 4; j++) ym[j] = to_mont(secrets[4 * h + j] % P);
+        x1[h] = _mm256_load_si256((const __m256i*)ym);
+        x0[h] = _mm256_set1_epi64x(to_mont(air.a0));
+        q0[h] = mont_mul4(x0[h], x0[h], pinv, p, lo32);
+    }
+    for (int j = 0; j < NT; j++) {
+        rows[j][0] = air.a0;
+        if (n1 > 1) rows[j][1] = secrets[j] % P;
+    }
+    for (uint64_t i = 2; i < n1; i++) {
+        for (int h = 0; h < NV; h++) {
+            const __m256i q1 = mont_mul4(x1[h], x1[h], pinv, p, lo32);
+            const __m256i xy = mont_mul4(x0[h], x1[h], pinv, p, lo32);
+            __m256i z = addmod4(mont_mul4(q1, c20, pinv, p, lo32), mont_mul4(q0[h], c02, pinv, p, lo32), p, one);
+            z = addmod4(z, mont_mul4(xy, c11, pinv, p, lo32), p, one);
+            z = addmod4(z, addmod4(mont_mul4(x1[h], c10, pinv, p, lo32), mont_mul4(x0[h], c01, pinv, p, lo32), p, one), p, one);
+            z = addmod4(z, c00, p, one);
+            x0[h] = x1[h];
+            q0[h] = q1;
+            x1[h] = z;
+            _mm256_store_si256((__m256i*)(tmp + 4 * h), mont_mul4(z, one, pinv, p, lo32));
+        }
+        for (int j = 0; j < NT; j++) rows[j][i] = (uint32_t)tmp[j];
+    }
+}
 }  // namespace
 #endif
 
@@ -111,10 +160,39 @@ static void trace1(uint32_t log_n, uint32_t secret, uint32_t* out)
     }
 }
 
+static void trace1_air(const HostAir& air, uint32_t log_n, uint32_t secret, uint32_t* out)
+{
+    const uint64_t n1 = ((uint64_t)1 << log_n) - 1;
+    const uint32_t c20 = to_mont(air.c20), c02 = to_mont(air.c02), c11 = to_mont(air.c11), c10 = to_mont(air.c10),
+                   c01 = to_mont(air.c01), c00 = to_mont(air.c00);
+    uint32_t x0 = to_mont(air.a0), x1 = to_mont(secret % P);
+    out[0] = air.a0;
+    if (n1 > 1) out[1] = secret % P;
+    for (uint64_t i = 2; i < n1; i++) {
+        uint32_t z = fadd(mont_mul(mont_mul(x1, x1), c20), mont_mul(mont_mul(x0, x0), c02));
+        z = fadd(z, mont_mul(mont_mul(x0, x1), c11));
+        z = fadd(z, fadd(mont_mul(x1, c10), mont_mul(x0, c01)));
+        z = fadd(z, c00);
+        out[i] = from_mont(z);
+        x0 = x1;
+        x1 = z;
+    }
+}
+
 // traces of `count` proofs: rows[j] receives the 2^log_n - 1 values of secrets[j].  count = 8 or 4 take the SIMD paths.
-void host_traces(uint32_t log_n, const uint32_t* secrets, uint32_t* const* rows, uint32_t count)
+void host_traces(const HostAir& air, uint32_t log_n, const uint32_t* secrets, uint32_t* const* rows, uint32_t count)
 {
     uint32_t j = 0;
+    if (air.generic) {
+#if defined(__x86_64__)
+        if (__builtin_cpu_supports("avx2")) {
+            for (; j + 8 <= count; j += 8) traces_air_avx2<2>(air, log_n, secrets + j, rows + j);
+            for (; j + 4 <= count; j += 4) traces_air_avx2<1>(air, log_n, secrets + j, rows + j);
+        }
+#endif
+        for (; j < count; j++) trace1_air(air, log_n, secrets[j], rows[j]);
+        return;
+    }
 #if defined(__x86_64__)
     if (__builtin_cpu_supports("avx2")) {
         for (; j + 8 <= count; j += 8) traces_avx2<2>(log_n, secrets + j, rows + j);

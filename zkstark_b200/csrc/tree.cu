@@ -128,6 +128,17 @@ __device__ __forceinline__ uint32_t mont_inv_chain(uint32_t x)   // x^(p-2); p -
     return r;
 }
 
+// transition numerator over R at one point: (f(g^2 x) - step(f(x), f(g x))) / R, values canonical (see AirCoef)
+__device__ __forceinline__ uint32_t air_num(const AirCoef& A, uint32_t fx, uint32_t fg, uint32_t fgg)
+{
+    if (!A.generic) return fsub(fsub(mont_mul(fgg, 1u), mont_mul(fg, fg)), mont_mul(fx, fx));   // prover.rs:134-138
+    uint32_t r = fadd(mont_mul(mont_mul(fg, fg), A.c20m), mont_mul(mont_mul(fx, fx), A.c02m));
+    r = fadd(r, mont_mul(mont_mul(fx, fg), A.c11m));
+    r = fadd(r, fadd(mont_mul(fg, A.c10), mont_mul(fx, A.c01)));
+    r = fadd(r, A.c00r);
+    return fsub(mont_mul(fgg, 1u), r);
+}
+
 struct CpCoef {
     uint32_t a0, a1;       // alpha_0, alpha_1 reduced (field.rs:20-24), e = 0
     uint32_t z[8];         // alpha_2 / (x^n - 1) for i mod 8, e = 5
@@ -185,7 +196,7 @@ __device__ __forceinline__ void cp_chunk(const CpArgs& c, const PowTab& pw, cons
         const uint32_t s = fadd(mont_mul(mont_mul(fsub(fx, k.a_first), d1), k.a0),
                                 mont_mul(mont_mul(fsub(fx, k.a_last), d0), k.a1));
         const uint32_t p01 = mont_mul(s, inv_d);
-        const uint32_t num = fsub(fsub(mont_mul(fggx, 1u), mont_mul(fgx, fgx)), mont_mul(fx, fx));
+        const uint32_t num = air_num(c.air, fx, fgx, fggx);
         const uint32_t cub = mont_mul(mont_mul(fsub(xs[j], c.g3), d1), fsub(xs[j], c.g1));
         const uint32_t p2 = mont_mul(mont_mul(num, cub), k.z[shard_global(c.shard, i) & 7]);
         out[i] = fadd(p01, p2);
@@ -259,7 +270,7 @@ __device__ __forceinline__ void cp_chunk_tab(const CpArgs& c, const uint32_t* f,
     for (int j = 0; j < C; j++) {
         const uint32_t p0 = mont_mul(mont_mul(fsub(fx[j], k.a_first), ta[j]), k.a0m);
         const uint32_t p1 = mont_mul(mont_mul(fsub(fx[j], k.a_last), tb[j]), k.a1m);
-        const uint32_t num = fsub(fsub(mont_mul(fgg[j], 1u), mont_mul(fg[j], fg[j])), mont_mul(fx[j], fx[j]));   // / R
+        const uint32_t num = air_num(c.air, fx[j], fg[j], fgg[j]);   // / R
         const uint32_t p2 = mont_mul(mont_mul(num, tc[j]), k.a2m);
         o[j] = fadd(fadd(p0, p1), p2);
     }

@@ -9,6 +9,7 @@
 
 #include "../../include/zkstark_b200.h"
 #include "field.cuh"
+#include "hostair.hpp"
 
 namespace zk {
 namespace sha {
@@ -90,6 +91,7 @@ struct ProofHead {
     uint32_t alpha[3], beta[33];
     const uint8_t* roots[33];
     uint32_t free_term, a_last;
+    zk::HostAir air;    // the program (default: the reference's FibonacciSq)
 };
 int check_query(const ProofHead& H, Reader& rd, Replay& ch, const uint8_t* transcript, uint32_t q_raw)
 {
@@ -128,9 +130,14 @@ int check_query(const ProofHead& H, Reader& rd, Replay& ch, const uint8_t* trans
     {
         const uint32_t f_x = fv[0] % P, f_gx = fv[1] % P, f_ggx = fv[2] % P;
         const uint32_t g1 = h_pow(g, n - 1), g2 = h_pow(g, n - 2), g3 = h_pow(g, n - 3);
-        const uint32_t p0 = f_div(f_sub(f_x, 1), f_sub(x, 1));
+        const uint32_t p0 = f_div(f_sub(f_x, H.air.a0), f_sub(x, 1));     // proof.rs:66: the first trace value (1 upstream)
         const uint32_t p1 = f_div(f_sub(f_x, H.a_last % P), f_sub(x, g2));
-        const uint32_t num = f_sub(f_sub(f_ggx, h_mul(f_gx, f_gx)), h_mul(f_x, f_x));
+        // proof.rs:70: f(g^2 x) - f(g x)^2 - f(x)^2 upstream; in general f(g^2 x) - step(f(x), f(g x)) of the program
+        uint32_t step = f_add(h_mul(H.air.c20, h_mul(f_gx, f_gx)), h_mul(H.air.c02, h_mul(f_x, f_x)));
+        step = f_add(step, h_mul(H.air.c11, h_mul(f_x, f_gx)));
+        step = f_add(step, f_add(h_mul(H.air.c10, f_gx), h_mul(H.air.c01, f_x)));
+        step = f_add(step, H.air.c00);
+        const uint32_t num = f_sub(f_ggx, step);
         const uint32_t den = f_div(f_sub(h_pow(x, n), 1), h_mul(h_mul(f_sub(x, g3), f_sub(x, g2)), f_sub(x, g1)));
         const uint32_t p2 = f_div(num, den);
         const uint32_t cp0 = f_add(f_add(h_mul(H.alpha[0] % P, p0), h_mul(H.alpha[1] % P, p1)), h_mul(H.alpha[2] % P, p2));
@@ -175,6 +182,15 @@ extern "C" size_t zk_transcript_len_ex(uint32_t log_n, uint32_t n_extra_queries)
 extern "C" int zk_verify_fibsq_ex(uint32_t log_n, uint32_t a_last, const uint8_t* transcript, size_t len, const uint8_t* state,
                                   const uint8_t* init_state, uint32_t n_extra_queries, int rederive, int* failed_check)
 {
+    return zk_verify_air(nullptr, log_n, a_last, transcript, len, state, init_state, n_extra_queries, rederive, failed_check);
+}
+
+// The same for a proof of another program of the zk_air family (air null: the reference's FibonacciSq): the
+// first boundary value is air->a0 and the transition numerator is f(g^2 x) - step(f(x), f(g x)).
+extern "C" int zk_verify_air(const zk_air* air, uint32_t log_n, uint32_t a_last, const uint8_t* transcript, size_t len,
+                             const uint8_t* state, const uint8_t* init_state, uint32_t n_extra_queries, int rederive,
+                             int* failed_check)
+{
     int dummy = 0;
     if (!failed_check) failed_check = &dummy;
     *failed_check = 0;
@@ -184,6 +200,11 @@ extern "C" int zk_verify_fibsq_ex(uint32_t log_n, uint32_t a_last, const uint8_t
     H.k = log_n; H.L = log_n; H.log_N = log_n + ZK_LOG_BLOWUP;
     H.n = (uint64_t)1 << log_n; H.N = H.n << ZK_LOG_BLOWUP; H.B = (uint64_t)1 << ZK_LOG_BLOWUP;
     H.a_last = a_last;
+    if (air) {
+        if (air->flags & ~ZK_AIR_NO_SPECIALISE) return ZK_ERR_INVALID;
+        H.air.a0 = air->a0 % P; H.air.c20 = air->c20 % P; H.air.c02 = air->c02 % P; H.air.c11 = air->c11 % P;
+        H.air.c10 = air->c10 % P; H.air.c01 = air->c01 % P; H.air.c00 = air->c00 % P;
+    }
     const uint32_t L = H.L;
     Reader rd{transcript, len};
     Replay ch(rederive != 0);
