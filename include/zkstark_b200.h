@@ -273,7 +273,8 @@ int zk_shard_decommit_dev(zk_ctx *ctx, uint32_t log_n, uint32_t n_ranks, uint32_
  * all-to-all on all ranks).
  * zk_shard_comm_init_local runs G VIRTUAL ranks on the context's own device (collectives become device copies): the
  * same driver and kernels on one GPU, used by the single-GPU test tier.  n_ranks: 1, 2, 4 or 8 (the LDE has 8 cosets).
- * A comm borrows its ctx: destroy the comm first.  Generalises generate_proof (prover.rs:9) like zk_prove_fibsq. */
+ * A comm borrows its ctx: destroy the comm first.  With real ranks zk_shard_comm_destroy is collective as well (like
+ * ncclCommDestroy): buffers a peer has mapped are freed only after every rank has closed its mappings.  Generalises generate_proof (prover.rs:9) like zk_prove_fibsq. */
 #define ZK_SHARD_ID_BYTES 128
 typedef struct zk_shard_comm zk_shard_comm;
 int zk_shard_unique_id(uint8_t id_out[ZK_SHARD_ID_BYTES]);

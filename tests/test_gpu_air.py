@@ -115,6 +115,36 @@ def test_sharded_driver(air_ctx, orc, G, lb):
     assert tr == want_tr and st == want_st
 
 
+def test_seeded_channel_and_further_queries(air_ctx, orc):
+    """zk_prove_fibsq_ex under another program: the reference-shaped transcript is a prefix, the whole verifies under the
+    program (seed, 5 further channel-drawn test points) and under no other"""
+    ctx = air_ctx
+    air = AIRS[2]
+    ctx.set_air(air)
+    log_n = 10
+    seed = hashlib.sha256(b"air seed").digest()
+    base_tr, base_st = ctx.prove_fibsq(log_n, 55)
+    tr, st = ctx.prove_fibsq_ex(log_n, 55, None, 5)
+    assert tr[: len(base_tr)] == base_tr
+    a_last = int(zk.trace_air(air, log_n, 55)[-1])
+    assert zk.verify_air(air, log_n, a_last, tr, st, None, 5) == (True, 0)
+    tr, st = ctx.prove_fibsq_ex(log_n, 55, seed, 3)
+    assert zk.verify_air(air, log_n, a_last, tr, st, seed, 3) == (True, 0)
+    assert not zk.verify_air(air, log_n, a_last, tr, st, None, 3)[0]
+    assert not zk.verify_air(AIRS[0], log_n, a_last, tr, st, seed, 3)[0]
+
+
+def test_full_size_program(air_ctx, orc):
+    """BASELINE configs[2] size (2^20 trace, 2^23-point LDE) under an every-term program, against the oracle"""
+    ctx = air_ctx
+    air = AIRS[1]
+    ctx.set_air(air)
+    want_tr, want_st, info = orc.prove_air(air, 20, secret=3141592)
+    tr, st = ctx.prove_fibsq(20, 3141592)
+    assert hashlib.sha256(tr).hexdigest() == hashlib.sha256(want_tr).hexdigest() and st == want_st
+    assert zk.verify_air(air, 20, info.a_last, tr, st) == (True, 0)
+
+
 def test_bad_air(ctx):
     import ctypes as C
     bad = (C.c_uint32 * 8)(1, 1, 1, 0, 0, 0, 0, 2)           # unknown flag

@@ -103,20 +103,31 @@ def test_native_rejects_bad_arguments(ctx):
         comm.close()
 
 
-def test_native_nccl_two_processes(tmp_path):
-    """Real ranks: 2 processes, 2 GPUs, NCCL all-to-all / all-gathers / ring / all-reduce inside the library."""
+@pytest.mark.parametrize("no_p2p", [False, True])
+def test_native_nccl_two_processes(tmp_path, orc, no_p2p):
+    """Real ranks: 2 processes, 2 GPUs; exchanges through peer memory (flag barriers) or, with ZK_SHARD_NO_P2P, NCCL
+    all-to-all / all-gathers / ring / all-reduce.  The communicator first proves smaller sizes of another program (SURVEY
+    8(f4)) in growing order -- the peer buffers are re-allocated and re-mapped between them -- then 2^18 of the reference's."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     log_n = 18
+    air = (7, 3, 5, 11, 13, 17, 19)
     idfile = str(tmp_path / "nccl_id")
     worker = os.path.join(ROOT, "tools", "shard_nccl_worker.py")
+    extra = ["--no-p2p"] if no_p2p else []
     procs = [subprocess.Popen([sys.executable, worker, "--rank", str(r), "--world", "2", "--log-n", str(log_n), "--id-file", idfile,
-                               "--out", str(tmp_path / f"out{r}.json")]) for r in range(2)]
+                               "--out", str(tmp_path / f"out{r}.json"), "--more", "12,16,14", "--air", ",".join(map(str, air))] + extra)
+             for r in range(2)]
     for p in procs:
         assert p.wait(timeout=600) == 0
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "large_digests.json")))
+    want_more = {k: orc.prove_air(air, k, secret=3141592) for k in (12, 16, 14)}
     for r in range(2):
         o = json.load(open(tmp_path / f"out{r}.json"))
         assert o["transcript_sha256"] == gold[str(log_n)]["sha256"]
         assert o["state"] == gold[str(log_n)]["state"]
+        assert [m["log_n"] for m in o["more"]] == [12, 16, 14]
+        for m in o["more"]:
+            w = want_more[m["log_n"]]
+            assert m["transcript_sha256"] == hashlib.sha256(w[0]).hexdigest() and m["state"] == w[1].hex()

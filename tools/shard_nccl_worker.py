@@ -22,7 +22,13 @@ def main():
     ap.add_argument("--id-file", required=True)
     ap.add_argument("--out", required=True)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--more", default="", help="further sizes proven on the same communicator before --log-n, e.g. 14,16 "
+                    "(growing sizes re-allocate and re-map the peer buffers)")
+    ap.add_argument("--air", default="", help="a0,c20,c02,c11,c10,c01,c00: another program for the --more proofs")
+    ap.add_argument("--no-p2p", action="store_true", help="NCCL collectives only (ZK_SHARD_NO_P2P=1)")
     a = ap.parse_args()
+    if a.no_p2p:
+        os.environ["ZK_SHARD_NO_P2P"] = "1"
     import zkstark_b200 as zk
     ctx = zk.Context(a.rank)
     if a.rank == 0:
@@ -39,11 +45,19 @@ def main():
             time.sleep(0.05)
         uid = open(a.id_file, "rb").read()
     comm = zk.ShardComm(ctx, a.world, a.rank, uid)
+    more = []
+    air = tuple(int(v) for v in a.air.split(",")) if a.air else None
+    for k in [int(v) for v in a.more.split(",") if v]:
+        ctx.set_air(air)
+        t = zk.trace_air(air, k, 3141592) if air else zk.trace_fibsq(k, 3141592)
+        tr, st = comm.prove(k, t)
+        more.append({"log_n": k, "transcript_sha256": hashlib.sha256(tr).hexdigest(), "state": st.hex()})
+    ctx.set_air(None)
     trace = zk.trace_fibsq(a.log_n, 3141592)
     for _ in range(a.reps):
         tr, st = comm.prove(a.log_n, trace)
     out = {"rank": a.rank, "transcript_sha256": hashlib.sha256(tr).hexdigest(), "state": st.hex(),
-           "phase_ms": comm.last_phase_ms(), "comm_bytes": comm.last_comm_bytes(), "first_tail": comm.last_first_tail()}
+           "phase_ms": comm.last_phase_ms(), "comm_bytes": comm.last_comm_bytes(), "first_tail": comm.last_first_tail(), "more": more}
     with open(a.out, "w") as f:
         json.dump(out, f)
     comm.close()

@@ -214,6 +214,7 @@ struct zk_shard_comm {
     DevBuf flags;                            // [0, 8) barrier flags written by the peers; word 16: time-out flag; word 32: scratch
     DevBuf xchg;                             // staging of the handle exchange
     uint32_t epoch = 0;
+    bool broken = false;                     // a collective failed or a peer timed out: no further rendezvous is attempted
 };
 
 namespace {
@@ -221,6 +222,7 @@ namespace {
 int fail_nccl(zk_shard_comm* cm, ncclResult_t r, const char* what)
 {
     NcclApi* A = nccl_api();
+    cm->broken = true;
     return fail(cm->ctx, ZK_ERR_COMM, std::string(what) + ": " + (A && A->GetErrorString ? A->GetErrorString(r) : "NCCL error"));
 }
 #define NK(call)                                                   \
@@ -350,6 +352,22 @@ void close_peers(zk_shard_comm* cm)
     cm->p2p = false;
 }
 
+// Exported memory must not be freed while a peer still has it mapped (cudaIpcOpenMemHandle: undefined behaviour).  Before
+// a mapped buffer is re-allocated or released every rank therefore closes its mappings and all ranks meet (a one-byte
+// all-reduce + stream synchronisation): only then may anybody free.  Collective; skipped on a communicator that has
+// already seen a failure (its peers may be gone, and waiting for them would hang).
+int quiesce_peers(zk_shard_comm* cm)
+{
+    if (cm->local || cm->G == 1 || !cm->p2p) return ZK_OK;
+    zk_ctx* ctx = cm->ctx;
+    CK(cudaStreamSynchronize(ctx->stream));
+    close_peers(cm);
+    if (cm->broken || !cm->nccl || !cm->xchg.p) return ZK_OK;
+    NK(nccl_api()->AllReduce(cm->xchg.p, cm->xchg.p, 1, ncclUint8, ncclMax, cm->nccl, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
 // (Re)maps the peers' buffers after they were (re)allocated.  Collective: every rank calls it at the same point (buffer
 // sizes depend on the geometry only).  Any rank that cannot map a peer makes ALL ranks fall back to NCCL collectives.
 int setup_peers(zk_shard_comm* cm)
@@ -404,7 +422,11 @@ int setup_peers(zk_shard_comm* cm)
     unsigned char any = 0;
     CK(cudaMemcpyAsync(&any, st + per * G, 1, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (any) { close_peers(cm); return ZK_OK; }
+    if (any) {   // agreed by all ranks: this communicator stays on NCCL collectives (no retry per proof)
+        close_peers(cm);
+        cm->p2p_wanted = false;
+        return ZK_OK;
+    }
     cm->p2p = true;
     for (int m = 0; m < NM; m++) cm->mapped_for[m] = bases[m];
     return ZK_OK;
@@ -432,6 +454,17 @@ const uint8_t* peer_ptr(zk_shard_comm* cm, int map, uint32_t r, DevBuf RankBufs:
 int ensure_bufs(zk_shard_comm* cm, const Geometry& g, size_t tail_first_len)
 {
     zk_ctx* ctx = cm->ctx;
+    {
+        // the buffers the peers have mapped: if one of them is about to move, un-map everywhere first (every rank sees the
+        // same sizes and the same call history, so all of them take this branch together)
+        const RankBufs& b0 = cm->rk[0];
+        const bool moves = b0.send.bytes < 4 * g.Nloc || b0.layers.bytes < 8 * g.Nloc || b0.heap_f.bytes < 64 * g.Nloc ||
+                           b0.heap_layers.bytes < 128 * g.Nloc;
+        if (moves) {
+            int rc = quiesce_peers(cm);
+            if (rc) return rc;
+        }
+    }
     for (RankBufs& b : cm->rk) {
         CK(b.state.ensure(sizeof(ProofState)));
         CK(b.transcript.ensure(g.trs + 64));
@@ -704,6 +737,7 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
     CK(cudaStreamSynchronize(s));
     if (peer_timeout) {
         cudaMemsetAsync((uint32_t*)cm->flags.p + 16, 0, 4, s);
+        cm->broken = true;
         return fail(ctx, ZK_ERR_COMM, "a rank did not reach a peer-memory barrier within ~15 s");
     }
     for (int p = 0; p + 1 < PH_COUNT; p++) cudaEventElapsedTime(&cm->phase_ms[p], cm->ev[p], cm->ev[p + 1]);
@@ -800,6 +834,7 @@ void zk_shard_comm_destroy(zk_shard_comm* cm)
     if (!cm) return;
     cudaSetDevice(cm->ctx->device);
     cudaStreamSynchronize(cm->ctx->stream);
+    quiesce_peers(cm);      // real ranks with peer mappings: nobody frees what somebody still maps (collective, like ncclCommDestroy)
     close_peers(cm);
     cm->flags.release();
     cm->xchg.release();
