@@ -709,5 +709,16 @@ def extras(args, ctx, zk, line, clocks, world, step_resident):
         line["parity_checked"] = bool(tr_g == otr and st_g == ost)
 
 
+def _only_the_json_line_on_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath print there too (NCCL writes its version banner
+    to stdout from C when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the
+    whole run and Python's sys.stdout keeps the real one: only print() of this script reaches it."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _only_the_json_line_on_stdout()
     main()
