@@ -145,6 +145,25 @@ def test_full_size_program(air_ctx, orc):
     assert zk.verify_air(air, 20, info.a_last, tr, st) == (True, 0)
 
 
+def test_device_trace_generator(orc, monkeypatch):
+    """ZK_TRACE_DEVICE=1 (read at context creation): the traces of a submitted batch come from trace_batch_kernel instead
+    of the host threads -- the reference's program and another one, 37 proofs (a full warp of proofs + a ragged one)."""
+    monkeypatch.setenv("ZK_TRACE_DEVICE", "1")
+    ctx = zk.Context(0)
+    try:
+        log_n, n = 10, 37
+        secrets = (np.arange(n, dtype=np.uint32) * 104729 + 11).astype(np.uint32)
+        for air in (None, AIRS[1]):
+            ctx.set_air(air)
+            ctx.prove_stream_submit(log_n, secrets)
+            trs, sts = ctx.prove_stream_collect(log_n, n)
+            for j in (0, 1, 31, 32, 36):
+                want = orc.prove_air(air, log_n, secret=int(secrets[j])) if air else orc.prove_fibsq(log_n, int(secrets[j]))
+                assert bytes(trs[j]) == want[0] and bytes(sts[j]) == want[1]
+    finally:
+        ctx.close()
+
+
 def test_bad_air(ctx):
     import ctypes as C
     bad = (C.c_uint32 * 8)(1, 1, 1, 0, 0, 0, 0, 2)           # unknown flag

@@ -1043,10 +1043,13 @@ int zk_prove_stream_submit(zk_ctx* ctx, uint32_t log_n, uint32_t n_proofs, const
     sl.log_n = log_n;
     sl.n = n_proofs;
     sl.err = cudaSuccess;
-    if (ctx->trace_on_device && !ctx->air.generic) {   // the device generator knows the reference's recurrence only
+    if (ctx->trace_on_device) {
+        const HostAir& h = ctx->air;
+        const TraceAir ta{h.generic ? 1u : 0u, h.a0, h_to_mont(h.c20), h_to_mont(h.c02), h_to_mont(h.c11), h_to_mont(h.c10),
+                          h_to_mont(h.c01), h_to_mont(h.c00)};
         CK(sl.secrets.ensure(4 * (size_t)n_proofs));
         CK(cudaMemcpyAsync(sl.secrets.p, sl.host_secrets.data(), 4 * (size_t)n_proofs, cudaMemcpyHostToDevice, ctx->trace_stream));
-        CK(launch_trace_batch(ctx->trace_stream, (const uint32_t*)sl.secrets.p, (uint32_t*)sl.traces.p, n, log_n, n_proofs));
+        CK(launch_trace_batch(ctx->trace_stream, (const uint32_t*)sl.secrets.p, (uint32_t*)sl.traces.p, n, log_n, n_proofs, ta));
         CK(cudaEventRecord(sl.ready, ctx->trace_stream));
         ctx->launches += 1;
     } else {

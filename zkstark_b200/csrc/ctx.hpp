@@ -26,7 +26,7 @@ cudaError_t launch_lde_one_coset(cudaStream_t s, const uint32_t* tw_fwd, const u
                                  uint32_t log_n, uint32_t r, const uint32_t* coeffs, uint32_t* work, uint32_t* out,
                                  int* n_launches, const NttPack* pack);
 cudaError_t launch_trace_batch(cudaStream_t s, const uint32_t* secrets_dev, uint32_t* traces, uint64_t stride,
-                               uint32_t log_n, uint32_t batch);
+                               uint32_t log_n, uint32_t batch, const TraceAir& air);
 cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
 double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);

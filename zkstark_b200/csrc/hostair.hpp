@@ -10,4 +10,6 @@ struct HostAir {
     uint32_t a0 = 1, c20 = 1, c02 = 1, c11 = 0, c10 = 0, c01 = 0, c00 = 0;   // canonical residues
     bool generic = false;
 };
+// the same program for the device trace generator (trace.cu): a0 canonical, the coefficients in Montgomery form
+struct TraceAir { uint32_t generic, a0, c20m, c02m, c11m, c10m, c01m, c00m; };
 }  // namespace zk
