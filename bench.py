@@ -653,6 +653,14 @@ def extras(args, ctx, zk, line, clocks, world, step_resident):
     line["roofline"]["share_of_step"] = tree_ms / stages["total"] if stages["total"] else None
     # HBM-bound kernels (north_star target: NTT / fold >= 60 % of the HBM roofline at 2^20)
     rk = {}
+    traffic_rec, traffic_ok = {}, False
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ncu_traffic
+        traffic_rec = json.load(open(os.path.join(ROOT, "zkstark_b200", "ncu_traffic.json")))
+        traffic_ok = traffic_rec.get("source_sha256") == ncu_traffic.source_hash()
+    except Exception:
+        pass
     for name, which, ls, nbytes in [
         ("lde (all passes)", 2, k, 4 * n + 4 * N),
         ("interpolate (all passes)", 3, k, 8 * n),
@@ -668,6 +676,13 @@ def extras(args, ctx, zk, line, clocks, world, step_resident):
         gbs = nbytes / (ms * 1e-3) / 1e9
         rk[name] = {"bound": "hbm", "ms": ms, "algorithmic_bytes": nbytes, "achieved": gbs, "peak": hbm_peak,
                     "unit": "GB/s", "frac": gbs / hbm_peak}
+        # dram__bytes_read + write and lts__t_bytes of the same launches in the committed ncu capture (tools/ncu_traffic.py),
+        # used only while the capture describes the sources being timed
+        t = traffic_rec.get("kernels", {}).get(f"{which}:{ls}") if traffic_ok else None
+        rk[name]["traffic"] = t["dram_bytes"] if t else None
+        rk[name]["l2_bytes"] = t["l2_bytes"] if t else None
+        rk[name]["traffic_source"] = ("zkstark_b200/ncu_traffic.json (ncu, per launch sequence behind an L2 flush; matches the sources)"
+                                      if t else "no capture of the current sources (tools/ncu_traffic.sh)")
     # the transforms are integer-ISSUE bound, not HBM bound (p > 2^31: a butterfly is 10 instructions, 3 of them 64-bit-result
     # multiplications): their roofline is the butterfly rate of the same arithmetic without any memory traffic, measured live
     try:
