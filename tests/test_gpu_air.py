@@ -164,6 +164,18 @@ def test_device_trace_generator(orc, monkeypatch):
         ctx.close()
 
 
+def test_api_mirror(air_ctx, orc):
+    from zkstark_b200 import api
+    air = AIRS[0]
+    proof = api.generate_proof(api.Channel.new(), 9, 17, ctx=air_ctx, air=air)
+    a_last = int(zk.trace_air(air, 9, 17)[-1])
+    proof.verify(9, a_last)
+    assert air_ctx.get_air() == (zk.AIR_FIBSQ, 0)
+    assert (proof.data, proof.state) == orc.prove_air(air, 9, secret=17)[:2]
+    with pytest.raises(zk.ZkError):
+        api.Proof(proof.state, proof.data).verify(9, a_last)          # not a FibonacciSq proof
+
+
 def test_bad_air(ctx):
     import ctypes as C
     bad = (C.c_uint32 * 8)(1, 1, 1, 0, 0, 0, 0, 2)           # unknown flag

@@ -82,14 +82,15 @@ class Channel:
 class Proof:
     """proof.rs:5-13: the final channel state and the bincode transcript."""
 
-    def __init__(self, state, data):
+    def __init__(self, state, data, air=None):
         self.state = state
         self.data = data
+        self.air = air          # the program the proof is about (SURVEY 8(f4)); None: the reference's FibonacciSq
 
     def verify(self, log_n=10, a_last=2338775057):
         """proof.rs:15-149: raises (the reference panics) if any check fails; also replays the channel."""
-        from ._binding import verify_fibsq
-        ok, line = verify_fibsq(log_n, a_last, self.data, self.state, rederive=True)
+        from ._binding import verify_air
+        ok, line = verify_air(self.air, log_n, a_last, self.data, self.state, rederive=True)
         if not ok:
             raise ZkError(-6, f"proof rejected: the assert at proof.rs:{line} fails")
 
@@ -111,10 +112,20 @@ class Proof:
         return 48 + len(self.data)
 
 
-def generate_proof(channel=None, log_n=10, secret=3141592, ctx=None):
-    """prover.rs:9 generalised to n = 2^log_n (the reference hard-codes log_n = 10)."""
+def generate_proof(channel=None, log_n=10, secret=3141592, ctx=None, air=None):
+    """prover.rs:9 generalised to n = 2^log_n (the reference hard-codes log_n = 10) and, with `air` =
+    (a0, c20, c02, c11, c10, c01, c00), to the other programs of the AIR family (zk_ctx_set_air; the context returns to
+    the reference's program afterwards)."""
     channel = channel or Channel.new()
     if channel.state != bytes(32) or channel.data:
         raise ZkError(-1, "generate_proof expects a fresh Channel::new() (channel.rs:12-17)")
-    data, state = (ctx or default_context()).prove_fibsq(log_n, secret)
-    return Proof(state, data)
+    ctx = ctx or default_context()
+    if air is None:
+        data, state = ctx.prove_fibsq(log_n, secret)
+        return Proof(state, data)
+    ctx.set_air(air)
+    try:
+        data, state = ctx.prove_fibsq(log_n, secret)
+    finally:
+        ctx.set_air(None)
+    return Proof(state, data, air)
