@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) shard_max_kernel(MaxPtrs ptrs, uint32_t G
 struct RankBufs {
     uint32_t rank = 0;
     DevBuf state, transcript, y, coeffs, work, send, recv, f_local, layers, heap_f, heap_layers, upper, stage, heads, halo,
-        tail_vals, tail_heaps, cp_tab;
+        tail_vals, tail_heaps, cp_tab, slice;
     uint32_t cp_tab_log_n = 0, cp_tab_lb = 0;   // the geometry cp_tab was built for
 };
 
@@ -208,7 +208,7 @@ struct zk_shard_comm {
     // gathered and re-ordered by one kernel -- with a flag barrier in peer memory in front of each instead of a collective.
     bool p2p_wanted = true;                  // ZK_SHARD_NO_P2P=1: NCCL collectives only
     bool p2p = false;                        // the peers' buffers are mapped (all ranks agree)
-    enum { MAP_SEND = 0, MAP_HEAP_F, MAP_HEAP_L, MAP_LAYERS, MAP_FLAGS, MAP_COUNT };
+    enum { MAP_SEND = 0, MAP_HEAP_F, MAP_HEAP_L, MAP_LAYERS, MAP_Y, MAP_HEADS, MAP_FLAGS, MAP_COUNT };
     void* mapped_for[MAP_COUNT] = {};        // the local buffers the mappings were made for
     uint8_t* peer[MAP_COUNT][8] = {};        // [buffer][rank]: that rank's buffer in this process's address space
     DevBuf flags;                            // [0, 8) barrier flags written by the peers; word 16: time-out flag; word 32: scratch
@@ -382,7 +382,7 @@ int setup_peers(zk_shard_comm* cm)
     RankBufs& b = cm->rk[0];
     CK(cm->flags.ensure(256));
     CK(cm->xchg.ensure(64 * NM * 8 + 64));
-    void* bases[NM] = {b.send.p, b.heap_f.p, b.heap_layers.p, b.layers.p, cm->flags.p};
+    void* bases[NM] = {b.send.p, b.heap_f.p, b.heap_layers.p, b.layers.p, b.slice.p, b.heads.p, cm->flags.p};
     bool same = cm->p2p;
     for (int m = 0; m < NM; m++) same = same && cm->mapped_for[m] == bases[m];
     if (same) return ZK_OK;
@@ -459,7 +459,7 @@ int ensure_bufs(zk_shard_comm* cm, const Geometry& g, size_t tail_first_len)
         // same sizes and the same call history, so all of them take this branch together)
         const RankBufs& b0 = cm->rk[0];
         const bool moves = b0.send.bytes < 4 * g.Nloc || b0.layers.bytes < 8 * g.Nloc || b0.heap_f.bytes < 64 * g.Nloc ||
-                           b0.heap_layers.bytes < 128 * g.Nloc;
+                           b0.heap_layers.bytes < 128 * g.Nloc || b0.slice.bytes < 4 * (g.n / g.G) || b0.heads.bytes < 64 * g.nbl;
         if (moves) {
             int rc = quiesce_peers(cm);
             if (rc) return rc;
@@ -469,6 +469,7 @@ int ensure_bufs(zk_shard_comm* cm, const Geometry& g, size_t tail_first_len)
         CK(b.state.ensure(sizeof(ProofState)));
         CK(b.transcript.ensure(g.trs + 64));
         CK(b.y.ensure(4 * g.n));
+        CK(b.slice.ensure(4 * (g.n / g.G)));       // this rank's 1/G of the trace as uploaded: what the peers pull
         CK(b.coeffs.ensure(4 * g.n));
         CK(b.work.ensure(4 * g.n));
         CK(b.send.ensure(4 * g.Nloc));
@@ -571,11 +572,29 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
         CK(cudaMemsetAsync(b.transcript.p, 0, g.trs + 64, s));
         if ((rc = zk_shard_state_init_dev(ctx, b.state.p, a_first, a_last))) return rc;
         const size_t lo = b.rank * chunk, hi = (lo + chunk < g.n - 1) ? lo + chunk : g.n - 1;
-        CK(cudaMemcpyAsync((uint32_t*)b.y.p + lo, trace + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, s));
-        if (hi - lo < chunk) CK(cudaMemsetAsync((uint32_t*)b.y.p + hi, 0, 4 * (lo + chunk - hi), s));
+        // peer mode: into the slice buffer (y is transformed in place while a slower peer may still be pulling)
+        uint32_t* up = (cm->p2p && g.G > 1) ? (uint32_t*)b.slice.p : (uint32_t*)b.y.p + lo;
+        CK(cudaMemcpyAsync(up, trace + lo, 4 * (hi - lo), cudaMemcpyHostToDevice, s));
+        if (hi - lo < chunk) CK(cudaMemsetAsync(up + (hi - lo), 0, 4 * (lo + chunk - hi), s));
         ys.push_back((uint8_t*)b.y.p);
     }
-    if ((rc = all_gather_inplace(cm, ys, 4 * chunk))) return rc;
+    if (cm->p2p && g.G > 1) {
+        // every rank pulls the other slices straight out of the peers' buffers (NVLink reads at full width) behind a flag
+        // barrier: ~0.07 ms for the 56 MB of a 2^24 trace on 8 GPUs against ~0.2 ms for the NCCL all-gather
+        if ((rc = peer_barrier(cm))) return rc;
+        for (RankBufs& b : cm->rk) {
+            PeerSrc ps{};
+            for (uint32_t r = 0; r < g.G; r++)
+                ps.p[r] = (const uint4*)peer_ptr(cm, zk_shard_comm::MAP_Y, r, &RankBufs::slice);
+            const size_t total = g.n / 4;
+            CK(zk_launch(shard_interleave_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, ps, (uint4*)b.y.p, g.G, 1u,
+                         (uint32_t)(chunk / 4)));
+            ctx->launches++;
+        }
+        cm->comm_bytes += 4 * chunk * (g.G - 1);
+    } else if ((rc = all_gather_inplace(cm, ys, 4 * chunk))) {
+        return rc;
+    }
     for (RankBufs& b : cm->rk)
         if ((rc = zk_interpolate_subgroup_dev(ctx, (uint32_t*)b.y.p, (uint32_t)(g.n - 1), log_n, (uint32_t*)b.coeffs.p))) return rc;
     mark(cm, PH_INTERP);
@@ -630,6 +649,13 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
     }
     mark(cm, PH_UNPACK);
 
+    // heads of the local blocks: what the rank before this one needs for f(g x), f(g^2 x) at the end of ITS blocks.  Produced
+    // in front of the f tree so that, in peer mode, the tree's barrier covers them and the CP kernel reads them in place.
+    for (RankBufs& b : cm->rk) {
+        CK(zk_launch(shard_heads_kernel, dim3((unsigned)((16 * g.nbl + 255) / 256)), dim3(256), 0, s, (const uint32_t*)b.f_local.p,
+                     (uint32_t*)b.heads.p, (uint32_t)g.nbl, g.lb));
+        ctx->launches++;
+    }
     // ---- f tree (prover.rs:81-85), then alpha_0..2 (prover.rs:163-165) on every rank
     for (RankBufs& b : cm->rk)
         if ((rc = zk_shard_merkle_blocks_dev(ctx, (const uint32_t*)b.f_local.p, g.Nloc, g.lb, (uint8_t*)b.heap_f.p))) return rc;
@@ -637,13 +663,13 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
     mark(cm, PH_FTREE);
 
     // ---- Part 2: composition polynomial (prover.rs:101-180), fused into the leaf pass of the block subtrees
-    {
+    const bool halo_in_place = cm->p2p && g.G > 1;   // the next rank's heads are read over NVLink by the CP kernel itself
+    if (halo_in_place) {
+        cm->comm_bytes += 64 * g.nbl;
+    } else {
         std::vector<const uint8_t*> send;
         std::vector<uint8_t*> recv;
         for (RankBufs& b : cm->rk) {
-            CK(zk_launch(shard_heads_kernel, dim3((unsigned)((16 * g.nbl + 255) / 256)), dim3(256), 0, s, (const uint32_t*)b.f_local.p,
-                         (uint32_t*)b.heads.p, (uint32_t)g.nbl, g.lb));
-            ctx->launches++;
             send.push_back((const uint8_t*)b.heads.p);
             recv.push_back((uint8_t*)b.halo.p);
         }
@@ -656,7 +682,9 @@ int prove_sharded(zk_shard_comm* cm, uint32_t log_n, const uint32_t* trace, uint
         if (b.cp_tab.p && (b.cp_tab_log_n != log_n || b.cp_tab_lb != g.lb)) b.cp_tab.release();   // another geometry: rebuild
         b.cp_tab_log_n = log_n;
         b.cp_tab_lb = g.lb;
-        if ((rc = shard_cp_blocks(ctx, (const uint32_t*)b.f_local.p, (const uint32_t*)b.halo.p, roll, g.Nloc, log_n, g.G, b.rank, g.lb,
+        const uint32_t* halo = halo_in_place ? (const uint32_t*)peer_ptr(cm, zk_shard_comm::MAP_HEADS, (b.rank + 1) % g.G, &RankBufs::heads)
+                                             : (const uint32_t*)b.halo.p;
+        if ((rc = shard_cp_blocks(ctx, (const uint32_t*)b.f_local.p, halo, roll, g.Nloc, log_n, g.G, b.rank, g.lb,
                                   b.state.p, (uint32_t*)b.layers.p, (uint8_t*)b.heap_layers.p, &b.cp_tab)))
             return rc;
     }
@@ -841,7 +869,7 @@ void zk_shard_comm_destroy(zk_shard_comm* cm)
     if (cm->nccl && nccl_api()) nccl_api()->CommDestroy(cm->nccl);
     for (RankBufs& b : cm->rk) {
         DevBuf* bufs[] = {&b.state, &b.transcript, &b.y, &b.coeffs, &b.work, &b.send, &b.recv, &b.f_local, &b.layers, &b.heap_f,
-                          &b.heap_layers, &b.upper, &b.stage, &b.heads, &b.halo, &b.tail_vals, &b.tail_heaps, &b.cp_tab};
+                          &b.heap_layers, &b.upper, &b.stage, &b.heads, &b.halo, &b.tail_vals, &b.tail_heaps, &b.cp_tab, &b.slice};
         for (DevBuf* d : bufs) d->release();
     }
     for (int i = 0; i < PH_COUNT; i++) if (cm->ev[i]) cudaEventDestroy(cm->ev[i]);
