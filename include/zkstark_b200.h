@@ -289,7 +289,7 @@ int zk_shard_comm_set(zk_shard_comm *comm, uint32_t log_block, uint32_t log_tail
 int zk_prove_fibsq_sharded(zk_shard_comm *comm, uint32_t log_n, const uint32_t *trace, uint8_t *transcript_out, size_t cap,
                            size_t *len_out, uint8_t state_out[32]);
 /* device time of the last sharded proof by phase, ms: [0] upload + trace all-gather + interpolation, [1] this rank's LDE
- * cosets, [2] all-to-all, [3] unpack, [4] f tree, [5] halo ring, [6] cp + tree, [7] sharded FRI layers, [8] gather +
+ * cosets, [2] all-to-all, [3] unpack, [4] f tree, [5] halo (ring exchange; none in peer mode), [6] cp + tree, [7] sharded FRI layers, [8] gather +
  * replicated FRI tail, [9] decommit + all-reduce, [10] download, [11] total */
 int zk_shard_last_phase_ms(const zk_shard_comm *comm, float out_ms[12]);
 /* bytes this rank received from other ranks during the last sharded proof */
