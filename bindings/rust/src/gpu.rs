@@ -154,6 +154,41 @@ pub fn prove_fibsq_batch(log_n: u32, secrets: &[u32]) -> Vec<(Hash, Vec<u8>)> {
         .collect()
 }
 
+/// The program as data (include/zkstark_b200.h `zk_air`): prove `a[i+2] = c20 a[i+1]^2 + c02 a[i]^2 + c11 a[i] a[i+1] +
+/// c10 a[i+1] + c01 a[i] + c00` from `a[0] = a0, a[1] = secret` instead of the reference's hard-coded FibonacciSq
+/// (prover.rs:32-39, :134-138).  The thread's context proves `air` for the duration of the call only.
+pub fn prove_air(air: &ffi::zk_air, log_n: u32, secret: u32) -> (Hash, Vec<u8>) {
+    with_ctx(|ctx| unsafe { check(ctx, ffi::zk_ctx_set_air(ctx, air)) });
+    struct Reset;
+    impl Drop for Reset {
+        fn drop(&mut self) {
+            with_ctx(|ctx| unsafe {
+                ffi::zk_ctx_set_air(ctx, std::ptr::null());
+            });
+        }
+    }
+    let _reset = Reset;
+    prove_fibsq(log_n, secret)
+}
+
+/// The trace of `air` (host): 2^log_n - 1 values.
+pub fn trace_air(air: &ffi::zk_air, log_n: u32, secret: u32) -> Vec<u32> {
+    let mut out = vec![0u32; (1usize << log_n) - 1];
+    let rc = unsafe { ffi::zk_trace_air(air, log_n, secret, out.as_mut_ptr()) };
+    assert_eq!(rc, 0, "zk_trace_air: bad log_n or zk_air");
+    out
+}
+
+/// proof.rs:15-149 for a proof of `air`, the channel replayed as well; panics like `Proof::verify` with the line of the
+/// failing assert.
+pub fn verify_air(air: &ffi::zk_air, log_n: u32, a_last: u32, state: &Hash, data: &[u8]) {
+    let mut line: c_int = 0;
+    let rc = unsafe {
+        ffi::zk_verify_air(air, log_n, a_last, data.as_ptr(), data.len(), state.as_ptr(), std::ptr::null(), 0, 1, &mut line)
+    };
+    assert_eq!(rc, 0, "proof rejected: the assert at proof.rs:{line} fails");
+}
+
 /// Wire format of `Proof { state, data }` as bincode 1.x writes the struct: state || u64-LE length || data.
 pub fn proof_to_bytes(state: &Hash, data: &[u8]) -> Vec<u8> {
     let cap = unsafe { ffi::zk_proof_serialized_len(data.len()) };
