@@ -281,7 +281,7 @@ int zk_shard_unique_id(uint8_t id_out[ZK_SHARD_ID_BYTES]);
 int zk_shard_comm_init(zk_ctx *ctx, const uint8_t id[ZK_SHARD_ID_BYTES], uint32_t n_ranks, uint32_t rank, zk_shard_comm **out);
 int zk_shard_comm_init_local(zk_ctx *ctx, uint32_t n_virtual_ranks, zk_shard_comm **out);
 void zk_shard_comm_destroy(zk_shard_comm *comm);
-/* tuning: log_block (0 keeps it; default 10), log2 of the largest layer that finishes in the replicated tail
+/* tuning: log_block (0 keeps it; default: 13, or half the rank's share of the evaluations when that is smaller), log2 of the largest layer that finishes in the replicated tail
  * (0xffffffff keeps it; default 18; 0 shards every layer that can be sharded) */
 int zk_shard_comm_set(zk_shard_comm *comm, uint32_t log_block, uint32_t log_tail_len);
 /* trace: HOST memory, 2^log_n - 1 values, identical on every rank (each rank uploads only its 1/n_ranks slice).

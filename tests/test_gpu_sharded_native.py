@@ -87,11 +87,17 @@ def test_native_single_real_rank(ctx, orc):
         comm.close()
 
 
-def test_native_rejects_bad_arguments(ctx):
+def test_native_rejects_bad_arguments(ctx, orc):
     with pytest.raises(zk.ZkError):
         zk.ShardComm.local(ctx, 3)
     comm = zk.ShardComm.local(ctx, 8)
     try:
+        with pytest.raises(zk.ZkError):
+            comm.prove(5, zk.trace_fibsq(5))         # 256 evaluations: not even two blocks of 32 per rank
+        # the smallest proof 8 ranks can share with the default (automatic) block size: two blocks of 32 points each
+        tr6, st6 = comm.prove(6, zk.trace_fibsq(6, 99))
+        assert (tr6, st6) == orc.prove_fibsq(6, 99)[:2]
+        comm.set(log_block=10, log_tail_len=0xFFFFFFFF)
         with pytest.raises(zk.ZkError):
             comm.prove(6, zk.trace_fibsq(6))         # too small for 8 ranks x 2 blocks of 1024
         tr = np.empty(16, dtype=np.uint8)
