@@ -72,3 +72,17 @@ def test_proof_wire_format_round_trip(orc, transcripts):
         zk.Proof.from_bytes(blob[:-1])
     with pytest.raises(zk.ZkError):
         zk.Proof.from_bytes(blob[:20])
+
+
+def test_every_byte_of_the_transcript_is_checked(orc):
+    """Exhaustive: one flipped bit in ANY byte of a small proof is rejected once the channel is replayed (the verifier
+    leaves no byte of the transcript unbound), by the product verifier and the oracle's alike."""
+    log_n = 3
+    tr, st, info = orc.prove_fibsq(log_n, 77)
+    rng = np.random.default_rng(1)
+    for pos in range(len(tr)):
+        bad = bytearray(tr)
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        ok, line = zk.verify_fibsq(log_n, info.a_last, bytes(bad), st, rederive=True)
+        assert not ok and line > 0, pos
+        assert orc.verify_fibsq(log_n, info.a_last, bytes(bad), True, st) != 0, pos
