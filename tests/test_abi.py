@@ -135,9 +135,15 @@ def test_rust_patches_apply(tmp_path):
     assert "pub fn new(mut size: usize, data: impl Iterator<Item = u32>) -> Self" in (work / "src" / "merkle.rs").read_text()
 
 
-def test_trace_batch_simd_matches_scalar(orc):
-    """zk_trace_fibsq_batch (8 traces per SIMD group, several threads) == zk_trace_fibsq == the oracle's trace, incl. a
-    batch that is not a multiple of 8 and secrets 0, 1, p - 1, >= p."""
+@pytest.mark.parametrize("simd", ["", "avx2", "scalar"])
+def test_trace_batch_simd_matches_scalar(orc, simd, monkeypatch):
+    """zk_trace_fibsq_batch (4 or 8 traces per SIMD group -- AVX-512 IFMA, AVX2 or scalar code, ZK_HOST_SIMD caps what the CPU
+    offers -- over several threads) == zk_trace_fibsq == the oracle's trace, incl. a batch that is not a multiple of 8 and
+    secrets 0, 1, p - 1, >= p."""
+    if simd:
+        monkeypatch.setenv("ZK_HOST_SIMD", simd)
+    else:
+        monkeypatch.delenv("ZK_HOST_SIMD", raising=False)
     P = 3221225473
     secrets = np.array([3141592, 0, 1, P - 1, P, P + 7, 0xFFFFFFFF, 12345, 99, 2**31, 2**31 + 1, 7, 8, 9, 10, 11, 12, 13, 14], dtype=np.uint32)
     for log_n in (1, 2, 3, 10, 13):
@@ -145,6 +151,7 @@ def test_trace_batch_simd_matches_scalar(orc):
             got = zk.trace_fibsq_batch(log_n, secrets, threads)
             for j, s in enumerate(secrets.tolist()):
                 assert np.array_equal(got[j], zk.trace_fibsq(log_n, s)), (log_n, j)
+                assert np.array_equal(got[j], orc.trace_fibsq(log_n, s)), (log_n, j)
     assert int(zk.trace_fibsq_batch(10, secrets[:1])[0][1022]) == 2338775057      # prover.rs:42
     import time
     t0 = time.perf_counter()

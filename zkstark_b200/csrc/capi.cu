@@ -887,13 +887,13 @@ int zk_trace_air_batch(const zk_air* air_in, uint32_t log_n, const uint32_t* sec
     const size_t n1 = ((size_t)1 << log_n) - 1;
     uint32_t T = threads ? threads : std::thread::hardware_concurrency();
     if (T < 1) T = 1;
-    const uint32_t gsz = (n_proofs + 7) / 8 >= T ? 8 : 4;
+    const uint32_t gsz = host_trace_group(n_proofs, T, air.generic);
     const uint32_t n_groups = (n_proofs + gsz - 1) / gsz;
     if (T > n_groups) T = n_groups;
     auto body = [&](uint32_t t) {
         for (uint32_t gi = t; gi < n_groups; gi += T) {
             const uint32_t b0 = gsz * gi, cnt = n_proofs - b0 < gsz ? n_proofs - b0 : gsz;
-            uint32_t* rows[8];
+            uint32_t* rows[16];
             for (uint32_t j = 0; j < cnt; j++) rows[j] = out + n1 * (b0 + j);
             host_traces(air, log_n, secrets + b0, rows, cnt);
         }
@@ -993,9 +993,9 @@ static void stream_worker(zk_ctx* ctx, zk_ctx::StreamSlot* sl)
     if (T < 1) T = 1;
     if (T > sl->n) T = sl->n;
     std::vector<cudaError_t> errs(T, cudaSuccess);
-    // a task is a group of 8 proofs (4 when there are more threads than such groups): they advance together as SIMD lanes
-    // (host_traces), then their rows are uploaded
-    const uint32_t gsz = (sl->n + 7) / 8 >= T ? 8 : 4;
+    // a task is a group of 4 or 8 proofs (host_trace_group: what the CPU's vector width and the thread count make
+    // fastest): they advance together as SIMD lanes (host_traces), then their rows are uploaded
+    const uint32_t gsz = host_trace_group(sl->n, T, ctx->air.generic);
     const uint32_t n_groups = (sl->n + gsz - 1) / gsz;
     if (T > n_groups) T = n_groups;
     errs.assign(T, cudaSuccess);
@@ -1003,7 +1003,7 @@ static void stream_worker(zk_ctx* ctx, zk_ctx::StreamSlot* sl)
         cudaSetDevice(ctx->device);
         for (uint32_t gi = t; gi < n_groups; gi += T) {
             const uint32_t b0 = gsz * gi, cnt = sl->n - b0 < gsz ? sl->n - b0 : gsz;
-            uint32_t* rows[8];
+            uint32_t* rows[16];
             for (uint32_t j = 0; j < cnt; j++) rows[j] = (uint32_t*)sl->pinned + n * (b0 + j);
             host_traces(ctx->air, sl->log_n, sl->host_secrets.data() + b0, rows, cnt);
             for (uint32_t j = 0; j < cnt; j++) {

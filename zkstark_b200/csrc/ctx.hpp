@@ -31,6 +31,8 @@ cudaError_t bench_fill(cudaStream_t s, uint32_t* p, size_t n, uint32_t seed);
 cudaError_t bench_flush(cudaStream_t s, void* p, size_t bytes);
 double bench_intpipe(cudaStream_t s, uint32_t* out, int n_sm, int mode);
 void host_traces(const HostAir& air, uint32_t log_n, const uint32_t* secrets, uint32_t* const* rows, uint32_t count);
+uint32_t host_trace_group(uint32_t n, uint32_t threads, bool generic);   // traces per group: 4 or 8
+int host_trace_isa();                                                    // 0 scalar, 1 AVX2, 2 AVX-512 IFMA
 int ntt_pass_times(float ms[4]);
 size_t ntt_table_words();
 cudaError_t ntt2_build_tables(cudaStream_t s, uint32_t* tw_fwd, uint32_t* tw_inv);
